@@ -1,0 +1,210 @@
+/* msst.h -- C ABI of the B200-native MaskedSST hot path (libmsst.so).
+ *
+ * The upstream project (HSG-AIML/MaskedSST) is pure Python/PyTorch: it has no FFI of its own, so the
+ * drop-in boundary is the nn.Module surface of src/vit_spatial_spectral.py / src/vit_simmim_original.py
+ * (mirrored by maskedsst_b200/ and the `src/` alias package).  Below that surface every arithmetic
+ * step is one of the entry points declared here; each cites the reference code (file:line relative to
+ * the upstream repo) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host; fp32 unless stated
+ *   - every function is asynchronous on `stream` (a cudaStream_t passed as void*), never synchronises
+ *     the device, allocates nothing, and is CUDA-graph capturable
+ *   - return value: 0 = ok, otherwise an MSST_ERR_* code; msst_last_error() gives the message
+ *   - token order t = c*S + s (spectral block major), patch vector order (p0 p1 p2), qkv rows q|k|v each
+ *     head-major (h d)  -- reference vit_spatial_spectral.py:198,218,68-69
+ *   - dropout masks are never stored: (seed, site, element index) -> Philox4x32-10; p = 0 disables
+ */
+#ifndef MSST_H_
+#define MSST_H_
+#if defined(__GNUC__)
+#define MSST_API __attribute__((visibility("default")))
+#else
+#define MSST_API
+#endif
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSST_OK 0
+#define MSST_ERR_ARG 1      /* unsupported shape / bad argument */
+#define MSST_ERR_CUDA 2     /* a CUDA runtime call or launch failed */
+
+#define MSST_PREC_FP32 0    /* FFMA everywhere; parity target rel-err <= 1e-5 */
+#define MSST_PREC_BF16 1    /* tcgen05 bf16 operands, fp32 accumulate / residual stream / statistics */
+
+typedef void* msst_stream_t;
+
+MSST_API const char* msst_last_error(void);
+MSST_API int msst_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * (1) fused patch embedding.  Replaces BlockwisePatchEmbedding.to_patch/.embed
+ *     (vit_spatial_spectral.py:197-229), PatchEmbed (:232-253, n_weight_blocks = 1), the pos-embed add
+ *     (:522-528 / vit_simmim_original.py:236-242), emb-dropout (:530) and the SimMIM mask-token
+ *     substitution (vit_simmim_original.py:245-249,285).
+ *       img      [B, C*p0, G*p1, G*p1]  NCHW cube
+ *       pos      [T, D] positional rows (learned table rows [0,T) or the materialised sincos cat)
+ *       mask     [B, T] uint8 or NULL; mask_token [D] or NULL
+ *       tokens   [B, T, D] out
+ *       patches_ln [B,T,P] optional out: pre-norm'ed patches (PatchEmbed SimMIM target, C6), or NULL
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int B, C, G, p0, p1, D;      /* G = spatial patches per side, P = p0*p1*p1, S = G*G, T = C*S */
+    int n_weight_blocks;         /* C for blockwise embedding, 1 for PatchEmbed */
+    float drop_p; uint64_t seed; /* emb-dropout (encoder.forward path only) */
+    const uint64_t* seed_dev;    /* optional device u64 added to seed (fresh masks per CUDA-graph replay); may be NULL */
+} msst_embed_dims;
+
+MSST_API int msst_patch_embed_fwd(const msst_embed_dims* d, const float* img, const float* pre_w, const float* pre_b,
+                         const float* W /*[nb,D,P]*/, const float* bias /*[nb,D]*/, const float* post_w,
+                         const float* post_b, const float* pos, const uint8_t* mask, const float* mask_token,
+                         float* tokens, float* patches_ln, msst_stream_t stream);
+/* grads ACCUMULATE (+=) into d_* (caller zeroes); d_pos [T,D]; d_mask_token may be NULL */
+MSST_API int msst_patch_embed_bwd(const msst_embed_dims* d, const float* img, const float* pre_w, const float* pre_b,
+                         const float* W, const float* bias, const float* post_w, const float* post_b,
+                         const uint8_t* mask, const float* d_tokens, const float* d_patches_ln /*or NULL*/,
+                         float* d_pre_w, float* d_pre_b, float* d_W, float* d_bias, float* d_post_w,
+                         float* d_post_b, float* d_pos, float* d_mask_token, msst_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (4) LayerNorm (nn.LayerNorm, biased variance, eps inside sqrt; PreNorm vit_spatial_spectral.py:22-29)
+ *     stats [rows,2] = (mean, rstd).  y may be fp32 or bf16 (y_bf16 != 0).
+ * ------------------------------------------------------------------------------------------- */
+MSST_API int msst_layernorm_fwd(const float* x, const float* w, const float* b, void* y, int y_bf16, float* stats,
+                       int64_t rows, int D, float eps, msst_stream_t stream);
+/* dx = (accumulate ? dx_add : 0) + LN'(dy); dw/db accumulate */
+MSST_API int msst_layernorm_bwd(const float* x, const float* w, const float* stats, const float* dy, const float* dx_add,
+                       float* dx, float* dw, float* db, int64_t rows, int D, msst_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (2) linear layers.  y = epilogue(x @ W^T).  Replaces nn.Linear call sites to_qkv / to_out / net.0 /
+ *     net.3 (vit_spatial_spectral.py:35-41,59-65) with fused bias, GELU(erf), dropout, residual.
+ *       x [M,K] (ldx), W [N,K], y [M,N] (ldy), residual [M,N] (ldy) or NULL, pre_act [M,N] optional out
+ *     order: t = xW^T + bias; pre_act = t; t = act(t); t = dropout(t); y = t + residual
+ *     prec = MSST_PREC_BF16: x, W, y(pre_act) are bf16 (residual / bias stay fp32; y fp32 if y_fp32 != 0)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t M; int N, K;
+    int act;                       /* 0 none, 1 GELU(erf) */
+    float drop_p; uint64_t seed; uint32_t site;
+    int prec;
+    const uint64_t* seed_dev;
+} msst_linear_dims;
+MSST_API int msst_linear_fwd(const msst_linear_dims* d, const void* x, const void* W, const float* bias,
+                    const float* residual, void* y, void* pre_act, msst_stream_t stream);
+/* dx = epilogue(dy @ W).  With pre_act != NULL the output is multiplied by gelu'(pre_act) and by the hidden
+ * dropout factor of (seed, site) -- i.e. the backward of  g = dropout(gelu(u))  fused into the data-gradient GEMM of
+ * the following layer; then + dx_add (optional).  Output-dropout sites are applied to dy beforehand with
+ * msst_dropout_apply (same (seed, site) => same mask as the forward). */
+MSST_API int msst_linear_bwd_data(const msst_linear_dims* d, const float* dy, const float* W, const float* pre_act,
+                         const float* dx_add, float* dx, msst_stream_t stream);
+/* dW += dy^T x, db += colsum(dy)  (db may be NULL) */
+MSST_API int msst_linear_bwd_weight(const msst_linear_dims* d, const float* dy, const float* x, float* dW, float* db,
+                           msst_stream_t stream);
+
+/* y = x * dropout_factor(seed, site, element index), n % 4 == 0 (inverted dropout, nn.Dropout call sites
+ * vit_spatial_spectral.py:38,40,57,62,391) */
+MSST_API int msst_dropout_apply(const float* x, float* y, int64_t n, float p, uint64_t seed, uint32_t site,
+                                const uint64_t* seed_dev, msst_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (3) fused attention.  softmax(q k^T * dh^-0.5) v per (sequence, head), flash-style (scores never
+ *     reach HBM).  Replaces Attention.forward :69-77.  Rows of sequence s, position i live at
+ *       row = (s / inner) * N * inner + (s % inner) + i * inner
+ *     so the spectral transformer (sequences of C tokens strided by S) needs no transpose copy
+ *     (reference Rearrange copies, vit_spatial_spectral.py:418-430).
+ *       qkv [R, 3*H*dh], out [R, H*dh], lse [R, H]  (R = n_seq * N)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t n_seq; int N, inner, H, dh;
+    float drop_p; uint64_t seed; uint32_t site;
+    int prec;
+    const uint64_t* seed_dev;
+} msst_attn_dims;
+MSST_API int msst_attention_fwd(const msst_attn_dims* d, const void* qkv, void* out, float* lse, msst_stream_t stream);
+MSST_API int msst_attention_bwd(const msst_attn_dims* d, const void* qkv, const void* out, const float* lse,
+                       const void* d_out, void* d_qkv, msst_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Transformer stack: L x { x = attn(LN(x)) + x ; x = ff(LN(x)) + x }  (Transformer.forward :100-104),
+ * all launches of one stack issued from native code.  Parameter pointers per layer, in reference
+ * state_dict order.  workspace holds what backward needs (see msst_transformer_workspace_bytes).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    const float *ln1_w, *ln1_b, *w_qkv, *w_out, *b_out, *ln2_w, *ln2_b, *w1, *b1, *w2, *b2;
+} msst_layer_params;
+typedef struct {
+    float *ln1_w, *ln1_b, *w_qkv, *w_out, *b_out, *ln2_w, *ln2_b, *w1, *b1, *w2, *b2;
+} msst_layer_grads;
+typedef struct {
+    int64_t n_seq; int N, inner;       /* sequence geometry (see attention) */
+    int D, H, dh, M, L;
+    float drop_p; uint64_t seed; uint32_t site_base;
+    int prec;
+    int save_for_backward;             /* 0: inference, workspace only needs scratch */
+    const uint64_t* seed_dev;
+} msst_tf_dims;
+MSST_API int64_t msst_transformer_workspace_bytes(const msst_tf_dims* d);
+MSST_API int msst_transformer_fwd(const msst_tf_dims* d, const msst_layer_params* layers, const float* x_in, float* x_out,
+                         void* workspace, msst_stream_t stream);
+/* d_x_in = grad wrt x_in; parameter grads accumulate. Needs the workspace written by the matching fwd. */
+MSST_API int msst_transformer_bwd(const msst_tf_dims* d, const msst_layer_params* layers, const msst_layer_grads* grads,
+                         const float* x_in, const float* d_x_out, float* d_x_in, void* workspace,
+                         msst_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Classification head: mean over spectral blocks, LN, Linear, 'b h w (p1 p2 nc) -> b nc (h p1)(w p2)'
+ * (vit_spatial_spectral.py:550-562, 481-493).  x [B, C*S, D] -> logits [B, nc, G*p1, G*p1].
+ * ------------------------------------------------------------------------------------------- */
+typedef struct { int B, C, G, p1, D, nc; } msst_head_dims;
+MSST_API int msst_head_fwd(const msst_head_dims* d, const float* x, const float* ln_w, const float* ln_b, const float* W,
+                  const float* bias, float* logits, msst_stream_t stream);
+MSST_API int msst_head_bwd(const msst_head_dims* d, const float* x, const float* ln_w, const float* ln_b, const float* W,
+                  const float* d_logits, float* d_x, float* d_ln_w, float* d_ln_b, float* d_W, float* d_bias,
+                  msst_stream_t stream);
+/* nn.CrossEntropyLoss(ignore_index) over [B,nc,H,W] logits (finetune.py:136): loss_sum_count[0] = sum of
+ * NLL over valid pixels, [1] = number of valid pixels (so data-parallel ranks can all-reduce both, §8(e));
+ * d_logits = softmax - onehot for valid pixels, 0 otherwise (UNSCALED: caller divides by the count). */
+MSST_API int msst_cross_entropy_fwd_bwd(const float* logits, const int64_t* labels, int B, int nc, int HW, int ignore_index,
+                               float* loss_sum_count, float* d_logits, msst_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * SimMIM decoder + masked L1 loss (vit_simmim_original.py:314-338, BlockwiseToPixels :9-40):
+ *   pred[b,n,:] = W[blk] enc[b, idx[b,n], :] + bias[blk],  blk = idx / S (0 when n_weight_blocks == 1)
+ *   target      = raw pixels of patch idx gathered from img (or target_tokens [B,T,P] if not NULL)
+ *   loss        = mean |pred - target| / num_masked          (double normalisation)
+ * idx [B,nm] int64 may disagree with the bool mask and may repeat (C3): backward accumulates.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct { int B, C, G, p0, p1, D, nm, n_weight_blocks; } msst_decode_dims;
+MSST_API int msst_simmim_decode_l1_fwd(const msst_decode_dims* d, const float* enc, const int64_t* idx, const float* img,
+                              const float* target_tokens, const float* W, const float* bias, float* pred /*or NULL*/,
+                              float* partial /*[B*nm] scratch*/, float* loss, msst_stream_t stream);
+/* d_enc [B,T,D] must be zeroed by the caller (scatter-add); d_W/d_bias accumulate; d_loss device scalar */
+MSST_API int msst_simmim_decode_l1_bwd(const msst_decode_dims* d, const float* enc, const int64_t* idx, const float* img,
+                              const float* target_tokens, const float* W, const float* bias, const float* d_loss,
+                              float* d_enc, float* d_W, float* d_bias, float* d_target_tokens /*or NULL*/,
+                              msst_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (5) fused Adam/AdamW over a flat fp32 arena segment (torch.optim.AdamW/Adam as configured by
+ *     src/utils.py:36-44, finetune.py:133-135) with the reference's elementwise grad clamp
+ *     (pretrain.py:71-73) and the data-parallel 1/world scaling folded in.
+ *     step_host = 1-based step number.  bf16_out (optional) receives a bf16 copy of the new params.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    float lr, beta1, beta2, eps, weight_decay;
+    int decoupled;          /* 1 AdamW, 0 Adam with L2 added to the gradient */
+    float clamp;            /* > 0: g = clamp(g, -clamp, clamp) after scaling; <= 0 off */
+    float grad_scale;       /* e.g. 1/world_size */
+    int step;
+} msst_adam_args;
+MSST_API int msst_adam_step(const msst_adam_args* a, float* p, const float* g, float* m, float* v, void* bf16_out, int64_t n,
+                   msst_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSST_H_ */

@@ -1,0 +1,16 @@
+// Error channel + version of the C ABI (include/msst.h).
+#include "common.cuh"
+#include <stdarg.h>
+
+namespace msst {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace msst
+
+extern "C" const char* msst_last_error(void) { return msst::g_err; }
+extern "C" int msst_version(void) { return 100; }

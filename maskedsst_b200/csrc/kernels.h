@@ -1,0 +1,27 @@
+// Internal (C++) launch functions shared between translation units; the public surface is include/msst.h.
+#pragma once
+#include "common.cuh"
+
+namespace msst {
+
+// layernorm.cu
+int layernorm_fwd(const float* x, const float* w, const float* b, void* y, int y_bf16, float* stats, int64_t rows, int D,
+                  float eps, cudaStream_t st);
+int layernorm_bwd(const float* x, const float* w, const float* stats, const float* dy, const float* dx_add, float* dx,
+                  float* dw, float* db, int64_t rows, int D, cudaStream_t st);
+
+// gemm_f32.cu
+int linear_fwd_f32(const float* x, const float* W, const float* bias, const float* residual, float* y, float* pre_act,
+                   int64_t M, int N, int K, int act, Drop drop, cudaStream_t st);
+int linear_bwd_data_f32(const float* dy, const float* W, const float* pre_act, const float* dx_add, float* dx, int64_t M,
+                        int N, int K, Drop drop, cudaStream_t st);
+int linear_bwd_weight_f32(const float* dy, const float* x, float* dW, float* db, int64_t M, int N, int K, cudaStream_t st);
+int colsum_f32(const float* dy, float* db, int64_t M, int N, cudaStream_t st);
+int dropout_apply_f32(const float* x, float* y, int64_t n, Drop drop, cudaStream_t st);
+
+// attention_f32.cu
+int attention_fwd_f32(const msst_attn_dims* d, const float* qkv, float* out, float* lse, cudaStream_t st);
+int attention_bwd_f32(const msst_attn_dims* d, const float* qkv, const float* out, const float* lse, const float* d_out,
+                      float* d_qkv, cudaStream_t st);
+
+}  // namespace msst

@@ -1,0 +1,373 @@
+// Kernel (1): fused gather + LN(P) + per-spectral-block Linear(P->D) + LN(D) + pos-embed add
+// + SimMIM mask-token select + emb-dropout, forward and backward.
+// Reference arithmetic: src/vit_spatial_spectral.py:197-229 (to_patch/embed), :522-530,
+// src/vit_simmim_original.py:236-249,285.  HBM-bound: per token it reads P fp32 pixels and writes D fp32.
+//
+// Work decomposition: one CTA per (sample b, spectral block c, chunk of 64 spatial positions).  With
+// spatial patch size 1 the chunk's pixels are P runs of 64 contiguous floats (256 B each) -> coalesced.
+#include "common.cuh"
+
+namespace msst {
+
+constexpr int kTok = 64;       // tokens per CTA chunk
+constexpr int kThreads = 256;  // 8 warps, 8 tokens each
+
+struct EmbedGeom {
+    int B, C, G, p0, p1, D, P, S, T, HW, Wimg, nb;
+};
+
+__device__ __forceinline__ int64_t pixel_index(const EmbedGeom& g, int b, int c, int s, int p) {
+    // element p = (p0i, p1i, p2i) of the patch at spatial position s = (h, w) of spectral block c
+    if (g.p1 == 1) return ((int64_t)(b * g.C + c) * g.p0 + p) * g.HW + s;
+    const int pp = g.p1 * g.p1;
+    const int p0i = p / pp, r = p % pp, p1i = r / g.p1, p2i = r % g.p1;
+    const int h = s / g.G, w = s % g.G;
+    return ((int64_t)(b * g.C + c) * g.p0 + p0i) * g.HW + (int64_t)(h * g.p1 + p1i) * g.Wimg + (w * g.p1 + p2i);
+}
+
+// loads the chunk's raw patches into xs[tok][P+1] and pre-normalises: xs <- xhat, hs <- xhat*w+b
+__device__ __forceinline__ void load_and_prenorm(const EmbedGeom& g, const float* __restrict__ img, int b, int c, int s0,
+                                                 const float* __restrict__ pre_w, const float* __restrict__ pre_b,
+                                                 float* xs, float* hs, float* rstd_s) {
+    const int P = g.P, ld = P + 1;
+    for (int i = threadIdx.x; i < kTok * P; i += kThreads) {
+        const int tok = i % kTok, p = i / kTok;
+        const int s = s0 + tok;
+        xs[tok * ld + p] = s < g.S ? __ldg(img + pixel_index(g, b, c, s, p)) : 0.f;
+    }
+    __syncthreads();
+    if (threadIdx.x < kTok) {
+        const int tok = threadIdx.x;
+        float mean = 0.f;
+        for (int p = 0; p < P; ++p) mean += xs[tok * ld + p];
+        mean /= P;
+        float var = 0.f;
+        for (int p = 0; p < P; ++p) { const float dlt = xs[tok * ld + p] - mean; var += dlt * dlt; }
+        const float rstd = rsqrtf(var / P + 1e-5f);
+        rstd_s[tok] = rstd;
+        for (int p = 0; p < P; ++p) {
+            const float xh = (xs[tok * ld + p] - mean) * rstd;
+            xs[tok * ld + p] = xh;
+            hs[tok * ld + p] = xh * pre_w[p] + pre_b[p];
+        }
+    }
+    __syncthreads();
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(kThreads)
+patch_embed_fwd_kernel(EmbedGeom g, int n_wb, const float* __restrict__ img, const float* __restrict__ pre_w,
+                       const float* __restrict__ pre_b, const float* __restrict__ W, const float* __restrict__ bias,
+                       const float* __restrict__ post_w, const float* __restrict__ post_b, const float* __restrict__ pos,
+                       const uint8_t* __restrict__ mask, const float* __restrict__ mask_token, float* __restrict__ tokens,
+                       float* __restrict__ patches_ln, Drop drop) {
+    extern __shared__ float smem[];
+    const int P = g.P, ld = P + 1, D = g.D;
+    float* xs = smem;                    // [64][P+1]
+    float* hs = xs + kTok * ld;          // [64][P+1]
+    float* Ws = hs + kTok * ld;          // [D][P+1]
+    float* rstd_s = Ws + D * ld;         // [64]
+    const int chunks = (g.S + kTok - 1) / kTok;
+    const int chunk = blockIdx.x % chunks, c = (blockIdx.x / chunks) % g.C, b = blockIdx.x / (chunks * g.C);
+    const int s0 = chunk * kTok;
+    const int wb = n_wb == 1 ? 0 : c;
+    for (int i = threadIdx.x; i < D * P; i += kThreads) Ws[(i / P) * ld + (i % P)] = __ldg(W + (int64_t)wb * D * P + i);
+    load_and_prenorm(g, img, b, c, s0, pre_w, pre_b, xs, hs, rstd_s);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float bj[NJ], pw[NJ], pb[NJ], mt[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int f = lane + 32 * j;
+        bj[j] = bias[wb * D + f]; pw[j] = post_w[f]; pb[j] = post_b[f];
+        mt[j] = mask_token ? mask_token[f] : 0.f;
+    }
+    for (int k = 0; k < kTok / 8; ++k) {
+        const int tok = warp * (kTok / 8) + k, s = s0 + tok;
+        if (s >= g.S) break;
+        const int t = c * g.S + s;
+        float y[NJ];
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int f = lane + 32 * j;
+            float acc = bj[j];
+            for (int p = 0; p < P; ++p) acc = fmaf(Ws[f * ld + p], hs[tok * ld + p], acc);
+            y[j] = acc; sum += acc;
+        }
+        const float mean = warp_sum(sum) / D;
+        float sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) { const float dlt = y[j] - mean; sq += dlt * dlt; }
+        const float rstd = rsqrtf(warp_sum(sq) / D + 1e-5f);
+        const bool masked = mask && mask[(int64_t)b * g.T + t];
+        const int64_t row = (int64_t)b * g.T + t;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int f = lane + 32 * j;
+            float o = (y[j] - mean) * rstd * pw[j] + pb[j];
+            if (masked) o = mt[j];
+            o += pos[(int64_t)t * D + f];
+            if (drop.on()) o *= drop_factor(drop, (uint64_t)row * D + f);
+            tokens[row * D + f] = o;
+        }
+        if (patches_ln) for (int p = lane; p < P; p += 32) patches_ln[row * P + p] = hs[tok * ld + p];
+    }
+}
+
+// Backward.  grid = (C * chunks, nb): CTA (c, chunk, z) loops over samples b = z, z+nb, ... so the token set
+// it touches is fixed -> d_pos / parameter gradients accumulate in registers, one atomic flush at the end.
+template <int NJ, int PMAX>
+__global__ void __launch_bounds__(kThreads)
+patch_embed_bwd_kernel(EmbedGeom g, int n_wb, const float* __restrict__ img, const float* __restrict__ pre_w,
+                       const float* __restrict__ pre_b, const float* __restrict__ W, const float* __restrict__ bias,
+                       const float* __restrict__ post_w, const float* __restrict__ post_b, const uint8_t* __restrict__ mask,
+                       const float* __restrict__ d_tokens, const float* __restrict__ d_patches_ln, float* __restrict__ d_pre_w,
+                       float* __restrict__ d_pre_b, float* __restrict__ d_W, float* __restrict__ d_bias,
+                       float* __restrict__ d_post_w, float* __restrict__ d_post_b, float* __restrict__ d_pos,
+                       float* __restrict__ d_mask_token, Drop drop) {
+    extern __shared__ float smem[];
+    const int P = g.P, ld = P + 1, D = g.D;
+    float* xs = smem;
+    float* hs = xs + kTok * ld;
+    float* Ws = hs + kTok * ld;
+    float* rstd_s = Ws + D * ld;
+    float* red = rstd_s + kTok;          // [8 warps][D] reduction scratch
+    const int chunks = (g.S + kTok - 1) / kTok;
+    const int chunk = blockIdx.x % chunks, c = blockIdx.x / chunks;
+    const int s0 = chunk * kTok;
+    const int wb = n_wb == 1 ? 0 : c;
+    for (int i = threadIdx.x; i < D * P; i += kThreads) Ws[(i / P) * ld + (i % P)] = __ldg(W + (int64_t)wb * D * P + i);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int TPW = kTok / 8;
+
+    float bj[NJ], pw[NJ];
+    float a_postw[NJ], a_postb[NJ], a_bias[NJ], a_mt[NJ], a_pos[TPW][NJ], a_W[NJ][PMAX];
+    float a_prew[PMAX], a_preb[PMAX];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int f = lane + 32 * j;
+        bj[j] = bias[wb * D + f]; pw[j] = post_w[f];
+        a_postw[j] = a_postb[j] = a_bias[j] = a_mt[j] = 0.f;
+#pragma unroll
+        for (int k = 0; k < TPW; ++k) a_pos[k][j] = 0.f;
+#pragma unroll
+        for (int p = 0; p < PMAX; ++p) a_W[j][p] = 0.f;
+    }
+#pragma unroll
+    for (int p = 0; p < PMAX; ++p) a_prew[p] = a_preb[p] = 0.f;
+
+    for (int b = blockIdx.y; b < g.B; b += gridDim.y) {
+        __syncthreads();
+        load_and_prenorm(g, img, b, c, s0, pre_w, pre_b, xs, hs, rstd_s);
+#pragma unroll
+        for (int k = 0; k < TPW; ++k) {
+            const int tok = warp * TPW + k, s = s0 + tok;
+            if (s >= g.S) continue;
+            const int t = c * g.S + s;
+            const int64_t row = (int64_t)b * g.T + t;
+            float dt[NJ];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int f = lane + 32 * j;
+                dt[j] = d_tokens[row * D + f];
+                if (drop.on()) dt[j] *= drop_factor(drop, (uint64_t)row * D + f);
+                a_pos[k][j] += dt[j];
+            }
+            const bool masked = mask && mask[row];
+            if (masked) {
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) a_mt[j] += dt[j];
+                if (!d_patches_ln) continue;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) dt[j] = 0.f;   // embedding path gets no token gradient
+            }
+            float y[NJ], sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int f = lane + 32 * j;
+                float acc = bj[j];
+                for (int p = 0; p < P; ++p) acc = fmaf(Ws[f * ld + p], hs[tok * ld + p], acc);
+                y[j] = acc; sum += acc;
+            }
+            const float mean = warp_sum(sum) / D;
+            float sq = 0.f;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) { y[j] -= mean; sq += y[j] * y[j]; }
+            const float rstd = rsqrtf(warp_sum(sq) / D + 1e-5f);
+            float c1 = 0.f, c2 = 0.f, dyh[NJ];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                y[j] *= rstd;                         // yhat
+                a_postw[j] += dt[j] * y[j];
+                a_postb[j] += dt[j];
+                dyh[j] = dt[j] * pw[j];
+                c1 += dyh[j]; c2 += dyh[j] * y[j];
+            }
+            c1 = warp_sum(c1) / D; c2 = warp_sum(c2) / D;
+            float dy[NJ];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                dy[j] = rstd * (dyh[j] - c1 - y[j] * c2);
+                a_bias[j] += dy[j];
+            }
+#pragma unroll
+            for (int p = 0; p < PMAX; ++p) {
+                if (p < P) {
+                    const float hv = hs[tok * ld + p];
+                    float dh = 0.f;
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        a_W[j][p] = fmaf(dy[j], hv, a_W[j][p]);
+                        dh = fmaf(Ws[(lane + 32 * j) * ld + p], dy[j], dh);
+                    }
+                    dh = warp_sum(dh);
+                    if (d_patches_ln) dh += d_patches_ln[row * P + p];
+                    a_prew[p] = fmaf(dh, xs[tok * ld + p], a_prew[p]);
+                    a_preb[p] += dh;
+                }
+            }
+        }
+    }
+    // ---- flush: d_pos rows are owned by this warp (other CTAs along y add to the same rows) ----
+#pragma unroll
+    for (int k = 0; k < TPW; ++k) {
+        const int s = s0 + warp * TPW + k;
+        if (s < g.S) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) atomicAdd(d_pos + (int64_t)(c * g.S + s) * D + lane + 32 * j, a_pos[k][j]);
+        }
+    }
+    // cross-warp reduction of the per-feature accumulators through smem, then one atomic per value per CTA
+    auto flush_feat = [&](float (&acc)[NJ], float* dst) {
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) red[warp * D + lane + 32 * j] = acc[j];
+        __syncthreads();
+        for (int f = threadIdx.x; f < D; f += kThreads) {
+            float s = 0.f;
+            for (int w = 0; w < 8; ++w) s += red[w * D + f];
+            atomicAdd(dst + f, s);
+        }
+    };
+    flush_feat(a_postw, d_post_w);
+    flush_feat(a_postb, d_post_b);
+    flush_feat(a_bias, d_bias + wb * D);
+    if (d_mask_token) flush_feat(a_mt, d_mask_token);
+#pragma unroll
+    for (int p = 0; p < PMAX; ++p) {
+        if (p < P) {
+            float col[NJ];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) col[j] = a_W[j][p];
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) red[warp * D + lane + 32 * j] = col[j];
+            __syncthreads();
+            for (int f = threadIdx.x; f < D; f += kThreads) {
+                float s = 0.f;
+                for (int w = 0; w < 8; ++w) s += red[w * D + f];
+                atomicAdd(d_W + ((int64_t)wb * D + f) * P + p, s);
+            }
+        }
+    }
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int p = 0; p < PMAX; ++p) if (p < P) { red[warp * 2 * PMAX + p] = a_prew[p]; red[warp * 2 * PMAX + PMAX + p] = a_preb[p]; }
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < P; p += kThreads) {
+        float sw = 0.f, sb = 0.f;
+        for (int w = 0; w < 8; ++w) { sw += red[w * 2 * PMAX + p]; sb += red[w * 2 * PMAX + PMAX + p]; }
+        atomicAdd(d_pre_w + p, sw);
+        atomicAdd(d_pre_b + p, sb);
+    }
+}
+
+static int make_geom(const msst_embed_dims* d, EmbedGeom& g) {
+    MSST_REQUIRE(d && d->B > 0 && d->C > 0 && d->G > 0 && d->p0 > 0 && d->p1 > 0, "patch_embed: bad dims");
+    MSST_REQUIRE(d->D % 32 == 0 && d->D >= 32 && d->D <= 256, "patch_embed: D=%d must be a multiple of 32 in [32,256]", d->D);
+    MSST_REQUIRE(d->n_weight_blocks == 1 || d->n_weight_blocks == d->C, "patch_embed: n_weight_blocks must be 1 or C");
+    g.B = d->B; g.C = d->C; g.G = d->G; g.p0 = d->p0; g.p1 = d->p1; g.D = d->D;
+    g.P = d->p0 * d->p1 * d->p1; g.S = d->G * d->G; g.T = g.C * g.S;
+    g.Wimg = d->G * d->p1; g.HW = g.Wimg * g.Wimg; g.nb = 1;
+    MSST_REQUIRE(g.P <= 64, "patch_embed: pixels per patch %d > 64 unsupported", g.P);
+    return MSST_OK;
+}
+
+template <int NJ>
+static int launch_fwd(const EmbedGeom& g, int n_wb, size_t smem, cudaStream_t st, const float* img, const float* pre_w,
+                      const float* pre_b, const float* W, const float* bias, const float* post_w, const float* post_b,
+                      const float* pos, const uint8_t* mask, const float* mask_token, float* tokens, float* patches_ln, Drop drop) {
+    const int chunks = (g.S + kTok - 1) / kTok;
+    MSST_CUDA(cudaFuncSetAttribute(patch_embed_fwd_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    patch_embed_fwd_kernel<NJ><<<g.B * g.C * chunks, kThreads, smem, st>>>(g, n_wb, img, pre_w, pre_b, W, bias, post_w, post_b,
+                                                                           pos, mask, mask_token, tokens, patches_ln, drop);
+    MSST_LAUNCH_CHECK();
+    return MSST_OK;
+}
+
+template <int NJ, int PMAX>
+static int launch_bwd(const EmbedGeom& g, int n_wb, size_t smem, cudaStream_t st, const float* img, const float* pre_w,
+                      const float* pre_b, const float* W, const float* bias, const float* post_w, const float* post_b,
+                      const uint8_t* mask, const float* d_tokens, const float* d_pln, float* d_pre_w, float* d_pre_b,
+                      float* d_W, float* d_bias, float* d_post_w, float* d_post_b, float* d_pos, float* d_mt, Drop drop) {
+    const int chunks = (g.S + kTok - 1) / kTok;
+    int nb = (int)ceil_div(2 * kNumSMs, (int64_t)g.C * chunks);
+    nb = nb < 1 ? 1 : (nb > g.B ? g.B : nb);
+    MSST_CUDA(cudaFuncSetAttribute(patch_embed_bwd_kernel<NJ, PMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    patch_embed_bwd_kernel<NJ, PMAX><<<dim3(g.C * chunks, nb), kThreads, smem, st>>>(
+        g, n_wb, img, pre_w, pre_b, W, bias, post_w, post_b, mask, d_tokens, d_pln, d_pre_w, d_pre_b, d_W, d_bias, d_post_w,
+        d_post_b, d_pos, d_mt, drop);
+    MSST_LAUNCH_CHECK();
+    return MSST_OK;
+}
+
+}  // namespace msst
+
+using namespace msst;
+
+extern "C" int msst_patch_embed_fwd(const msst_embed_dims* d, const float* img, const float* pre_w, const float* pre_b,
+                                    const float* W, const float* bias, const float* post_w, const float* post_b,
+                                    const float* pos, const uint8_t* mask, const float* mask_token, float* tokens,
+                                    float* patches_ln, msst_stream_t stream) {
+    EmbedGeom g;
+    if (int rc = make_geom(d, g)) return rc;
+    MSST_REQUIRE(!mask || mask_token, "patch_embed: mask given without mask_token");
+    const size_t smem = sizeof(float) * ((size_t)2 * kTok * (g.P + 1) + (size_t)g.D * (g.P + 1) + kTok);
+    const Drop drop = make_drop(d->drop_p, d->seed, kSiteEmb, d->seed_dev);
+    cudaStream_t st = (cudaStream_t)stream;
+#define MSST_FWD(NJ) return launch_fwd<NJ>(g, d->n_weight_blocks, smem, st, img, pre_w, pre_b, W, bias, post_w, post_b, pos, mask, mask_token, tokens, patches_ln, drop)
+    switch (g.D / 32) {
+        case 1: MSST_FWD(1); case 2: MSST_FWD(2); case 3: MSST_FWD(3); case 4: MSST_FWD(4);
+    }
+#undef MSST_FWD
+    set_error("patch_embed: D=%d unsupported (32,64,96,128)", g.D);
+    return MSST_ERR_ARG;
+}
+
+extern "C" int msst_patch_embed_bwd(const msst_embed_dims* d, const float* img, const float* pre_w, const float* pre_b,
+                                    const float* W, const float* bias, const float* post_w, const float* post_b,
+                                    const uint8_t* mask, const float* d_tokens, const float* d_patches_ln, float* d_pre_w,
+                                    float* d_pre_b, float* d_W, float* d_bias, float* d_post_w, float* d_post_b,
+                                    float* d_pos, float* d_mask_token, msst_stream_t stream) {
+    EmbedGeom g;
+    if (int rc = make_geom(d, g)) return rc;
+    MSST_REQUIRE(g.P <= 16, "patch_embed_bwd: pixels per patch %d > 16 unsupported in backward", g.P);
+    const int pmax = 16;
+    size_t red = (size_t)8 * g.D;
+    if (red < (size_t)8 * 2 * pmax) red = (size_t)8 * 2 * pmax;
+    const size_t smem = sizeof(float) * ((size_t)2 * kTok * (g.P + 1) + (size_t)g.D * (g.P + 1) + kTok + red);
+    const Drop drop = make_drop(d->drop_p, d->seed, kSiteEmb, d->seed_dev);
+    cudaStream_t st = (cudaStream_t)stream;
+#define MSST_BWD(NJ, PM) return launch_bwd<NJ, PM>(g, d->n_weight_blocks, smem, st, img, pre_w, pre_b, W, bias, post_w, post_b, mask, d_tokens, d_patches_ln, d_pre_w, d_pre_b, d_W, d_bias, d_post_w, d_post_b, d_pos, d_mask_token, drop)
+    if (pmax == 16) {
+        switch (g.D / 32) {
+            case 1: MSST_BWD(1, 16); case 2: MSST_BWD(2, 16); case 3: MSST_BWD(3, 16); case 4: MSST_BWD(4, 16);
+        }
+    }
+#undef MSST_BWD
+    set_error("patch_embed_bwd: (D=%d, P=%d) unsupported", g.D, g.P);
+    return MSST_ERR_ARG;
+}

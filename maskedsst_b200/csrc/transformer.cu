@@ -1,0 +1,181 @@
+// Native orchestration of one Transformer stack (L pre-norm layers) -- all launches of the stack are issued
+// from here so the Python host makes one call per stack per direction.
+// Reference: Transformer.forward, src/vit_spatial_spectral.py:100-104 (x = attn(LN(x)) + x ; x = ff(LN(x)) + x),
+// Attention :47-78, FeedForward :32-44; backward = autograd of the same.
+//
+// Workspace (device memory owned by the caller, see msst_transformer_workspace_bytes):
+//   per layer (only layer 0's slot when save_for_backward == 0):
+//     stats1 [R,2] stats2 [R,2] | qkv [R,3I] | o [R,I] | lse [R,H] | xmid [R,D] | u [R,M] | g [R,M] | xout [R,D]
+//   shared scratch: h [R,D]; backward adds dqkv [R,3I], do [R,I], du [R,M], dh [R,D], dy [R,D], dxa [R,D], dxb [R,D]
+// The residual stream, LN statistics and lse are always fp32.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace msst {
+
+static inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+struct TfLayout {
+    int64_t R; int I;
+    size_t o_stats1, o_stats2, o_qkv, o_o, o_lse, o_xmid, o_u, o_g, o_xout, layer_bytes;
+    size_t s_h, s_dqkv, s_do, s_du, s_dh, s_dy, s_dxa, s_dxb, total;
+    int layer_slots;
+};
+
+static TfLayout make_layout(const msst_tf_dims* d) {
+    TfLayout L{};
+    L.R = d->n_seq * d->N; L.I = d->H * d->dh;
+    const size_t R = (size_t)L.R, f = sizeof(float);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
+    L.o_stats1 = take(R * 2 * f); L.o_stats2 = take(R * 2 * f);
+    L.o_qkv = take(R * 3 * L.I * f); L.o_o = take(R * L.I * f); L.o_lse = take(R * d->H * f);
+    L.o_xmid = take(R * d->D * f); L.o_u = take(R * d->M * f); L.o_g = take(R * d->M * f); L.o_xout = take(R * d->D * f);
+    L.layer_bytes = off;
+    L.layer_slots = d->save_for_backward ? d->L : 1;
+    off = L.layer_bytes * L.layer_slots;
+    L.s_h = take(R * d->D * f);
+    if (d->save_for_backward) {
+        L.s_dqkv = take(R * 3 * L.I * f); L.s_do = take(R * L.I * f); L.s_du = take(R * d->M * f);
+        L.s_dh = take(R * d->D * f); L.s_dy = take(R * d->D * f); L.s_dxa = take(R * d->D * f); L.s_dxb = take(R * d->D * f);
+    }
+    L.total = off;
+    return L;
+}
+
+static int check_dims(const msst_tf_dims* d) {
+    MSST_REQUIRE(d && d->n_seq >= 0 && d->N > 0 && d->inner > 0 && d->L > 0, "transformer: bad dims");
+    MSST_REQUIRE(d->D > 0 && d->D <= 256 && d->M > 0 && d->H > 0, "transformer: bad model dims");
+    MSST_REQUIRE(d->D % 4 == 0 && d->M % 4 == 0, "transformer: D and M must be multiples of 4");
+    MSST_REQUIRE(d->prec == MSST_PREC_FP32, "transformer: precision mode %d not built into this library", d->prec);
+    return MSST_OK;
+}
+
+}  // namespace msst
+using namespace msst;
+
+extern "C" int64_t msst_transformer_workspace_bytes(const msst_tf_dims* d) {
+    if (check_dims(d)) return -1;
+    return (int64_t)make_layout(d).total;
+}
+
+extern "C" int msst_transformer_fwd(const msst_tf_dims* d, const msst_layer_params* layers, const float* x_in, float* x_out,
+                                    void* workspace, msst_stream_t stream) {
+    if (int rc = check_dims(d)) return rc;
+    MSST_REQUIRE(layers && x_in && x_out && workspace, "transformer_fwd: null pointer");
+    const TfLayout L = make_layout(d);
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)workspace;
+    const int64_t R = L.R;
+    const int D = d->D, I = L.I, M = d->M;
+    float* h = (float*)(ws + L.s_h);
+    const float* x = x_in;
+    for (int l = 0; l < d->L; ++l) {
+        char* lw = ws + L.layer_bytes * (d->save_for_backward ? l : 0);
+        const msst_layer_params& p = layers[l];
+        float* stats1 = (float*)(lw + L.o_stats1); float* stats2 = (float*)(lw + L.o_stats2);
+        float* qkv = (float*)(lw + L.o_qkv); float* o = (float*)(lw + L.o_o); float* lse = (float*)(lw + L.o_lse);
+        float* xmid = (float*)(lw + L.o_xmid); float* u = (float*)(lw + L.o_u); float* g = (float*)(lw + L.o_g);
+        float* y = (l == d->L - 1) ? x_out : (float*)(lw + L.o_xout);
+        const uint32_t site = d->site_base + 8u * l;
+        const Drop none = make_drop(0.f, 0, 0);
+        if (int rc = layernorm_fwd(x, p.ln1_w, p.ln1_b, h, 0, stats1, R, D, 1e-5f, st)) return rc;
+        if (int rc = linear_fwd_f32(h, p.w_qkv, nullptr, nullptr, qkv, nullptr, R, 3 * I, D, 0, none, st)) return rc;
+        msst_attn_dims ad{d->n_seq, d->N, d->inner, d->H, d->dh, d->drop_p, d->seed, site + kSiteAttnProb, d->prec, d->seed_dev};
+        if (int rc = attention_fwd_f32(&ad, qkv, o, lse, st)) return rc;
+        if (int rc = linear_fwd_f32(o, p.w_out, p.b_out, x, xmid, nullptr, R, D, I, 0, make_drop(d->drop_p, d->seed, site + kSiteAttnOut, d->seed_dev), st)) return rc;
+        if (int rc = layernorm_fwd(xmid, p.ln2_w, p.ln2_b, h, 0, stats2, R, D, 1e-5f, st)) return rc;
+        if (int rc = linear_fwd_f32(h, p.w1, p.b1, nullptr, g, u, R, M, D, 1, make_drop(d->drop_p, d->seed, site + kSiteMlpHidden, d->seed_dev), st)) return rc;
+        if (int rc = linear_fwd_f32(g, p.w2, p.b2, xmid, y, nullptr, R, D, M, 0, make_drop(d->drop_p, d->seed, site + kSiteMlpOut, d->seed_dev), st)) return rc;
+        x = y;
+    }
+    return MSST_OK;
+}
+
+extern "C" int msst_transformer_bwd(const msst_tf_dims* d, const msst_layer_params* layers, const msst_layer_grads* grads,
+                                    const float* x_in, const float* d_x_out, float* d_x_in, void* workspace,
+                                    msst_stream_t stream) {
+    if (int rc = check_dims(d)) return rc;
+    MSST_REQUIRE(d->save_for_backward, "transformer_bwd: forward was not run with save_for_backward");
+    MSST_REQUIRE(layers && grads && x_in && d_x_out && d_x_in && workspace, "transformer_bwd: null pointer");
+    const TfLayout L = make_layout(d);
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)workspace;
+    const int64_t R = L.R;
+    const int D = d->D, I = L.I, M = d->M;
+    float* h = (float*)(ws + L.s_h); float* dqkv = (float*)(ws + L.s_dqkv); float* dO = (float*)(ws + L.s_do);
+    float* du = (float*)(ws + L.s_du); float* dh = (float*)(ws + L.s_dh); float* dyb = (float*)(ws + L.s_dy);
+    float* dxa = (float*)(ws + L.s_dxa); float* dxb = (float*)(ws + L.s_dxb);
+    const float* dcur = d_x_out;
+    const Drop none = make_drop(0.f, 0, 0);
+    for (int l = d->L - 1; l >= 0; --l) {
+        char* lw = ws + L.layer_bytes * l;
+        const msst_layer_params& p = layers[l];
+        const msst_layer_grads& gr = grads[l];
+        float* stats1 = (float*)(lw + L.o_stats1); float* stats2 = (float*)(lw + L.o_stats2);
+        float* qkv = (float*)(lw + L.o_qkv); float* o = (float*)(lw + L.o_o); float* lse = (float*)(lw + L.o_lse);
+        float* xmid = (float*)(lw + L.o_xmid); float* u = (float*)(lw + L.o_u); float* g = (float*)(lw + L.o_g);
+        const float* x = (l == 0) ? x_in : (const float*)(ws + L.layer_bytes * (l - 1) + L.o_xout);
+        const uint32_t site = d->site_base + 8u * l;
+        // ---- MLP branch: y = xmid + drop(W2 g + b2) ----
+        const float* dy = dcur;
+        if (d->drop_p > 0.f) {
+            if (int rc = dropout_apply_f32(dcur, dyb, R * D, make_drop(d->drop_p, d->seed, site + kSiteMlpOut, d->seed_dev), st)) return rc;
+            dy = dyb;
+        }
+        if (int rc = linear_bwd_weight_f32(dy, g, gr.w2, gr.b2, R, D, M, st)) return rc;
+        if (int rc = linear_bwd_data_f32(dy, p.w2, u, nullptr, du, R, D, M, make_drop(d->drop_p, d->seed, site + kSiteMlpHidden, d->seed_dev), st)) return rc;
+        if (int rc = layernorm_fwd(xmid, p.ln2_w, p.ln2_b, h, 0, nullptr, R, D, 1e-5f, st)) return rc;
+        if (int rc = linear_bwd_weight_f32(du, h, gr.w1, gr.b1, R, M, D, st)) return rc;
+        if (int rc = linear_bwd_data_f32(du, p.w1, nullptr, nullptr, dh, R, M, D, none, st)) return rc;
+        if (int rc = layernorm_bwd(xmid, p.ln2_w, stats2, dh, dcur, dxa, gr.ln2_w, gr.ln2_b, R, D, st)) return rc;
+        // ---- attention branch: xmid = x + drop(Wo o + bo) ----
+        dy = dxa;
+        if (d->drop_p > 0.f) {
+            if (int rc = dropout_apply_f32(dxa, dyb, R * D, make_drop(d->drop_p, d->seed, site + kSiteAttnOut, d->seed_dev), st)) return rc;
+            dy = dyb;
+        }
+        if (int rc = linear_bwd_weight_f32(dy, o, gr.w_out, gr.b_out, R, D, I, st)) return rc;
+        if (int rc = linear_bwd_data_f32(dy, p.w_out, nullptr, nullptr, dO, R, D, I, none, st)) return rc;
+        msst_attn_dims ad{d->n_seq, d->N, d->inner, d->H, d->dh, d->drop_p, d->seed, site + kSiteAttnProb, d->prec, d->seed_dev};
+        if (int rc = attention_bwd_f32(&ad, qkv, o, lse, dO, dqkv, st)) return rc;
+        if (int rc = layernorm_fwd(x, p.ln1_w, p.ln1_b, h, 0, nullptr, R, D, 1e-5f, st)) return rc;
+        if (int rc = linear_bwd_weight_f32(dqkv, h, gr.w_qkv, nullptr, R, 3 * I, D, st)) return rc;
+        if (int rc = linear_bwd_data_f32(dqkv, p.w_qkv, nullptr, nullptr, dh, R, 3 * I, D, none, st)) return rc;
+        float* dx = (l == 0) ? d_x_in : dxb;
+        if (int rc = layernorm_bwd(x, p.ln1_w, stats1, dh, dxa, dx, gr.ln1_w, gr.ln1_b, R, D, st)) return rc;
+        dcur = dx;
+    }
+    return MSST_OK;
+}
+
+// ---- stand-alone entry points (unit tests, microbench) ----
+extern "C" int msst_linear_fwd(const msst_linear_dims* d, const void* x, const void* W, const float* bias, const float* residual,
+                               void* y, void* pre_act, msst_stream_t stream) {
+    MSST_REQUIRE(d && d->prec == MSST_PREC_FP32, "linear_fwd: precision mode not built");
+    return linear_fwd_f32((const float*)x, (const float*)W, bias, residual, (float*)y, (float*)pre_act, d->M, d->N, d->K, d->act,
+                          make_drop(d->drop_p, d->seed, d->site, d->seed_dev), (cudaStream_t)stream);
+}
+extern "C" int msst_linear_bwd_data(const msst_linear_dims* d, const float* dy, const float* W, const float* pre_act,
+                                    const float* dx_add, float* dx, msst_stream_t stream) {
+    MSST_REQUIRE(d && d->prec == MSST_PREC_FP32, "linear_bwd_data: precision mode not built");
+    return linear_bwd_data_f32(dy, W, pre_act, dx_add, dx, d->M, d->N, d->K, make_drop(d->drop_p, d->seed, d->site, d->seed_dev), (cudaStream_t)stream);
+}
+extern "C" int msst_linear_bwd_weight(const msst_linear_dims* d, const float* dy, const float* x, float* dW, float* db,
+                                      msst_stream_t stream) {
+    MSST_REQUIRE(d && d->prec == MSST_PREC_FP32, "linear_bwd_weight: precision mode not built");
+    return linear_bwd_weight_f32(dy, x, dW, db, d->M, d->N, d->K, (cudaStream_t)stream);
+}
+extern "C" int msst_attention_fwd(const msst_attn_dims* d, const void* qkv, void* out, float* lse, msst_stream_t stream) {
+    MSST_REQUIRE(d && d->prec == MSST_PREC_FP32, "attention_fwd: precision mode not built");
+    return attention_fwd_f32(d, (const float*)qkv, (float*)out, lse, (cudaStream_t)stream);
+}
+extern "C" int msst_attention_bwd(const msst_attn_dims* d, const void* qkv, const void* out, const float* lse, const void* d_out,
+                                  void* d_qkv, msst_stream_t stream) {
+    MSST_REQUIRE(d && d->prec == MSST_PREC_FP32, "attention_bwd: precision mode not built");
+    return attention_bwd_f32(d, (const float*)qkv, (const float*)out, lse, (const float*)d_out, (float*)d_qkv, (cudaStream_t)stream);
+}
+extern "C" int msst_dropout_apply(const float* x, float* y, int64_t n, float p, uint64_t seed, uint32_t site,
+                                  const uint64_t* seed_dev, msst_stream_t stream) {
+    return dropout_apply_f32(x, y, n, make_drop(p, seed, site, seed_dev), (cudaStream_t)stream);
+}

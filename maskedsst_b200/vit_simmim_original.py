@@ -1,0 +1,135 @@
+"""B200-native SimMIMSpatialSpectral: same surface / state_dict as the reference's src/vit_simmim_original.py
+(:139-340), with mask-token substitution fused into the patch-embedding kernel and gather + to_pixels + L1 fused
+into msst_simmim_decode_l1_*.  Mask generation stays on the host and is bit-compatible with the reference's
+MaskGenerator (numpy global RNG, :343-416), including the mask/index mismatch quirk."""
+import numpy as np
+import torch
+from torch import nn
+
+from . import ops
+from .vit_spatial_spectral import ViTSpatialSpectral, KLinear
+
+
+class BlockwiseToPixels(nn.Module):
+    """One Linear(dim -> pixels_per_patch) per spectral block (reference :9-40); parameter container --
+    the arithmetic runs inside msst_simmim_decode_l1_*."""
+
+    def __init__(self, dim, num_spectral_blocks, pixels_per_patch, precision):
+        super().__init__()
+        self.pixels_per_patch = pixels_per_patch
+        self.layers = nn.ModuleList([nn.Linear(dim, pixels_per_patch) for _ in range(num_spectral_blocks)])
+        if precision == "16-mixed":
+            self.dtype = torch.float16
+        elif precision == "32-true":
+            self.dtype = torch.float32
+
+    def kernel_params(self):
+        return torch.stack([l.weight for l in self.layers]), torch.stack([l.bias for l in self.layers])
+
+
+class MaskGenerator:
+    """Host mask generator, draws from numpy's global RNG in the same order as the reference (:343-416)."""
+
+    def __init__(self, input_size=16, mask_patch_size=4, model_patch_size=1, mask_ratio=0.6):
+        self.input_size, self.mask_patch_size = input_size, mask_patch_size
+        self.model_patch_size, self.mask_ratio = model_patch_size, mask_ratio
+        assert self.input_size % self.mask_patch_size == 0
+        assert self.mask_patch_size % self.model_patch_size == 0
+        self.rand_size = self.input_size // self.mask_patch_size
+        self.scale = self.mask_patch_size // self.model_patch_size
+        self.token_count = self.rand_size ** 2
+        self.mask_count = int(np.ceil(self.token_count * self.mask_ratio))
+
+    def __call__(self):
+        chosen = np.random.permutation(self.token_count)[: self.mask_count]
+        cells = np.zeros(self.token_count, dtype=int)
+        cells[chosen] = 1
+        cells = cells.reshape(self.rand_size, self.rand_size)
+        return cells.repeat(self.scale, axis=0).repeat(self.scale, axis=1)
+
+    def bool_mask_to_indices(self, masked_bool_mask, batch, num_masked, device):
+        """Column ids of the set bits in row-major order, cut into consecutive runs of num_masked -- NOT per row
+        (reference :372-382; rows >= 1 therefore take ids that belong to neighbouring samples, quirk C3)."""
+        m = masked_bool_mask.cpu().numpy() if torch.is_tensor(masked_bool_mask) else np.asarray(masked_bool_mask)
+        cols = np.nonzero(m)[1]
+        if cols.shape[0] < batch * num_masked:
+            raise RuntimeError("mask has fewer set positions than batch * num_masked")
+        idx = cols[: batch * num_masked].reshape(batch, num_masked).astype(np.int64)
+        return torch.from_numpy(idx).to(device)
+
+    def _finish(self, cells, batch_size, num_masked, device):
+        flat = torch.from_numpy(np.ascontiguousarray(cells.reshape(batch_size, -1)).astype(bool))
+        return flat.to(device), self.bool_mask_to_indices(flat, batch_size, num_masked, device)
+
+    def get_batch(self, batch_size, channel_tokens, num_masked, device):
+        cells = np.stack([self() for _ in range(batch_size * channel_tokens)])
+        return self._finish(cells.reshape(batch_size, channel_tokens, *cells.shape[1:]), batch_size, num_masked, device)
+
+    def get_batch_tube_masked(self, batch_size, channel_tokens, num_masked, device):
+        cells = np.stack([self() for _ in range(batch_size)])[:, None].repeat(channel_tokens, axis=1)
+        return self._finish(cells, batch_size, num_masked, device)
+
+
+class SimMIMSpatialSpectral(nn.Module):
+    def __init__(self, *, encoder, masking_ratio=0.5, mask_patch_size=1, tube_masking=False, intermediate_losses=False,
+                 to_pixels_per_spectral_block=False, precision="32-true"):
+        super().__init__()
+        assert masking_ratio > 0 and masking_ratio < 1, "masking ratio must be kept between 0 and 1"
+        if not isinstance(encoder, ViTSpatialSpectral):
+            raise NotImplementedError("maskedsst_b200: SimMIMSpatialSpectral supports ViTSpatialSpectral encoders")
+        if intermediate_losses:
+            raise NotImplementedError("intermediate_losses needs the legacy ViTSpatialSpectral_V1 encoder (not built)")
+        self.masking_ratio = masking_ratio
+        self.mask_patch_size = mask_patch_size
+        self.intermediate_losses = intermediate_losses
+        self.to_pixels_per_spectral_block = to_pixels_per_spectral_block
+        self.tube_masking = tube_masking
+        if self.mask_patch_size != 1:
+            self.mask_generator = MaskGenerator(input_size=encoder.image_size, mask_patch_size=mask_patch_size,
+                                                model_patch_size=encoder.patch_height, mask_ratio=self.masking_ratio)
+        self.encoder = encoder
+        encoder_dim = encoder.dim
+        # reference :181-182 -- with PatchEmbed these are sub-modules and add alias keys to the state_dict
+        self.to_patch = encoder.to_patch_embedding.to_patch
+        self.patch_to_emb = encoder.to_patch_embedding.embed
+        self.pixel_values_per_patch = encoder.pixels_per_patch
+        self.mask_token = nn.Parameter(torch.randn(encoder_dim))
+        if self.to_pixels_per_spectral_block:
+            self.to_pixels = BlockwiseToPixels(encoder_dim, encoder.num_spectral_patches, self.pixel_values_per_patch,
+                                               precision=precision)
+        else:
+            self.to_pixels = nn.Linear(encoder_dim, self.pixel_values_per_patch)
+
+    # ---- masks --------------------------------------------------------------------------------------------
+    def draw_masks(self, batch, device):
+        """(bool mask [B,T], indices [B,nm]) exactly as the reference draws them (:252-282)."""
+        enc = self.encoder
+        num_patches = enc.num_patches
+        num_masked = int(self.masking_ratio * num_patches)
+        if self.mask_patch_size == 1:
+            idx = torch.rand(batch, num_patches, device=device).topk(k=num_masked, dim=-1).indices
+            mask = torch.zeros((batch, num_patches), device=device).scatter_(-1, idx, 1).bool()
+            return mask, idx
+        fn = self.mask_generator.get_batch_tube_masked if self.tube_masking else self.mask_generator.get_batch
+        return fn(batch_size=batch, channel_tokens=enc.num_spectral_patches, num_masked=num_masked, device=device)
+
+    # ---- forward ------------------------------------------------------------------------------------------
+    def forward(self, img, masks=None):
+        """img [B, channels, H, W] -> scalar loss.  `masks` = optional externally supplied
+        (masked_bool_mask [B,T], masked_indices [B,nm]); by default they are drawn like the reference."""
+        enc = self.encoder
+        B = img.shape[0]
+        mask, idx = masks if masks is not None else self.draw_masks(B, img.device)
+        blockwise = enc.blockwise_patch_embed
+        # tokens = where(mask, mask_token + pos, embed(patches) + pos); no emb-dropout on this path (C5)
+        tokens, pln = enc.to_patch_embedding._embed_img(img, pos=enc._pos_rows(), mask_token=self.mask_token, mask=mask,
+                                                        drop_p=0.0, want_ln=not blockwise)
+        encoded = enc.transformer_forward(tokens)
+        if self.to_pixels_per_spectral_block:
+            W, b = self.to_pixels.kernel_params()
+        else:
+            W, b = self.to_pixels.weight[None], self.to_pixels.bias[None]
+        geom = (B, enc.num_spectral_patches, enc.num_spatial_patches_sqrt, enc.patch_depth, enc.patch_height, enc.dim,
+                idx.shape[1])
+        # target: raw pixels (blockwise embedding) or the LayerNormed patches (PatchEmbed), C6
+        return ops.simmim_decode_l1(encoded, idx, img if blockwise else None, None if blockwise else pln, W, b, geom=geom)

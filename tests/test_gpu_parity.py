@@ -1,0 +1,170 @@
+"""GPU parity (fp32 mode): CUDA path through the nn.Module surface / C-ABI vs the CPU oracle and the golden
+vectors generated from the unmodified reference.  Tolerances: logits / loss rel-err <= 1e-5 (north star, fp32 mode);
+gradients <= 1e-4 on per-tensor summaries (they pass through fp32 atomics in a different summation order)."""
+import json
+import numpy as np
+import pytest
+import torch
+
+import maskedsst_b200 as M
+from maskedsst_b200 import ops
+from oracle import maskedsst_oracle as O
+from tests.helpers import gold, rel_l2, grad_rows, check_grad_rows
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 1e-5
+GTOL = 1e-4
+
+
+def make_encoder(spec, dropout=0.0):
+    return M.ViTSpatialSpectral(
+        image_size=spec.image_size, spatial_patch_size=spec.spatial_patch_size, spectral_patch_size=spec.spectral_patch_size,
+        num_classes=spec.num_classes, dim=spec.dim, depth=spec.depth, heads=spec.heads, mlp_dim=spec.mlp_dim,
+        dropout=dropout, emb_dropout=dropout, channels=spec.channels, spectral_pos_embed=spec.spectral_pos_embed,
+        blockwise_patch_embed=spec.blockwise_patch_embed, spectral_pos=spec.pos(), spectral_only=spec.spectral_only)
+
+
+@pytest.mark.parametrize("name,kw,zero_pad,B,seed", [
+    ("houston_encoder", dict(**O.HOUSTON), 2, 2, 5),
+    ("enmap_encoder", dict(**O.ENMAP), 0, 1, 6),
+    ("enmap_encoder_spectralpos", dict(**O.ENMAP, spectral_pos_embed=True), 0, 1, 7),
+    ("houston_encoder_spectral_only", dict(**O.HOUSTON, spectral_only=True), 2, 2, 8),
+])
+def test_encoder_vs_reference_golden(name, kw, zero_pad, B, seed):
+    g = gold(name)
+    spec = O.Spec(**kw)
+    m = make_encoder(spec).eval()
+    m.load_state_dict(O.synthetic_state_dict(spec, seed=seed), strict=True)
+    m = m.to(DEV)
+    x = O.synthetic_cube(spec, B, seed=seed, zero_pad_bands=zero_pad).to(DEV)
+    st = int(g["token_stride"])
+    with torch.no_grad():
+        tok = m.to_patch_embedding(x)
+        feats = m.forward_features(x)
+        logits = m(x)
+    assert rel_l2(tok[:, ::st], g["tokens"]) < TOL
+    assert rel_l2(feats[:, ::st], g["features"]) < TOL
+    assert rel_l2(logits, g["logits"]) < TOL
+    assert logits.shape == g["logits"].shape
+
+
+@pytest.mark.parametrize("B", [1, 7, 32])
+def test_encoder_vs_oracle_batches(B):
+    spec = O.Spec(**O.HOUSTON)
+    sd = O.synthetic_state_dict(spec, seed=21)
+    m = make_encoder(spec).eval()
+    m.load_state_dict(sd)
+    m.to(DEV)
+    x = O.synthetic_cube(spec, B, seed=21, zero_pad_bands=2)
+    with torch.no_grad():
+        got = m(x.to(DEV))
+        want = O.encoder_forward(x, sd, spec)
+    assert rel_l2(got, want) < TOL
+
+
+def test_finetune_ce_step_vs_reference_golden():
+    g = gold("houston_finetune_ce")
+    spec = O.Spec(**O.HOUSTON)
+    m = make_encoder(spec).train()
+    m.load_state_dict(O.synthetic_state_dict(spec, seed=9))
+    m.to(DEV)
+    x = O.synthetic_cube(spec, 3, seed=9).to(DEV)
+    labels = torch.from_numpy(g["labels"]).to(DEV)
+    logits = m(x)
+    loss = M.cross_entropy(logits, labels, ignore_index=-1)
+    loss.backward()
+    assert rel_l2(logits, g["logits"]) < TOL
+    assert abs(loss.item() - float(g["loss"])) < TOL * abs(float(g["loss"]))
+    rows = grad_rows([(k, p.grad) for k, p in m.named_parameters() if p.grad is not None])
+    check_grad_rows(rows, g["grad_names"], g["grad_rows"], tol=GTOL)
+    assert rel_l2(m.mlp_head[1].weight.grad, g["grad_head_w"]) < GTOL
+    assert rel_l2(m.to_patch_embedding.pre_norm.weight.grad, g["grad_pre_norm_w"]) < GTOL
+    # torch's own CE on our logits gives the same loss (the reference's call, finetune.py:136)
+    ref = torch.nn.functional.cross_entropy(logits.detach(), labels, ignore_index=-1)
+    assert abs(ref.item() - loss.item()) < 1e-5 * abs(ref.item())
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("houston_simmim_tube", dict(**O.HOUSTON)),
+    ("enmap_simmim_block", dict(**O.ENMAP)),
+    ("houston_simmim_spectralpos", dict(**O.HOUSTON, spectral_pos_embed=True)),
+    ("houston_simmim_patchembed", dict(**O.HOUSTON, blockwise_patch_embed=False)),
+])
+def test_simmim_step_vs_reference_golden(name, kw):
+    g = gold(name)
+    meta = json.loads(str(g["meta"]))
+    spec = O.Spec(**kw)
+    enc = make_encoder(spec)
+    m = M.SimMIMSpatialSpectral(encoder=enc, masking_ratio=meta["ratio"], mask_patch_size=meta["mask_patch"],
+                                tube_masking=meta["tube"], to_pixels_per_spectral_block=meta["blockwise_decoder"]).train()
+    sd = O.synthetic_state_dict(spec, seed=meta["seed"], simmim=True, blockwise_decoder=meta["blockwise_decoder"])
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith(("to_patch.", "patch_to_emb.")) for k in missing)
+    m.to(DEV)
+    x = O.synthetic_cube(spec, meta["B"], seed=meta["seed"], zero_pad_bands=meta["zero_pad"]).to(DEV)
+    # the module's own host mask generator reproduces the reference's draw bit for bit
+    np.random.seed(meta["seed"])
+    mask, idx = m.draw_masks(meta["B"], DEV)
+    assert np.array_equal(mask.cpu().numpy(), g["mask"]) and np.array_equal(idx.cpu().numpy(), g["idx"])
+    np.random.seed(meta["seed"])
+    loss = m(x)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < TOL * abs(float(g["loss"]))
+    seen, named = set(), []
+    for k, p in m.named_parameters():
+        if id(p) in seen or p.grad is None:
+            continue
+        seen.add(id(p)); named.append((k, p.grad))
+    rows = grad_rows(named)
+    by_name = dict(m.named_parameters(remove_duplicate=False))
+    for k in [str(n) for n in g["grad_names"]]:
+        if k not in rows and k in by_name and by_name[k].grad is not None:
+            rows[k] = grad_rows([(k, by_name[k].grad)])[k]
+    check_grad_rows(rows, g["grad_names"], g["grad_rows"], tol=GTOL)
+    for k in g.files:
+        if k.startswith("grad__"):
+            assert rel_l2(by_name[k[6:]].grad, g[k]) < GTOL, k
+
+
+def test_simmim_external_masks_inconsistent_and_duplicate_indices():
+    """C3: the (bool mask, index) pair may disagree and indices may repeat; backward must accumulate."""
+    spec = O.Spec(**O.HOUSTON)
+    sd = O.synthetic_state_dict(spec, seed=31, simmim=True)
+    m = M.SimMIMSpatialSpectral(encoder=make_encoder(spec), masking_ratio=0.7, mask_patch_size=4, tube_masking=True,
+                                to_pixels_per_spectral_block=True).train()
+    m.load_state_dict(sd)
+    m.to(DEV)
+    B = 2
+    x = O.synthetic_cube(spec, B, seed=31)
+    rng = np.random.Generator(np.random.PCG64(3))
+    mask = torch.from_numpy(rng.random((B, spec.T)) < 0.6)
+    idx = torch.from_numpy(rng.integers(0, spec.T, (B, 100)).astype(np.int64))   # random, with repeats
+    idx[:, 1] = idx[:, 0]
+    loss = m(x.to(DEV), masks=(mask.to(DEV), idx.to(DEV)))
+    loss.backward()
+    p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    want = O.simmim_forward(x, p, spec, mask, idx)
+    want.backward()
+    assert abs(loss.item() - want.item()) < TOL * abs(want.item())
+    for k, v in m.named_parameters():
+        if p[k].grad is None:
+            continue
+        assert rel_l2(v.grad, p[k].grad) < GTOL or float(p[k].grad.norm()) < 1e-9, k
+
+
+def test_state_dict_roundtrip_and_load_checkpoint_semantics(tmp_path):
+    """Appendix B: pretrain checkpoint -> strip 'encoder.' -> swap head -> strict load (src/utils.py:276-313)."""
+    from src.utils import load_checkpoint, Dotdict
+    spec = O.Spec(**O.HOUSTON)
+    sd = O.synthetic_state_dict(spec, seed=41, simmim=True)
+    path = tmp_path / "pretrain.pth"
+    torch.save({"config": Dotdict({"a": 1}), "model_state_dict": sd, "lr_current": 0.008}, path)
+    enc = make_encoder(O.Spec(**O.HOUSTON, num_classes=11))
+    head_w = enc.mlp_head[1].weight.detach().clone()
+    cfg = Dotdict({"checkpoint_path": str(path), "patch_sub": 0, "image_size": 8})
+    load_checkpoint(cfg, enc, "mlp_head", "cpu")
+    assert torch.equal(enc.mlp_head[1].weight, head_w)           # fresh head kept
+    assert torch.equal(enc.pos_embedding, sd["encoder.pos_embedding"])
+    k = "spatial_spectral_transformer.3.layers.2.0.fn.to_qkv.weight"
+    assert torch.equal(enc.state_dict()[k], sd["encoder." + k])
