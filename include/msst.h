@@ -39,6 +39,8 @@ typedef void* msst_stream_t;
 
 MSST_API const char* msst_last_error(void);
 MSST_API int msst_version(void);
+/* number of kernels this library has launched in this process (bench.py reports it as gpu_launches) */
+MSST_API long long msst_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * (1) fused patch embedding.  Replaces BlockwisePatchEmbedding.to_patch/.embed

@@ -56,6 +56,7 @@ class AdamArgs(C.Structure):
 SIGNATURES = {
     "msst_last_error": (C.c_char_p, []),
     "msst_version": (C.c_int, []),
+    "msst_launch_count": (C.c_longlong, []),
     "msst_patch_embed_fwd": (C.c_int, [C.POINTER(EmbedDims)] + [vp] * 12 + [vp]),
     "msst_patch_embed_bwd": (C.c_int, [C.POINTER(EmbedDims)] + [vp] * 18 + [vp]),
     "msst_layernorm_fwd": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, C.c_int64, C.c_int, C.c_float, vp]),
@@ -85,9 +86,8 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from . import build as _build
-        _build.build()
+    from . import build as _build
+    _build.build()   # no-op when the in-tree library is up to date (source digest) or nvcc is absent
     try:
         L = C.CDLL(LIB_PATH)
     except OSError as e:   # fail loudly: there is no CPU / eager fallback

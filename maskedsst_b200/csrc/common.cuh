@@ -21,7 +21,8 @@ inline int cuda_fail(cudaError_t e, const char* what, const char* file, int line
         cudaError_t e__ = (call);                                              \
         if (e__ != cudaSuccess) return ::msst::cuda_fail(e__, #call, __FILE__, __LINE__); \
     } while (0)
-#define MSST_LAUNCH_CHECK() MSST_CUDA(cudaPeekAtLastError())
+void count_launch();
+#define MSST_LAUNCH_CHECK() do { ::msst::count_launch(); MSST_CUDA(cudaPeekAtLastError()); } while (0)
 #define MSST_REQUIRE(cond, ...)                                                \
     do {                                                                       \
         if (!(cond)) { ::msst::set_error(__VA_ARGS__); return MSST_ERR_ARG; }  \

@@ -111,13 +111,12 @@ class TransformerStackFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, cfg, *params):
-        n_seq, N, inner, H, dh, M, L, drop_p, seed, site_base, prec = cfg
+        n_seq, N, inner, H, dh, M, L, drop_p, seed, site_base, prec, need_grad = cfg
         _chk(x, "x")
         for t in params:
             _chk(t, "transformer parameter")
         R, D = x.shape
         assert R == n_seq * N, (R, n_seq, N)
-        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
         dims = _lib.TfDims(n_seq, N, inner, D, H, dh, M, L, float(drop_p), seed, site_base, prec, int(need_grad), None)
         nbytes = _lib.lib().msst_transformer_workspace_bytes(C.byref(dims))
         if nbytes < 0:
@@ -150,7 +149,9 @@ def transformer_stack(x, layer_params, *, n_seq, N, inner, heads, dim_head, mlp_
                       prec=PREC_FP32):
     """layer_params: list (per layer) of the 11 tensors in _LAYER_FIELDS order."""
     flat = [t for lp in layer_params for t in lp]
-    cfg = (n_seq, N, inner, heads, dim_head, mlp_dim, len(layer_params), drop_p, seed, site_base, prec)
+    # Function.forward runs with grad mode off, so decide here whether activations must be kept for backward
+    need_grad = torch.is_grad_enabled() and (x.requires_grad or any(t.requires_grad for t in flat))
+    cfg = (n_seq, N, inner, heads, dim_head, mlp_dim, len(layer_params), drop_p, seed, site_base, prec, need_grad)
     return TransformerStackFn.apply(x, cfg, *flat)
 
 

@@ -122,8 +122,9 @@ class SimMIMSpatialSpectral(nn.Module):
         mask, idx = masks if masks is not None else self.draw_masks(B, img.device)
         blockwise = enc.blockwise_patch_embed
         # tokens = where(mask, mask_token + pos, embed(patches) + pos); no emb-dropout on this path (C5)
-        tokens, pln = enc.to_patch_embedding._embed_img(img, pos=enc._pos_rows(), mask_token=self.mask_token, mask=mask,
-                                                        drop_p=0.0, want_ln=not blockwise)
+        out = enc.to_patch_embedding._embed_img(img, pos=enc._pos_rows(), mask_token=self.mask_token, mask=mask,
+                                                drop_p=0.0, want_ln=not blockwise)
+        tokens, pln = (out, None) if blockwise else out
         encoded = enc.transformer_forward(tokens)
         if self.to_pixels_per_spectral_block:
             W, b = self.to_pixels.kernel_params()

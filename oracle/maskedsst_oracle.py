@@ -234,44 +234,45 @@ def gelu_erf(x):
     return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
 
 
-def attention(x, sd, base: str, heads: int, dim_head: int):
-    """Attention.forward (vit_spatial_spectral.py:67-78), dropout off. x [n,N,D]."""
+def attention(x, sd, base: str, heads: int, dim_head: int, drop: float = 0.0):
+    """Attention.forward (vit_spatial_spectral.py:67-78). x [n,N,D].  drop > 0 = training-mode dropout on the
+    probabilities (:74) and the output projection (:62), only used by the CPU-baseline timing leg."""
     n, N, D = x.shape
     qkv = x @ sd[base + "to_qkv.weight"].T
     q, k, v = qkv.split(heads * dim_head, dim=-1)
     sh = lambda t: t.reshape(n, N, heads, dim_head).permute(0, 2, 1, 3)
     q, k, v = sh(q), sh(k), sh(v)
     dots = (q @ k.transpose(-1, -2)) * dim_head ** -0.5
-    p = torch.softmax(dots, dim=-1)
+    p = F.dropout(torch.softmax(dots, dim=-1), drop)
     o = (p @ v).permute(0, 2, 1, 3).reshape(n, N, heads * dim_head)
-    return o @ sd[base + "to_out.0.weight"].T + sd[base + "to_out.0.bias"]
+    return F.dropout(o @ sd[base + "to_out.0.weight"].T + sd[base + "to_out.0.bias"], drop)
 
 
-def transformer(x, sd, base: str, spec: Spec):
+def transformer(x, sd, base: str, spec: Spec, drop: float = 0.0):
     """Transformer.forward (vit_spatial_spectral.py:100-104): pre-norm attn + pre-norm MLP, no final norm."""
     for l in range(spec.depth):
         b = base + f"layers.{l}."
         h = _ln(x, sd[b + "0.norm.weight"], sd[b + "0.norm.bias"])
-        x = attention(h, sd, b + "0.fn.", spec.heads, spec.dim_head) + x
+        x = attention(h, sd, b + "0.fn.", spec.heads, spec.dim_head, drop) + x
         h = _ln(x, sd[b + "1.norm.weight"], sd[b + "1.norm.bias"])
-        u = gelu_erf(h @ sd[b + "1.fn.net.0.weight"].T + sd[b + "1.fn.net.0.bias"])
-        x = u @ sd[b + "1.fn.net.3.weight"].T + sd[b + "1.fn.net.3.bias"] + x
+        u = F.dropout(gelu_erf(h @ sd[b + "1.fn.net.0.weight"].T + sd[b + "1.fn.net.0.bias"]), drop)
+        x = F.dropout(u @ sd[b + "1.fn.net.3.weight"].T + sd[b + "1.fn.net.3.bias"], drop) + x
     return x
 
 
-def transformer_forward(tokens, sd, spec: Spec, pre: str = ""):
+def transformer_forward(tokens, sd, spec: Spec, pre: str = "", drop: float = 0.0):
     """spatial_spectral_transformer (vit_spatial_spectral.py:393-431). tokens [B,T,D], t = c*S + s."""
     B = tokens.shape[0]
     C, S, D = spec.C, spec.S, spec.dim
     base = pre + "spatial_spectral_transformer."
     x = tokens
     if not spec.spectral_only:
-        x = transformer(x.reshape(B * C, S, D), sd, base + "1.", spec)
+        x = transformer(x.reshape(B * C, S, D), sd, base + "1.", spec, drop)
         x = x.reshape(B, C, S, D).permute(0, 2, 1, 3).reshape(B * S, C, D)
-        x = transformer(x, sd, base + "3.", spec)
+        x = transformer(x, sd, base + "3.", spec, drop)
     else:
         x = x.reshape(B, C, S, D).permute(0, 2, 1, 3).reshape(B * S, C, D)
-        x = transformer(x, sd, base + "1.", spec)
+        x = transformer(x, sd, base + "1.", spec, drop)
     return x.reshape(B, S, C, D).permute(0, 2, 1, 3).reshape(B, spec.T, D)
 
 
@@ -299,7 +300,7 @@ def encoder_forward(img, sd, spec: Spec, pre: str = ""):
 
 
 def simmim_forward(img, sd, spec: Spec, bool_mask: torch.Tensor, idx: torch.Tensor,
-                   blockwise_decoder: bool = True, return_parts: bool = False):
+                   blockwise_decoder: bool = True, return_parts: bool = False, drop: float = 0.0):
     """SimMIMSpatialSpectral.forward (vit_simmim_original.py:203-340) with the mask pair supplied
     from outside (the pair may be mutually inconsistent).  Dropout off; the SimMIM
     path never applies emb-dropout (C5).  loss = mean|pred-target| / num_masked (C4)."""
@@ -316,7 +317,7 @@ def simmim_forward(img, sd, spec: Spec, bool_mask: torch.Tensor, idx: torch.Tens
     tokens = tokens + pos
     mask_tokens = sd["mask_token"][None, None, :] + pos
     tokens = torch.where(bool_mask[..., None], mask_tokens, tokens)
-    enc = transformer_forward(tokens, sd, spec, pre)
+    enc = transformer_forward(tokens, sd, spec, pre, drop)
     nm = idx.shape[1]
     br = torch.arange(B)[:, None]
     sel = enc[br, idx]                                              # [B,nm,D]

@@ -151,20 +151,3 @@ def test_simmim_external_masks_inconsistent_and_duplicate_indices():
         if p[k].grad is None:
             continue
         assert rel_l2(v.grad, p[k].grad) < GTOL or float(p[k].grad.norm()) < 1e-9, k
-
-
-def test_state_dict_roundtrip_and_load_checkpoint_semantics(tmp_path):
-    """Appendix B: pretrain checkpoint -> strip 'encoder.' -> swap head -> strict load (src/utils.py:276-313)."""
-    from src.utils import load_checkpoint, Dotdict
-    spec = O.Spec(**O.HOUSTON)
-    sd = O.synthetic_state_dict(spec, seed=41, simmim=True)
-    path = tmp_path / "pretrain.pth"
-    torch.save({"config": Dotdict({"a": 1}), "model_state_dict": sd, "lr_current": 0.008}, path)
-    enc = make_encoder(O.Spec(**O.HOUSTON, num_classes=11))
-    head_w = enc.mlp_head[1].weight.detach().clone()
-    cfg = Dotdict({"checkpoint_path": str(path), "patch_sub": 0, "image_size": 8})
-    load_checkpoint(cfg, enc, "mlp_head", "cpu")
-    assert torch.equal(enc.mlp_head[1].weight, head_w)           # fresh head kept
-    assert torch.equal(enc.pos_embedding, sd["encoder.pos_embedding"])
-    k = "spatial_spectral_transformer.3.layers.2.0.fn.to_qkv.weight"
-    assert torch.equal(enc.state_dict()[k], sd["encoder." + k])

@@ -1,0 +1,85 @@
+"""CPU: host-side logic of the drop-in surface -- state_dict layout, checkpoint loading semantics, mask generator
+bit-compatibility with the reference, init parity with torch.manual_seed."""
+import json
+import numpy as np
+import torch
+
+import maskedsst_b200 as M
+from oracle import maskedsst_oracle as O
+from tests.helpers import gold
+
+
+def make_encoder(spec, dropout=0.0):
+    return M.ViTSpatialSpectral(
+        image_size=spec.image_size, spatial_patch_size=spec.spatial_patch_size, spectral_patch_size=spec.spectral_patch_size,
+        num_classes=spec.num_classes, dim=spec.dim, depth=spec.depth, heads=spec.heads, mlp_dim=spec.mlp_dim,
+        dropout=dropout, emb_dropout=dropout, channels=spec.channels, spectral_pos_embed=spec.spectral_pos_embed,
+        blockwise_patch_embed=spec.blockwise_patch_embed, spectral_pos=spec.pos(), spectral_only=spec.spectral_only)
+
+
+def test_state_dict_roundtrip_and_load_checkpoint_semantics(tmp_path):
+    """Appendix B: pretrain checkpoint -> strip 'encoder.' -> swap head -> strict load (src/utils.py:276-313)."""
+    from src.utils import load_checkpoint, Dotdict
+    spec = O.Spec(**O.HOUSTON)
+    sd = O.synthetic_state_dict(spec, seed=41, simmim=True)
+    path = tmp_path / "pretrain.pth"
+    torch.save({"config": Dotdict({"a": 1}), "model_state_dict": sd, "lr_current": 0.008}, path)
+    enc = make_encoder(O.Spec(channels=50, num_classes=11))
+    head_w = enc.mlp_head[1].weight.detach().clone()
+    cfg = Dotdict({"checkpoint_path": str(path), "patch_sub": 0, "image_size": 8})
+    load_checkpoint(cfg, enc, "mlp_head", "cpu")
+    assert torch.equal(enc.mlp_head[1].weight, head_w)           # fresh head kept
+    assert torch.equal(enc.pos_embedding, sd["encoder.pos_embedding"])
+    k = "spatial_spectral_transformer.3.layers.2.0.fn.to_qkv.weight"
+    assert torch.equal(enc.state_dict()[k], sd["encoder." + k])
+
+
+def test_state_dict_layout_matches_reference_keys():
+    for kw, simmim, bd in [(dict(**O.HOUSTON), False, True), (dict(**O.ENMAP), True, True),
+                           (dict(**O.ENMAP, spectral_pos_embed=True), True, True),
+                           (dict(**O.HOUSTON, spectral_only=True), False, True),
+                           (dict(**O.HOUSTON, blockwise_patch_embed=False), True, False)]:
+        spec = O.Spec(**kw)
+        m = make_encoder(spec)
+        if simmim:
+            m = M.SimMIMSpatialSpectral(encoder=m, masking_ratio=0.7, mask_patch_size=4, tube_masking=True,
+                                        to_pixels_per_spectral_block=bd)
+        ours = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        lay = dict(O.state_dict_layout(spec, simmim, bd))
+        extra = set(ours) - set(lay)
+        assert set(lay) <= set(ours) and all(ours[k] == s for k, s in lay.items())
+        assert all(k.startswith(("to_patch.", "patch_to_emb.")) for k in extra)   # PatchEmbed alias keys (Appendix B)
+    assert sum(p.numel() for p in make_encoder(O.Spec(**O.ENMAP)).parameters()) == 1_821_564   # notebook cell 8
+
+
+def test_mask_generator_bit_compatible_with_reference():
+    g = gold("maskgen")
+    for k in g.files:
+        if not k.startswith("mask__"):
+            continue
+        tag = k[6:]
+        f = dict((t[0], t[1:]) for t in tag.split("_"))
+        seed, B, C, tube, ratio, mps, img = int(f["s"]), int(f["B"]), int(f["C"]), bool(int(f["t"])), float(f["r"]), int(f["m"]), int(f["i"])
+        gen = M.MaskGenerator(input_size=img, mask_patch_size=mps, model_patch_size=1, mask_ratio=ratio)
+        np.random.seed(seed)
+        fn = gen.get_batch_tube_masked if tube else gen.get_batch
+        mask, idx = fn(batch_size=B, channel_tokens=C, num_masked=int(ratio * C * img * img), device="cpu")
+        assert mask.dtype == torch.bool and idx.dtype == torch.int64
+        assert np.array_equal(mask.numpy(), g["mask__" + tag]) and np.array_equal(idx.numpy(), g["idx__" + tag])
+
+
+def test_sincos_tables_match_reference():
+    from src.pos_embed import get_2d_sincos_pos_embed, get_1d_sincos_pos_embed_from_grid
+    g = gold("sincos")
+    assert np.allclose(get_2d_sincos_pos_embed(64, 8), g["pos2d_64_8"], atol=1e-12)
+    assert np.allclose(get_1d_sincos_pos_embed_from_grid(32, np.array([0, 3, 4, 9, 17])), g["pos1d_32_odd"], atol=1e-12)
+    enc = make_encoder(O.Spec(**O.ENMAP, spectral_pos_embed=True))
+    assert np.allclose(enc.pos_embed[0].detach().numpy(), g["pos2d_64_8"].astype(np.float32))
+    assert np.allclose(enc.channel_embed[0].detach().numpy(), g["pos1d_32_20"].astype(np.float32))
+
+
+def test_reference_import_paths():
+    from src.vit_spatial_spectral import ViTSpatialSpectral, get_pos_for_spectral_embedding, MoveAxis
+    from src.vit_simmim_original import SimMIMSpatialSpectral
+    assert ViTSpatialSpectral is M.ViTSpatialSpectral and SimMIMSpatialSpectral is M.SimMIMSpatialSpectral
+    assert get_pos_for_spectral_embedding(10, list(range(400, 600)), list(range(400, 1000)))[:3] == [0, 1, 2]
