@@ -289,7 +289,7 @@ def roofline(args, B, dev, model, peaks):
     x = torch.randn(R, D, device=dev).to(dt)
     W = (torch.randn(N, D, device=dev) / 10).to(dt)
     y = torch.empty(R, N, device=dev, dtype=dt)
-    dims = _lib.LinearDims(R, N, D, 0, 0.0, 0, 0, prec, None)
+    dims = _lib.LinearDims(R, N, D, 0, 0.0, 0, 0, prec, None, 0)
     st = torch.cuda.current_stream().cuda_stream
     lib = _lib.lib()
     try:

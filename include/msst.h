@@ -86,7 +86,9 @@ MSST_API int msst_layernorm_bwd(const float* x, const float* w, const float* sta
  *     net.3 (vit_spatial_spectral.py:35-41,59-65) with fused bias, GELU(erf), dropout, residual.
  *       x [M,K] (ldx), W [N,K], y [M,N] (ldy), residual [M,N] (ldy) or NULL, pre_act [M,N] optional out
  *     order: t = xW^T + bias; pre_act = t; t = act(t); t = dropout(t); y = t + residual
- *     prec = MSST_PREC_BF16: x, W, y(pre_act) are bf16 (residual / bias stay fp32; y fp32 if y_fp32 != 0)
+ *     prec = MSST_PREC_BF16 (tcgen05 path): x, W, pre_act are bf16; bias / residual fp32; y bf16 or fp32 (y_fp32);
+ *     K % 8 == 0.  In that mode msst_linear_bwd_data takes dy bf16, W = the TRANSPOSED bf16 copy W^T [K,N], pre_act bf16,
+ *     dx bf16/fp32 (y_fp32); msst_linear_bwd_weight takes dy, x bf16 and accumulates fp32 dW (db must be NULL).
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
     int64_t M; int N, K;
@@ -94,6 +96,7 @@ typedef struct {
     float drop_p; uint64_t seed; uint32_t site;
     int prec;
     const uint64_t* seed_dev;
+    int y_fp32;                    /* BF16 mode only: 1 = the output (y / dx) is fp32, 0 = bf16 */
 } msst_linear_dims;
 MSST_API int msst_linear_fwd(const msst_linear_dims* d, const void* x, const void* W, const float* bias,
                     const float* residual, void* y, void* pre_act, msst_stream_t stream);
@@ -101,10 +104,10 @@ MSST_API int msst_linear_fwd(const msst_linear_dims* d, const void* x, const voi
  * dropout factor of (seed, site) -- i.e. the backward of  g = dropout(gelu(u))  fused into the data-gradient GEMM of
  * the following layer; then + dx_add (optional).  Output-dropout sites are applied to dy beforehand with
  * msst_dropout_apply (same (seed, site) => same mask as the forward). */
-MSST_API int msst_linear_bwd_data(const msst_linear_dims* d, const float* dy, const float* W, const float* pre_act,
-                         const float* dx_add, float* dx, msst_stream_t stream);
+MSST_API int msst_linear_bwd_data(const msst_linear_dims* d, const void* dy, const void* W, const void* pre_act,
+                         const float* dx_add, void* dx, msst_stream_t stream);
 /* dW += dy^T x, db += colsum(dy)  (db may be NULL) */
-MSST_API int msst_linear_bwd_weight(const msst_linear_dims* d, const float* dy, const float* x, float* dW, float* db,
+MSST_API int msst_linear_bwd_weight(const msst_linear_dims* d, const void* dy, const void* x, float* dW, float* db,
                            msst_stream_t stream);
 
 /* y = x * dropout_factor(seed, site, element index), n % 4 == 0 (inverted dropout, nn.Dropout call sites

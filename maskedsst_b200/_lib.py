@@ -19,7 +19,7 @@ class EmbedDims(C.Structure):
 
 class LinearDims(C.Structure):
     _fields_ = [("M", C.c_int64), ("N", C.c_int), ("K", C.c_int), ("act", C.c_int), ("drop_p", C.c_float),
-                ("seed", C.c_uint64), ("site", C.c_uint32), ("prec", C.c_int), ("seed_dev", vp)]
+                ("seed", C.c_uint64), ("site", C.c_uint32), ("prec", C.c_int), ("seed_dev", vp), ("y_fp32", C.c_int)]
 
 
 class AttnDims(C.Structure):

@@ -19,6 +19,19 @@ int linear_bwd_weight_f32(const float* dy, const float* x, float* dW, float* db,
 int colsum_f32(const float* dy, float* db, int64_t M, int N, cudaStream_t st);
 int dropout_apply_f32(const float* x, float* y, int64_t n, Drop drop, cudaStream_t st);
 
+// gemm_bf16.cu (tcgen05 / TMA)
+struct GemmBf16Args {
+    const __nv_bfloat16* A; const __nv_bfloat16* B;   // A [M,K], B [N,K], both K contiguous
+    int64_t M; int N, K;
+    const float* bias; const float* residual;          // fp32 [N], fp32 [M,N]
+    void* out; int out_fp32;                           // [M,N] fp32 or bf16
+    __nv_bfloat16* pre_act; const __nv_bfloat16* aux;  // optional bf16 [M,N] out (pre-activation) / in (GELU' argument)
+    int act;                                           // 0 none, 1 GELU(erf), 2 multiply by GELU'(aux)
+    Drop drop;
+};
+int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st);
+int gemm_wgrad_bf16(const __nv_bfloat16* dy, const __nv_bfloat16* x, float* dW, int64_t M, int N, int K, cudaStream_t st);
+
 // attention_f32.cu
 int attention_fwd_f32(const msst_attn_dims* d, const float* qkv, float* out, float* lse, cudaStream_t st);
 int attention_bwd_f32(const msst_attn_dims* d, const float* qkv, const float* out, const float* lse, const float* d_out,

@@ -152,19 +152,36 @@ extern "C" int msst_transformer_bwd(const msst_tf_dims* d, const msst_layer_para
 // ---- stand-alone entry points (unit tests, microbench) ----
 extern "C" int msst_linear_fwd(const msst_linear_dims* d, const void* x, const void* W, const float* bias, const float* residual,
                                void* y, void* pre_act, msst_stream_t stream) {
-    MSST_REQUIRE(d && d->prec == MSST_PREC_FP32, "linear_fwd: precision mode not built");
+    MSST_REQUIRE(d, "linear_fwd: null dims");
+    const Drop drop = make_drop(d->drop_p, d->seed, d->site, d->seed_dev);
+    if (d->prec == MSST_PREC_BF16) {
+        GemmBf16Args a{(const __nv_bfloat16*)x, (const __nv_bfloat16*)W, d->M, d->N, d->K, bias, residual, y, d->y_fp32,
+                       (__nv_bfloat16*)pre_act, nullptr, d->act, drop};
+        return gemm_tn_bf16(a, (cudaStream_t)stream);
+    }
     return linear_fwd_f32((const float*)x, (const float*)W, bias, residual, (float*)y, (float*)pre_act, d->M, d->N, d->K, d->act,
-                          make_drop(d->drop_p, d->seed, d->site, d->seed_dev), (cudaStream_t)stream);
+                          drop, (cudaStream_t)stream);
 }
-extern "C" int msst_linear_bwd_data(const msst_linear_dims* d, const float* dy, const float* W, const float* pre_act,
-                                    const float* dx_add, float* dx, msst_stream_t stream) {
-    MSST_REQUIRE(d && d->prec == MSST_PREC_FP32, "linear_bwd_data: precision mode not built");
-    return linear_bwd_data_f32(dy, W, pre_act, dx_add, dx, d->M, d->N, d->K, make_drop(d->drop_p, d->seed, d->site, d->seed_dev), (cudaStream_t)stream);
+extern "C" int msst_linear_bwd_data(const msst_linear_dims* d, const void* dy, const void* W, const void* pre_act,
+                                    const float* dx_add, void* dx, msst_stream_t stream) {
+    MSST_REQUIRE(d, "linear_bwd_data: null dims");
+    const Drop drop = make_drop(d->drop_p, d->seed, d->site, d->seed_dev);
+    if (d->prec == MSST_PREC_BF16) {   // dx[M,K] = dy[M,N] . (W^T)[K,N]^T
+        GemmBf16Args a{(const __nv_bfloat16*)dy, (const __nv_bfloat16*)W, d->M, d->K, d->N, nullptr, dx_add, dx, d->y_fp32,
+                       nullptr, (const __nv_bfloat16*)pre_act, pre_act ? 2 : 0, drop};
+        return gemm_tn_bf16(a, (cudaStream_t)stream);
+    }
+    return linear_bwd_data_f32((const float*)dy, (const float*)W, (const float*)pre_act, dx_add, (float*)dx, d->M, d->N, d->K, drop,
+                               (cudaStream_t)stream);
 }
-extern "C" int msst_linear_bwd_weight(const msst_linear_dims* d, const float* dy, const float* x, float* dW, float* db,
+extern "C" int msst_linear_bwd_weight(const msst_linear_dims* d, const void* dy, const void* x, float* dW, float* db,
                                       msst_stream_t stream) {
-    MSST_REQUIRE(d && d->prec == MSST_PREC_FP32, "linear_bwd_weight: precision mode not built");
-    return linear_bwd_weight_f32(dy, x, dW, db, d->M, d->N, d->K, (cudaStream_t)stream);
+    MSST_REQUIRE(d, "linear_bwd_weight: null dims");
+    if (d->prec == MSST_PREC_BF16) {
+        MSST_REQUIRE(db == nullptr, "linear_bwd_weight: bias gradient is not fused in bf16 mode");
+        return gemm_wgrad_bf16((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, dW, d->M, d->N, d->K, (cudaStream_t)stream);
+    }
+    return linear_bwd_weight_f32((const float*)dy, (const float*)x, dW, db, d->M, d->N, d->K, (cudaStream_t)stream);
 }
 extern "C" int msst_attention_fwd(const msst_attn_dims* d, const void* qkv, void* out, float* lse, msst_stream_t stream) {
     MSST_REQUIRE(d && d->prec == MSST_PREC_FP32, "attention_fwd: precision mode not built");

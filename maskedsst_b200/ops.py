@@ -303,7 +303,7 @@ class LinearFn(torch.autograd.Function):
         pre = torch.empty_like(y) if act else None
         if residual is not None:
             residual = _c(residual)
-        dims = _lib.LinearDims(M, N, K, act, 0.0, 0, 0, PREC_FP32, None)
+        dims = _lib.LinearDims(M, N, K, act, 0.0, 0, 0, PREC_FP32, None, 1)
         check(_lib.lib().msst_linear_fwd(C.byref(dims), _p(x), _p(W), _p(bias), _p(residual), _p(y), _p(pre), _stream()))
         ctx.save_for_backward(x, W, pre)
         ctx.dims = dims
