@@ -1,0 +1,375 @@
+// Kernel (3), bf16 mode: fused flash-style attention forward / backward on tensor cores.
+// softmax(q k^T * dh^-0.5) v per (sequence, head); dh = 64; q/k/v/o bf16, statistics + accumulation fp32.
+// Reference: Attention.forward, src/vit_spatial_spectral.py:67-78 (and its autograd).
+//
+// Same tiling / packing geometry as attention_f32.cu (64 query slots x 64 key slots, short sequences packed with a
+// block-diagonal mask, strided row addressing for the spectral stack).  One CTA = 4 warps, each warp owns 16 query
+// rows (FlashAttention-2 register layout): S and P never leave registers, O / dQ accumulate in registers; the tiles
+// here are 64x64x64 -- too small for a tcgen05 pipeline to pay off (one UMMA M=64 tile per CTA), so the
+// contractions use mma.sync.m16n8k16 with ldmatrix-fed fragments.  Scores never reach HBM.
+// Algorithmic HBM bytes per (slot, head): fwd 3*128 B in + 128 B out + 4 B lse; bwd 5*128 B in + 3*128 B out.
+#include "common.cuh"
+#include "kernels.h"
+#include "attn_geom.cuh"
+
+namespace msst {
+
+constexpr int BT = 128;         // threads per CTA (4 warps)
+constexpr int PITCH = 72;       // bf16 elements per smem row (64 + 8 pad -> conflict-free ldmatrix)
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const bf16* p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const bf16* p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// C[16 x 64] (8 n-tiles) += A[16 rows of As starting at row0][64] . B^T, B stored [n][k] in Bs (rows = n, 64 k each)
+__device__ __forceinline__ void gemm_a_bnk(float (&c)[8][4], const bf16* As, int row0, const bf16* Bs, int lane) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        uint32_t a[4];
+        ldsm_x4(a, As + (row0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * PITCH + ks * 16 + 8 * (lane >> 4));
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+            uint32_t b[4];
+            ldsm_x4(b, Bs + (np * 16 + (lane & 7) + 8 * (lane >> 4)) * PITCH + ks * 16 + 8 * ((lane >> 3) & 1));
+            mma16816(c[2 * np], a, b[0], b[1]);
+            mma16816(c[2 * np + 1], a, b[2], b[3]);
+        }
+    }
+}
+// C[16 x 64] += P[16 x 64 (regs, C-fragment layout)] . B, B stored [k][n] in Bs (rows = k, 64 n each)
+__device__ __forceinline__ void gemm_p_bkn(float (&c)[8][4], const float (&p)[8][4], const bf16* Bs, int lane) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t a[4] = {pack2(p[2 * j][0], p[2 * j][1]), pack2(p[2 * j][2], p[2 * j][3]),
+                         pack2(p[2 * j + 1][0], p[2 * j + 1][1]), pack2(p[2 * j + 1][2], p[2 * j + 1][3])};
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+            uint32_t b[4];
+            ldsm_x4_t(b, Bs + (j * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * PITCH + np * 16 + 8 * (lane >> 4));
+            mma16816(c[2 * np], a, b[0], b[1]);
+            mma16816(c[2 * np + 1], a, b[2], b[3]);
+        }
+    }
+}
+// C[16 x 64] += A^T . B with A stored [k][m] in As (this warp's m = col0..col0+15), B stored [k][n] in Bs; k = 0..63
+__device__ __forceinline__ void gemm_at_bkn(float (&c)[8][4], const bf16* As, int col0, const bf16* Bs, int lane) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        uint32_t a[4];
+        ldsm_x4_t(a, As + (ks * 16 + (lane & 7) + 8 * (lane >> 4)) * PITCH + col0 + 8 * ((lane >> 3) & 1));
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+            uint32_t b[4];
+            ldsm_x4_t(b, Bs + (ks * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * PITCH + np * 16 + 8 * (lane >> 4));
+            mma16816(c[2 * np], a, b[0], b[1]);
+            mma16816(c[2 * np + 1], a, b[2], b[3]);
+        }
+    }
+}
+
+// [64 slots x 64] bf16 tile of one of q/k/v/o (column offset col0) -> smem, zero rows for invalid slots
+__device__ __forceinline__ void load_tile_bf16(const AttnGeom& g, const bf16* __restrict__ base, int64_t ld, int col0, int64_t group,
+                                               int tile, bf16* dst) {
+    for (int i = threadIdx.x; i < TS * 8; i += BT) {
+        const int r = i >> 3, c = (i & 7) * 8;
+        int64_t seq; int pos;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (slot_to(g, group, tile, r, seq, pos)) v = *reinterpret_cast<const uint4*>(base + row_of(g, seq, pos) * ld + col0 + c);
+        *reinterpret_cast<uint4*>(dst + r * PITCH + c) = v;
+    }
+}
+// smem tile rows [row0, row0+16) (bf16) -> global rows (one warp, coalesced 16-byte stores)
+__device__ __forceinline__ void store_rows16(const AttnGeom& g, const bf16* src, int row0, bf16* __restrict__ base, int64_t ld, int col0,
+                                             const int* seq_s, const int* pos_s, int64_t group, int lane) {
+    for (int i = lane; i < 16 * 8; i += 32) {
+        const int r = row0 + (i >> 3), c = (i & 7) * 8;
+        if (seq_s[r] < 0) continue;
+        const int64_t row = row_of(g, group * g.G + seq_s[r], pos_s[r]);
+        *reinterpret_cast<uint4*>(base + row * ld + col0 + c) = *reinterpret_cast<const uint4*>(src + r * PITCH + c);
+    }
+}
+
+// attention-probability dropout: one 32-bit hash decides two neighbouring key slots (16 bits each)
+__device__ __forceinline__ uint32_t pair_hash(const Drop& d, uint64_t idx) {
+    const uint64_t s = d.seed + (d.seed_dev ? __ldg(d.seed_dev) : 0ull);
+    uint32_t x = (uint32_t)idx * 0x9E3779B1u ^ ((uint32_t)(idx >> 32) * 0x85EBCA77u) ^ (uint32_t)s ^ (d.site * 0xC2B2AE3Du);
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    x += (uint32_t)(s >> 32);
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ void pair_factors(const Drop& d, uint64_t idx, float& f0, float& f1) {
+    const uint32_t h = pair_hash(d, idx), t16 = d.thresh >> 16;
+    f0 = (h & 0xFFFFu) >= t16 ? d.scale : 0.f;
+    f1 = (h >> 16) >= t16 ? d.scale : 0.f;
+}
+__device__ __forceinline__ uint64_t tile_pair_base(const AttnGeom& g, int64_t group, int h, int qt, int kt) {
+    return ((((uint64_t)group * g.H + h) * g.tiles + qt) * g.tiles + kt) * (uint64_t)(TS * TS / 2);
+}
+
+struct AttnSmemIdx { int qseq[TS], qpos[TS], kseq[TS], kpos[TS]; };
+
+__device__ __forceinline__ void fill_idx(const AttnGeom& g, int64_t group, int tile, int* seq_s, int* pos_s, int invalid) {
+    if (threadIdx.x < TS) {
+        int64_t seq; int pos;
+        const bool ok = slot_to(g, group, tile, threadIdx.x, seq, pos);
+        seq_s[threadIdx.x] = ok ? (int)(seq - group * g.G) : invalid;
+        pos_s[threadIdx.x] = pos;
+    }
+}
+
+__global__ void __launch_bounds__(BT) attn_fwd_bf16_kernel(AttnGeom g, const bf16* __restrict__ qkv, bf16* __restrict__ out,
+                                                           float* __restrict__ lse, Drop drop) {
+    __shared__ __align__(16) bf16 Qs[TS * PITCH];
+    __shared__ __align__(16) bf16 Ks[TS * PITCH];
+    __shared__ __align__(16) bf16 Vs[TS * PITCH];
+    __shared__ AttnSmemIdx ix;
+    const int I = g.H * 64, h = blockIdx.y;
+    const int64_t ld = 3 * (int64_t)I;
+    const int64_t group = blockIdx.x / g.tiles;
+    const int qt = blockIdx.x % g.tiles;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+    const int r0 = warp * 16 + gq, r1 = r0 + 8;
+    const float sl2 = g.scale * 1.4426950408889634f;   // scores are kept in log2 units: exp2f(s*scale*log2e - m)
+
+    load_tile_bf16(g, qkv, ld, h * 64, group, qt, Qs);
+    fill_idx(g, group, qt, ix.qseq, ix.qpos, -1);
+    float o[8][4] = {};
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    for (int kt = 0; kt < g.tiles; ++kt) {
+        __syncthreads();
+        load_tile_bf16(g, qkv, ld, I + h * 64, group, kt, Ks);
+        load_tile_bf16(g, qkv, ld, 2 * I + h * 64, group, kt, Vs);
+        fill_idx(g, group, kt, ix.kseq, ix.kpos, -2);
+        __syncthreads();
+        float s[8][4] = {};
+        gemm_a_bnk(s, Qs, warp * 16, Ks, lane);
+        const int qs0 = ix.qseq[r0], qs1 = ix.qseq[r1];
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int c = nt * 8 + 2 * tq;
+            const int ks0 = ix.kseq[c], ks1 = ix.kseq[c + 1];
+            s[nt][0] = qs0 == ks0 ? s[nt][0] * sl2 : -INFINITY; s[nt][1] = qs0 == ks1 ? s[nt][1] * sl2 : -INFINITY;
+            s[nt][2] = qs1 == ks0 ? s[nt][2] * sl2 : -INFINITY; s[nt][3] = qs1 == ks1 ? s[nt][3] * sl2 : -INFINITY;
+            mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1])); mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        const float c0 = mn0 == -INFINITY ? 1.f : exp2f(m0 - mn0), c1 = mn1 == -INFINITY ? 1.f : exp2f(m1 - mn1);
+        const float sub0 = mn0 == -INFINITY ? 0.f : mn0, sub1 = mn1 == -INFINITY ? 0.f : mn1;
+        float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            s[nt][0] = exp2f(s[nt][0] - sub0); s[nt][1] = exp2f(s[nt][1] - sub0);
+            s[nt][2] = exp2f(s[nt][2] - sub1); s[nt][3] = exp2f(s[nt][3] - sub1);
+            rs0 += s[nt][0] + s[nt][1]; rs1 += s[nt][2] + s[nt][3];
+        }
+        rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1); rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
+        rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1); rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
+        l0 = l0 * c0 + rs0; l1 = l1 * c1 + rs1; m0 = mn0; m1 = mn1;
+        if (drop.on()) {
+            const uint64_t base = tile_pair_base(g, group, h, qt, kt);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                float f0, f1;
+                pair_factors(drop, base + (uint64_t)(r0 * 32 + nt * 4 + tq), f0, f1); s[nt][0] *= f0; s[nt][1] *= f1;
+                pair_factors(drop, base + (uint64_t)(r1 * 32 + nt * 4 + tq), f0, f1); s[nt][2] *= f0; s[nt][3] *= f1;
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) { o[nt][0] *= c0; o[nt][1] *= c0; o[nt][2] *= c1; o[nt][3] *= c1; }
+        gemm_p_bkn(o, s, Vs, lane);
+    }
+    // normalise, stage this warp's 16 rows through its own Q rows (no other warp reads them), coalesced store
+    const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
+    __syncwarp();
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        *reinterpret_cast<uint32_t*>(Qs + r0 * PITCH + nt * 8 + 2 * tq) = pack2(o[nt][0] * i0, o[nt][1] * i0);
+        *reinterpret_cast<uint32_t*>(Qs + r1 * PITCH + nt * 8 + 2 * tq) = pack2(o[nt][2] * i1, o[nt][3] * i1);
+    }
+    __syncwarp();
+    store_rows16(g, Qs, warp * 16, out, I, h * 64, ix.qseq, ix.qpos, group, lane);
+    if (tq == 0) {
+        if (ix.qseq[r0] >= 0) lse[row_of(g, group * g.G + ix.qseq[r0], ix.qpos[r0]) * g.H + h] = (m0 + log2f(l0)) * 0.6931471805599453f;
+        if (ix.qseq[r1] >= 0) lse[row_of(g, group * g.G + ix.qseq[r1], ix.qpos[r1]) * g.H + h] = (m1 + log2f(l1)) * 0.6931471805599453f;
+    }
+}
+
+// MODE 0: one tile (N <= 64): dQ, dK, dV in one CTA.  MODE 1: dQ of q tile blockIdx (loops key tiles).
+// MODE 2: dK, dV of key tile blockIdx (loops query tiles).
+template <int MODE>
+__global__ void __launch_bounds__(BT) attn_bwd_bf16_kernel(AttnGeom g, const bf16* __restrict__ qkv, const bf16* __restrict__ out,
+                                                           const float* __restrict__ lse, const bf16* __restrict__ d_out,
+                                                           bf16* __restrict__ d_qkv, Drop drop) {
+    extern __shared__ __align__(16) uint8_t smem_bwd[];
+    bf16* Qs = reinterpret_cast<bf16*>(smem_bwd);
+    bf16* Ks = Qs + TS * PITCH;
+    bf16* Vs = Ks + TS * PITCH;
+    bf16* dOs = Vs + TS * PITCH;
+    bf16* Ps = dOs + TS * PITCH;     // P * dropout factor   [q][key]
+    bf16* dSs = Ps + TS * PITCH;     // dS                   [q][key]
+    float* Drow = reinterpret_cast<float*>(dSs + TS * PITCH);
+    float* lse_s = Drow + TS;
+    AttnSmemIdx& ix = *reinterpret_cast<AttnSmemIdx*>(lse_s + TS);
+
+    const int I = g.H * 64, h = blockIdx.y;
+    const int64_t ld = 3 * (int64_t)I;
+    const int64_t group = blockIdx.x / g.tiles;
+    const int own = blockIdx.x % g.tiles;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+    const int r0 = warp * 16 + gq, r1 = r0 + 8;
+    const float sl2 = g.scale * 1.4426950408889634f;
+    const int n_inner = MODE == 0 ? 1 : g.tiles;
+
+    float dq[8][4] = {}, dk[8][4] = {}, dv[8][4] = {};
+    for (int it = 0; it < n_inner; ++it) {
+        const int qt = MODE == 2 ? it : own, kt = MODE == 1 ? it : own;
+        __syncthreads();
+        if (MODE != 2 || it == 0) {
+            load_tile_bf16(g, qkv, ld, I + h * 64, group, kt, Ks);
+            load_tile_bf16(g, qkv, ld, 2 * I + h * 64, group, kt, Vs);
+            fill_idx(g, group, kt, ix.kseq, ix.kpos, -2);
+        }
+        if (MODE != 1 || it == 0) {
+            load_tile_bf16(g, qkv, ld, h * 64, group, qt, Qs);
+            load_tile_bf16(g, d_out, I, h * 64, group, qt, dOs);
+            fill_idx(g, group, qt, ix.qseq, ix.qpos, -1);
+        }
+        __syncthreads();
+        if (MODE != 1 || it == 0) {
+            // D_i = dO_i . O_i, lse_i  (warp: 16 rows, two rows per pass, 16 lanes x 4 elements per row)
+            for (int k = 0; k < 8; ++k) {
+                const int r = warp * 16 + k * 2 + (lane >> 4), c = (lane & 15) * 4;
+                float dsum = 0.f, l = 0.f;
+                if (ix.qseq[r] >= 0) {
+                    const int64_t row = row_of(g, group * g.G + ix.qseq[r], ix.qpos[r]);
+                    const uint2 ov = *reinterpret_cast<const uint2*>(out + row * I + h * 64 + c);
+                    const __nv_bfloat162 o01 = *reinterpret_cast<const __nv_bfloat162*>(&ov.x), o23 = *reinterpret_cast<const __nv_bfloat162*>(&ov.y);
+                    const bf16* dp = dOs + r * PITCH + c;
+                    dsum = __bfloat162float(dp[0]) * __low2float(o01) + __bfloat162float(dp[1]) * __high2float(o01) +
+                           __bfloat162float(dp[2]) * __low2float(o23) + __bfloat162float(dp[3]) * __high2float(o23);
+                    l = lse[row * g.H + h];
+                }
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+                if ((lane & 15) == 0) { Drow[r] = dsum; lse_s[r] = l * 1.4426950408889634f; }
+            }
+            __syncthreads();
+        }
+        float s[8][4] = {}, dp[8][4] = {};
+        gemm_a_bnk(s, Qs, warp * 16, Ks, lane);
+        gemm_a_bnk(dp, dOs, warp * 16, Vs, lane);
+        const int qs0 = ix.qseq[r0], qs1 = ix.qseq[r1];
+        const float L0 = lse_s[r0], L1 = lse_s[r1], D0 = Drow[r0], D1 = Drow[r1];
+        const uint64_t base = tile_pair_base(g, group, h, qt, kt);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int c = nt * 8 + 2 * tq;
+            const int ks0 = ix.kseq[c], ks1 = ix.kseq[c + 1];
+            float p0 = qs0 == ks0 ? exp2f(s[nt][0] * sl2 - L0) : 0.f, p1 = qs0 == ks1 ? exp2f(s[nt][1] * sl2 - L0) : 0.f;
+            float p2 = qs1 == ks0 ? exp2f(s[nt][2] * sl2 - L1) : 0.f, p3 = qs1 == ks1 ? exp2f(s[nt][3] * sl2 - L1) : 0.f;
+            float f0 = 1.f, f1 = 1.f, f2 = 1.f, f3 = 1.f;
+            if (drop.on()) {
+                pair_factors(drop, base + (uint64_t)(r0 * 32 + nt * 4 + tq), f0, f1);
+                pair_factors(drop, base + (uint64_t)(r1 * 32 + nt * 4 + tq), f2, f3);
+            }
+            // dS = P * (f * dP - D) * scale ; Pf = P * f
+            s[nt][0] = p0 * (f0 * dp[nt][0] - D0) * g.scale; s[nt][1] = p1 * (f1 * dp[nt][1] - D0) * g.scale;
+            s[nt][2] = p2 * (f2 * dp[nt][2] - D1) * g.scale; s[nt][3] = p3 * (f3 * dp[nt][3] - D1) * g.scale;
+            if (MODE != 1) {
+                *reinterpret_cast<uint32_t*>(Ps + r0 * PITCH + c) = pack2(p0 * f0, p1 * f1);
+                *reinterpret_cast<uint32_t*>(Ps + r1 * PITCH + c) = pack2(p2 * f2, p3 * f3);
+                *reinterpret_cast<uint32_t*>(dSs + r0 * PITCH + c) = pack2(s[nt][0], s[nt][1]);
+                *reinterpret_cast<uint32_t*>(dSs + r1 * PITCH + c) = pack2(s[nt][2], s[nt][3]);
+            }
+        }
+        if (MODE != 2) gemm_p_bkn(dq, s, Ks, lane);          // dQ[16 rows] += dS . K
+        if (MODE != 1) {
+            __syncthreads();
+            gemm_at_bkn(dv, Ps, warp * 16, dOs, lane);       // dV[16 keys] += (P f)^T . dO
+            gemm_at_bkn(dk, dSs, warp * 16, Qs, lane);       // dK[16 keys] += dS^T . Q
+        }
+    }
+    __syncthreads();
+    // stage results through smem (Q/K/V tiles are dead now) and store coalesced
+    if (MODE != 2) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            *reinterpret_cast<uint32_t*>(Qs + r0 * PITCH + nt * 8 + 2 * tq) = pack2(dq[nt][0], dq[nt][1]);
+            *reinterpret_cast<uint32_t*>(Qs + r1 * PITCH + nt * 8 + 2 * tq) = pack2(dq[nt][2], dq[nt][3]);
+        }
+    }
+    if (MODE != 1) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            *reinterpret_cast<uint32_t*>(Ks + r0 * PITCH + nt * 8 + 2 * tq) = pack2(dk[nt][0], dk[nt][1]);
+            *reinterpret_cast<uint32_t*>(Ks + r1 * PITCH + nt * 8 + 2 * tq) = pack2(dk[nt][2], dk[nt][3]);
+            *reinterpret_cast<uint32_t*>(Vs + r0 * PITCH + nt * 8 + 2 * tq) = pack2(dv[nt][0], dv[nt][1]);
+            *reinterpret_cast<uint32_t*>(Vs + r1 * PITCH + nt * 8 + 2 * tq) = pack2(dv[nt][2], dv[nt][3]);
+        }
+    }
+    __syncwarp();
+    if (MODE != 2) store_rows16(g, Qs, warp * 16, d_qkv, ld, h * 64, ix.qseq, ix.qpos, group, lane);
+    if (MODE != 1) {
+        store_rows16(g, Ks, warp * 16, d_qkv, ld, I + h * 64, ix.kseq, ix.kpos, group, lane);
+        store_rows16(g, Vs, warp * 16, d_qkv, ld, 2 * I + h * 64, ix.kseq, ix.kpos, group, lane);
+    }
+}
+
+constexpr size_t kBwdSmem = sizeof(bf16) * 6 * TS * PITCH + sizeof(float) * 2 * TS + sizeof(AttnSmemIdx);
+
+int attention_fwd_bf16(const msst_attn_dims* d, const bf16* qkv, bf16* out, float* lse, cudaStream_t st) {
+    AttnGeom g;
+    if (int rc = make_attn_geom(d, g, false)) return rc;
+    if (g.n_seq == 0) return MSST_OK;
+    const Drop drop = make_drop(d->drop_p, d->seed, d->site, d->seed_dev);
+    attn_fwd_bf16_kernel<<<dim3((unsigned)(g.groups * g.tiles), g.H), BT, 0, st>>>(g, qkv, out, lse, drop);
+    MSST_LAUNCH_CHECK();
+    return MSST_OK;
+}
+
+int attention_bwd_bf16(const msst_attn_dims* d, const bf16* qkv, const bf16* out, const float* lse, const bf16* d_out, bf16* d_qkv,
+                       cudaStream_t st) {
+    AttnGeom g;
+    if (int rc = make_attn_geom(d, g, false)) return rc;
+    if (g.n_seq == 0) return MSST_OK;
+    const Drop drop = make_drop(d->drop_p, d->seed, d->site, d->seed_dev);
+    const dim3 grid((unsigned)(g.groups * g.tiles), g.H);
+    static bool attr_set = false;
+    if (!attr_set) {
+        MSST_CUDA(cudaFuncSetAttribute(attn_bwd_bf16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
+        MSST_CUDA(cudaFuncSetAttribute(attn_bwd_bf16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
+        MSST_CUDA(cudaFuncSetAttribute(attn_bwd_bf16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
+        attr_set = true;
+    }
+    if (g.tiles == 1) {
+        attn_bwd_bf16_kernel<0><<<grid, BT, kBwdSmem, st>>>(g, qkv, out, lse, d_out, d_qkv, drop);
+        MSST_LAUNCH_CHECK();
+    } else {   // long sequences: dQ pass over key tiles, dK/dV pass over query tiles (no atomics)
+        attn_bwd_bf16_kernel<1><<<grid, BT, kBwdSmem, st>>>(g, qkv, out, lse, d_out, d_qkv, drop);
+        MSST_LAUNCH_CHECK();
+        attn_bwd_bf16_kernel<2><<<grid, BT, kBwdSmem, st>>>(g, qkv, out, lse, d_out, d_qkv, drop);
+        MSST_LAUNCH_CHECK();
+    }
+    return MSST_OK;
+}
+
+}  // namespace msst

@@ -10,25 +10,9 @@
 // '(b c)(h w) d -> (b h w) c d' transpose copies into index arithmetic.
 #include "common.cuh"
 #include "kernels.h"
+#include "attn_geom.cuh"
 
 namespace msst {
-
-constexpr int TS = 64;      // slots per tile
-constexpr int AT = 256;     // threads
-
-struct AttnGeom {
-    int64_t n_seq; int N, inner, H, dh, G, tiles;   // tiles = key/query tiles per sequence (1 when N <= 64)
-    int64_t groups;                                 // slot groups along the sequence axis
-    float scale;
-};
-
-__device__ __forceinline__ bool slot_to(const AttnGeom& g, int64_t group, int tile, int r, int64_t& seq, int& pos) {
-    if (g.N <= TS) { seq = group * g.G + r / g.N; pos = r % g.N; return r < g.G * g.N && seq < g.n_seq; }
-    seq = group; pos = tile * TS + r; return pos < g.N;
-}
-__device__ __forceinline__ int64_t row_of(const AttnGeom& g, int64_t seq, int pos) {
-    return (seq / g.inner) * g.N * g.inner + (seq % g.inner) + (int64_t)pos * g.inner;
-}
 
 // loads a [64 x DH] tile (rows = slots) of one of q/k/v (column offset col0) into smem, zero for invalid slots
 template <int DH>
@@ -320,19 +304,6 @@ __global__ void __launch_bounds__(AT) attn_bwd_kernel(AttnGeom g, const float* _
     }
 }
 
-static int make_geom(const msst_attn_dims* d, AttnGeom& g) {
-    MSST_REQUIRE(d && d->n_seq >= 0 && d->N > 0 && d->inner > 0 && d->H > 0, "attention: bad dims");
-    MSST_REQUIRE(d->dh == 32 || d->dh == 64 || d->dh == 128, "attention: dim_head=%d unsupported (32, 64, 128)", d->dh);
-    MSST_REQUIRE(d->n_seq % d->inner == 0, "attention: n_seq must be a multiple of inner");
-    MSST_REQUIRE(d->H <= 65535, "attention: too many heads");
-    g.n_seq = d->n_seq; g.N = d->N; g.inner = d->inner; g.H = d->H; g.dh = d->dh;
-    g.scale = 1.0f / sqrtf((float)d->dh);
-    if (d->N <= TS) { g.G = TS / d->N; g.tiles = 1; g.groups = ceil_div(d->n_seq, g.G); }
-    else { g.G = 1; g.tiles = (int)ceil_div(d->N, TS); g.groups = d->n_seq; }
-    MSST_REQUIRE(g.groups * g.tiles < (int64_t)2147483647, "attention: grid too large");
-    return MSST_OK;
-}
-
 template <int DH>
 static int launch_fwd(const AttnGeom& g, const float* qkv, float* out, float* lse, Drop drop, cudaStream_t st) {
     const size_t smem = sizeof(float) * ((size_t)3 * TS * (DH + 1) + (size_t)TS * (TS + 1) + 3 * TS) + sizeof(int) * 4 * TS;
@@ -353,7 +324,7 @@ static int launch_bwd(const AttnGeom& g, const float* qkv, const float* out, con
 
 int attention_fwd_f32(const msst_attn_dims* d, const float* qkv, float* out, float* lse, cudaStream_t st) {
     AttnGeom g;
-    if (int rc = make_geom(d, g)) return rc;
+    if (int rc = make_attn_geom(d, g, true)) return rc;
     if (g.n_seq == 0) return MSST_OK;
     const Drop drop = make_drop(d->drop_p, d->seed, d->site, d->seed_dev);
     switch (g.dh) {
@@ -366,7 +337,7 @@ int attention_fwd_f32(const msst_attn_dims* d, const float* qkv, float* out, flo
 int attention_bwd_f32(const msst_attn_dims* d, const float* qkv, const float* out, const float* lse, const float* d_out,
                       float* d_qkv, cudaStream_t st) {
     AttnGeom g;
-    if (int rc = make_geom(d, g)) return rc;
+    if (int rc = make_attn_geom(d, g, true)) return rc;
     if (g.n_seq == 0) return MSST_OK;
     const Drop drop = make_drop(d->drop_p, d->seed, d->site, d->seed_dev);
     if (g.tiles > 1)   // dQ is accumulated across key tiles with atomics

@@ -32,6 +32,18 @@ struct GemmBf16Args {
 int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st);
 int gemm_wgrad_bf16(const __nv_bfloat16* dy, const __nv_bfloat16* x, float* dW, int64_t M, int N, int K, cudaStream_t st);
 
+// bf16_util.cu
+int cast_rows_f32(const float* x, __nv_bfloat16* y, float* colsum, int64_t M, int N, Drop drop, cudaStream_t st);
+int cast_rows_bf16(const __nv_bfloat16* x, __nv_bfloat16* y, float* colsum, int64_t M, int N, Drop drop, cudaStream_t st);
+struct WeightCastEntry { const float* src; __nv_bfloat16* dst; __nv_bfloat16* dst_t; int rows, cols; };
+struct WeightCastTable { WeightCastEntry e[32]; int n; };
+int weights_to_bf16(const WeightCastTable& t, cudaStream_t st);
+
+// attention_bf16.cu (mma.sync, dh = 64)
+int attention_fwd_bf16(const msst_attn_dims* d, const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, cudaStream_t st);
+int attention_bwd_bf16(const msst_attn_dims* d, const __nv_bfloat16* qkv, const __nv_bfloat16* out, const float* lse,
+                       const __nv_bfloat16* d_out, __nv_bfloat16* d_qkv, cudaStream_t st);
+
 // attention_f32.cu
 int attention_fwd_f32(const msst_attn_dims* d, const float* qkv, float* out, float* lse, cudaStream_t st);
 int attention_bwd_f32(const msst_attn_dims* d, const float* qkv, const float* out, const float* lse, const float* d_out,

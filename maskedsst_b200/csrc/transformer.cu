@@ -18,6 +18,7 @@ static inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
 struct TfLayout {
     int64_t R; int I;
     size_t o_stats1, o_stats2, o_qkv, o_o, o_lse, o_xmid, o_u, o_g, o_xout, layer_bytes;
+    size_t o_wq, o_wqT, o_wo, o_woT, o_w1, o_w1T, o_w2, o_w2T, wlayer_bytes, w_base;   // bf16 mode: per-layer bf16 weight copies
     size_t s_h, s_dqkv, s_do, s_du, s_dh, s_dy, s_dxa, s_dxb, total;
     int layer_slots;
 };
@@ -26,18 +27,29 @@ static TfLayout make_layout(const msst_tf_dims* d) {
     TfLayout L{};
     L.R = d->n_seq * d->N; L.I = d->H * d->dh;
     const size_t R = (size_t)L.R, f = sizeof(float);
+    const size_t a = d->prec == MSST_PREC_BF16 ? 2 : 4;   // activation element size (qkv, o, u, g, h, d*): bf16 or fp32
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
     L.o_stats1 = take(R * 2 * f); L.o_stats2 = take(R * 2 * f);
-    L.o_qkv = take(R * 3 * L.I * f); L.o_o = take(R * L.I * f); L.o_lse = take(R * d->H * f);
-    L.o_xmid = take(R * d->D * f); L.o_u = take(R * d->M * f); L.o_g = take(R * d->M * f); L.o_xout = take(R * d->D * f);
+    L.o_qkv = take(R * 3 * L.I * a); L.o_o = take(R * L.I * a); L.o_lse = take(R * d->H * f);
+    L.o_xmid = take(R * d->D * f); L.o_u = take(R * d->M * a); L.o_g = take(R * d->M * a); L.o_xout = take(R * d->D * f);
     L.layer_bytes = off;
     L.layer_slots = d->save_for_backward ? d->L : 1;
     off = L.layer_bytes * L.layer_slots;
-    L.s_h = take(R * d->D * f);
+    if (d->prec == MSST_PREC_BF16) {
+        const size_t base = off;
+        off = 0;
+        const size_t nq = (size_t)3 * L.I * d->D * 2, no = (size_t)d->D * L.I * 2, n1 = (size_t)d->M * d->D * 2;
+        L.o_wq = take(nq); L.o_wqT = take(nq); L.o_wo = take(no); L.o_woT = take(no);
+        L.o_w1 = take(n1); L.o_w1T = take(n1); L.o_w2 = take(n1); L.o_w2T = take(n1);
+        L.wlayer_bytes = off;
+        L.w_base = base;
+        off = base + L.wlayer_bytes * d->L;
+    }
+    L.s_h = take(R * d->D * a);
     if (d->save_for_backward) {
-        L.s_dqkv = take(R * 3 * L.I * f); L.s_do = take(R * L.I * f); L.s_du = take(R * d->M * f);
-        L.s_dh = take(R * d->D * f); L.s_dy = take(R * d->D * f); L.s_dxa = take(R * d->D * f); L.s_dxb = take(R * d->D * f);
+        L.s_dqkv = take(R * 3 * L.I * a); L.s_do = take(R * L.I * a); L.s_du = take(R * d->M * a);
+        L.s_dh = take(R * d->D * f); L.s_dy = take(R * d->D * a); L.s_dxa = take(R * d->D * f); L.s_dxb = take(R * d->D * f);
     }
     L.total = off;
     return L;
@@ -47,7 +59,118 @@ static int check_dims(const msst_tf_dims* d) {
     MSST_REQUIRE(d && d->n_seq >= 0 && d->N > 0 && d->inner > 0 && d->L > 0, "transformer: bad dims");
     MSST_REQUIRE(d->D > 0 && d->D <= 256 && d->M > 0 && d->H > 0, "transformer: bad model dims");
     MSST_REQUIRE(d->D % 4 == 0 && d->M % 4 == 0, "transformer: D and M must be multiples of 4");
-    MSST_REQUIRE(d->prec == MSST_PREC_FP32, "transformer: precision mode %d not built into this library", d->prec);
+    MSST_REQUIRE(d->prec == MSST_PREC_FP32 || d->prec == MSST_PREC_BF16, "transformer: unknown precision mode %d", d->prec);
+    if (d->prec == MSST_PREC_BF16) {
+        MSST_REQUIRE(d->dh == 64, "transformer (bf16): dim_head must be 64");
+        MSST_REQUIRE(d->D % 8 == 0 && d->M % 8 == 0 && d->L <= 8, "transformer (bf16): D, M must be multiples of 8 and L <= 8");
+    }
+    return MSST_OK;
+}
+
+typedef __nv_bfloat16 bf16;
+
+struct Bf16Weights { bf16 *wq, *wqT, *wo, *woT, *w1, *w1T, *w2, *w2T; };
+static Bf16Weights layer_weights(const TfLayout& L, char* ws, int l) {
+    char* b = ws + L.w_base + L.wlayer_bytes * l;
+    return {(bf16*)(b + L.o_wq), (bf16*)(b + L.o_wqT), (bf16*)(b + L.o_wo), (bf16*)(b + L.o_woT),
+            (bf16*)(b + L.o_w1), (bf16*)(b + L.o_w1T), (bf16*)(b + L.o_w2), (bf16*)(b + L.o_w2T)};
+}
+
+static GemmBf16Args gemm_args(const bf16* A, const bf16* B, int64_t M, int N, int K, void* out, int out_fp32) {
+    GemmBf16Args a{};
+    a.A = A; a.B = B; a.M = M; a.N = N; a.K = K; a.out = out; a.out_fp32 = out_fp32; a.drop = make_drop(0.f, 0, 0);
+    return a;
+}
+
+// ---- bf16 mode: tcgen05 GEMMs + tensor-core attention; residual stream / LN statistics / lse stay fp32 ----
+static int tf_fwd_bf16(const msst_tf_dims* d, const msst_layer_params* layers, const float* x_in, float* x_out, char* ws, cudaStream_t st) {
+    const TfLayout L = make_layout(d);
+    const int64_t R = L.R;
+    const int D = d->D, I = L.I, M = d->M;
+    // bf16 (and transposed) copies of this stack's weight matrices: one launch
+    WeightCastTable tab{}; tab.n = 0;
+    for (int l = 0; l < d->L; ++l) {
+        const Bf16Weights w = layer_weights(L, ws, l);
+        tab.e[tab.n++] = {layers[l].w_qkv, w.wq, w.wqT, 3 * I, D};
+        tab.e[tab.n++] = {layers[l].w_out, w.wo, w.woT, D, I};
+        tab.e[tab.n++] = {layers[l].w1, w.w1, w.w1T, M, D};
+        tab.e[tab.n++] = {layers[l].w2, w.w2, w.w2T, D, M};
+    }
+    if (int rc = weights_to_bf16(tab, st)) return rc;
+    bf16* h = (bf16*)(ws + L.s_h);
+    const float* x = x_in;
+    for (int l = 0; l < d->L; ++l) {
+        char* lw = ws + L.layer_bytes * (d->save_for_backward ? l : 0);
+        const msst_layer_params& p = layers[l];
+        const Bf16Weights w = layer_weights(L, ws, l);
+        float* stats1 = (float*)(lw + L.o_stats1); float* stats2 = (float*)(lw + L.o_stats2);
+        bf16* qkv = (bf16*)(lw + L.o_qkv); bf16* o = (bf16*)(lw + L.o_o); float* lse = (float*)(lw + L.o_lse);
+        float* xmid = (float*)(lw + L.o_xmid); bf16* u = (bf16*)(lw + L.o_u); bf16* g = (bf16*)(lw + L.o_g);
+        float* y = (l == d->L - 1) ? x_out : (float*)(lw + L.o_xout);
+        const uint32_t site = d->site_base + 8u * l;
+        if (int rc = layernorm_fwd(x, p.ln1_w, p.ln1_b, h, 1, stats1, R, D, 1e-5f, st)) return rc;
+        if (int rc = gemm_tn_bf16(gemm_args(h, w.wq, R, 3 * I, D, qkv, 0), st)) return rc;
+        msst_attn_dims ad{d->n_seq, d->N, d->inner, d->H, d->dh, d->drop_p, d->seed, site + kSiteAttnProb, d->prec, d->seed_dev};
+        if (int rc = attention_fwd_bf16(&ad, qkv, o, lse, st)) return rc;
+        GemmBf16Args a = gemm_args(o, w.wo, R, D, I, xmid, 1);
+        a.bias = p.b_out; a.residual = x; a.drop = make_drop(d->drop_p, d->seed, site + kSiteAttnOut, d->seed_dev);
+        if (int rc = gemm_tn_bf16(a, st)) return rc;
+        if (int rc = layernorm_fwd(xmid, p.ln2_w, p.ln2_b, h, 1, stats2, R, D, 1e-5f, st)) return rc;
+        a = gemm_args(h, w.w1, R, M, D, g, 0);
+        a.bias = p.b1; a.pre_act = u; a.act = 1; a.drop = make_drop(d->drop_p, d->seed, site + kSiteMlpHidden, d->seed_dev);
+        if (int rc = gemm_tn_bf16(a, st)) return rc;
+        a = gemm_args(g, w.w2, R, D, M, y, 1);
+        a.bias = p.b2; a.residual = xmid; a.drop = make_drop(d->drop_p, d->seed, site + kSiteMlpOut, d->seed_dev);
+        if (int rc = gemm_tn_bf16(a, st)) return rc;
+        x = y;
+    }
+    return MSST_OK;
+}
+
+static int tf_bwd_bf16(const msst_tf_dims* d, const msst_layer_params* layers, const msst_layer_grads* grads, const float* x_in,
+                       const float* d_x_out, float* d_x_in, char* ws, cudaStream_t st) {
+    const TfLayout L = make_layout(d);
+    const int64_t R = L.R;
+    const int D = d->D, I = L.I, M = d->M;
+    bf16* h = (bf16*)(ws + L.s_h); bf16* dqkv = (bf16*)(ws + L.s_dqkv); bf16* dO = (bf16*)(ws + L.s_do);
+    bf16* du = (bf16*)(ws + L.s_du); float* dh = (float*)(ws + L.s_dh); bf16* dyb = (bf16*)(ws + L.s_dy);
+    float* dxa = (float*)(ws + L.s_dxa); float* dxb = (float*)(ws + L.s_dxb);
+    const float* dcur = d_x_out;
+    const Drop none = make_drop(0.f, 0, 0);
+    for (int l = d->L - 1; l >= 0; --l) {
+        char* lw = ws + L.layer_bytes * l;
+        const msst_layer_params& p = layers[l];
+        const msst_layer_grads& gr = grads[l];
+        const Bf16Weights w = layer_weights(L, ws, l);
+        float* stats1 = (float*)(lw + L.o_stats1); float* stats2 = (float*)(lw + L.o_stats2);
+        bf16* qkv = (bf16*)(lw + L.o_qkv); bf16* o = (bf16*)(lw + L.o_o); float* lse = (float*)(lw + L.o_lse);
+        float* xmid = (float*)(lw + L.o_xmid); bf16* u = (bf16*)(lw + L.o_u); bf16* g = (bf16*)(lw + L.o_g);
+        const float* x = (l == 0) ? x_in : (const float*)(ws + L.layer_bytes * (l - 1) + L.o_xout);
+        const uint32_t site = d->site_base + 8u * l;
+        // ---- MLP branch ----
+        if (int rc = cast_rows_f32(dcur, dyb, gr.b2, R, D, make_drop(d->drop_p, d->seed, site + kSiteMlpOut, d->seed_dev), st)) return rc;
+        if (int rc = gemm_wgrad_bf16(dyb, g, gr.w2, R, D, M, st)) return rc;
+        GemmBf16Args a = gemm_args(dyb, w.w2T, R, M, D, du, 0);        // du = (dy . W2) * gelu'(u) * hidden-dropout
+        a.aux = u; a.act = 2; a.drop = make_drop(d->drop_p, d->seed, site + kSiteMlpHidden, d->seed_dev);
+        if (int rc = gemm_tn_bf16(a, st)) return rc;
+        if (int rc = cast_rows_bf16(du, nullptr, gr.b1, R, M, none, st)) return rc;
+        if (int rc = layernorm_fwd(xmid, p.ln2_w, p.ln2_b, h, 1, nullptr, R, D, 1e-5f, st)) return rc;
+        if (int rc = gemm_wgrad_bf16(du, h, gr.w1, R, M, D, st)) return rc;
+        if (int rc = gemm_tn_bf16(gemm_args(du, w.w1T, R, D, M, dh, 1), st)) return rc;
+        if (int rc = layernorm_bwd(xmid, p.ln2_w, stats2, dh, dcur, dxa, gr.ln2_w, gr.ln2_b, R, D, st)) return rc;
+        // ---- attention branch ----
+        if (int rc = cast_rows_f32(dxa, dyb, gr.b_out, R, D, make_drop(d->drop_p, d->seed, site + kSiteAttnOut, d->seed_dev), st)) return rc;
+        if (int rc = gemm_wgrad_bf16(dyb, o, gr.w_out, R, D, I, st)) return rc;
+        if (int rc = gemm_tn_bf16(gemm_args(dyb, w.woT, R, I, D, dO, 0), st)) return rc;
+        msst_attn_dims ad{d->n_seq, d->N, d->inner, d->H, d->dh, d->drop_p, d->seed, site + kSiteAttnProb, d->prec, d->seed_dev};
+        if (int rc = attention_bwd_bf16(&ad, qkv, o, lse, dO, dqkv, st)) return rc;
+        if (int rc = layernorm_fwd(x, p.ln1_w, p.ln1_b, h, 1, nullptr, R, D, 1e-5f, st)) return rc;
+        if (int rc = gemm_wgrad_bf16(dqkv, h, gr.w_qkv, R, 3 * I, D, st)) return rc;
+        if (int rc = gemm_tn_bf16(gemm_args(dqkv, w.wqT, R, D, 3 * I, dh, 1), st)) return rc;
+        float* dx = (l == 0) ? d_x_in : dxb;
+        if (int rc = layernorm_bwd(x, p.ln1_w, stats1, dh, dxa, dx, gr.ln1_w, gr.ln1_b, R, D, st)) return rc;
+        dcur = dx;
+    }
     return MSST_OK;
 }
 
@@ -63,6 +186,7 @@ extern "C" int msst_transformer_fwd(const msst_tf_dims* d, const msst_layer_para
                                     void* workspace, msst_stream_t stream) {
     if (int rc = check_dims(d)) return rc;
     MSST_REQUIRE(layers && x_in && x_out && workspace, "transformer_fwd: null pointer");
+    if (d->prec == MSST_PREC_BF16) return tf_fwd_bf16(d, layers, x_in, x_out, (char*)workspace, (cudaStream_t)stream);
     const TfLayout L = make_layout(d);
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)workspace;
@@ -98,6 +222,7 @@ extern "C" int msst_transformer_bwd(const msst_tf_dims* d, const msst_layer_para
     if (int rc = check_dims(d)) return rc;
     MSST_REQUIRE(d->save_for_backward, "transformer_bwd: forward was not run with save_for_backward");
     MSST_REQUIRE(layers && grads && x_in && d_x_out && d_x_in && workspace, "transformer_bwd: null pointer");
+    if (d->prec == MSST_PREC_BF16) return tf_bwd_bf16(d, layers, grads, x_in, d_x_out, d_x_in, (char*)workspace, (cudaStream_t)stream);
     const TfLayout L = make_layout(d);
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)workspace;
@@ -184,12 +309,15 @@ extern "C" int msst_linear_bwd_weight(const msst_linear_dims* d, const void* dy,
     return linear_bwd_weight_f32((const float*)dy, (const float*)x, dW, db, d->M, d->N, d->K, (cudaStream_t)stream);
 }
 extern "C" int msst_attention_fwd(const msst_attn_dims* d, const void* qkv, void* out, float* lse, msst_stream_t stream) {
-    MSST_REQUIRE(d && d->prec == MSST_PREC_FP32, "attention_fwd: precision mode not built");
+    MSST_REQUIRE(d, "attention_fwd: null dims");
+    if (d->prec == MSST_PREC_BF16) return attention_fwd_bf16(d, (const bf16*)qkv, (bf16*)out, lse, (cudaStream_t)stream);
     return attention_fwd_f32(d, (const float*)qkv, (float*)out, lse, (cudaStream_t)stream);
 }
 extern "C" int msst_attention_bwd(const msst_attn_dims* d, const void* qkv, const void* out, const float* lse, const void* d_out,
                                   void* d_qkv, msst_stream_t stream) {
-    MSST_REQUIRE(d && d->prec == MSST_PREC_FP32, "attention_bwd: precision mode not built");
+    MSST_REQUIRE(d, "attention_bwd: null dims");
+    if (d->prec == MSST_PREC_BF16)
+        return attention_bwd_bf16(d, (const bf16*)qkv, (const bf16*)out, lse, (const bf16*)d_out, (bf16*)d_qkv, (cudaStream_t)stream);
     return attention_bwd_f32(d, (const float*)qkv, (const float*)out, lse, (const float*)d_out, (float*)d_qkv, (cudaStream_t)stream);
 }
 extern "C" int msst_dropout_apply(const float* x, float* y, int64_t n, float p, uint64_t seed, uint32_t site,

@@ -334,10 +334,11 @@ class AttentionFn(torch.autograd.Function):
     def forward(ctx, qkv, cfg):
         n_seq, N, inner, H, dh, drop_p, seed, site = cfg
         qkv = _c(qkv)
-        _chk(qkv, "qkv")
+        prec = PREC_BF16 if qkv.dtype == torch.bfloat16 else PREC_FP32   # bf16 tensors -> tensor-core kernels
+        _chk(qkv, "qkv", qkv.dtype if prec == PREC_BF16 else torch.float32)
         R = n_seq * N
-        dims = _lib.AttnDims(n_seq, N, inner, H, dh, float(drop_p), seed, site, PREC_FP32, None)
-        out = torch.empty(R, H * dh, device=qkv.device, dtype=torch.float32)
+        dims = _lib.AttnDims(n_seq, N, inner, H, dh, float(drop_p), seed, site, prec, None)
+        out = torch.empty(R, H * dh, device=qkv.device, dtype=qkv.dtype)
         lse = torch.empty(R, H, device=qkv.device, dtype=torch.float32)
         check(_lib.lib().msst_attention_fwd(C.byref(dims), _p(qkv), _p(out), _p(lse), _stream()))
         ctx.save_for_backward(qkv, out, lse)
@@ -347,7 +348,7 @@ class AttentionFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_out):
         qkv, out, lse = ctx.saved_tensors
-        d_out = _c(d_out)
+        d_out = _c(d_out.to(qkv.dtype))
         d_qkv = torch.empty_like(qkv)
         check(_lib.lib().msst_attention_bwd(C.byref(ctx.dims), _p(qkv), _p(out), _p(lse), _p(d_out), _p(d_qkv), _stream()))
         return d_qkv, None
