@@ -178,9 +178,12 @@ def run_ours(args):
     dev_x = [t.to(dev) for t in host_x]
     dev_masks = [model.draw_masks(B, dev) for _ in range(pool)]
 
-    def allreduce_grads():
-        if world > 1:
-            dist.all_reduce(opt.grad_arena)
+    from maskedsst_b200.dp import GradSync
+    sync = GradSync(opt.arena, num_buckets=3) if world > 1 else None
+
+    def allreduce_grads():   # bucketed all-reduce overlapped with backward (hooks); this only drains it
+        if sync is not None:
+            sync.finish()
 
     def step_resident(i):
         opt.zero_grad()

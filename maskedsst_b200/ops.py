@@ -214,6 +214,34 @@ def cross_entropy(logits, labels, ignore_index=-1):
     return CrossEntropyFn.apply(logits, labels, ignore_index)
 
 
+class CrossEntropySumFn(torch.autograd.Function):
+    """(sum of NLL over valid pixels, number of valid pixels) -- the two pieces a data-parallel run all-reduces."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, ignore_index):
+        logits = _c(logits)
+        _chk(logits, "logits")
+        labels = _c(labels)
+        _chk(labels, "labels", torch.int64)
+        B, nc = logits.shape[:2]
+        HW = logits[0, 0].numel()
+        sc = torch.empty(2, device=logits.device, dtype=torch.float32)
+        dl = torch.empty_like(logits)
+        check(_lib.lib().msst_cross_entropy_fwd_bwd(_p(logits), _p(labels), B, nc, HW, ignore_index, _p(sc), _p(dl), _stream()))
+        ctx.save_for_backward(dl)
+        ctx.mark_non_differentiable(sc[1])
+        return sc[0], sc[1]
+
+    @staticmethod
+    def backward(ctx, g, _):
+        (dl,) = ctx.saved_tensors
+        return dl * g, None, None
+
+
+def cross_entropy_sum_count(logits, labels, ignore_index=-1):
+    return CrossEntropySumFn.apply(logits, labels, ignore_index)
+
+
 # ---- SimMIM decoder + masked L1 ---------------------------------------------------------------------------
 class DecodeL1Fn(torch.autograd.Function):
     @staticmethod

@@ -17,6 +17,38 @@ from . import _lib
 from ._lib import check
 
 
+class FlatArena:
+    """Re-homes parameters (and their .grad) into one contiguous fp32 buffer each; the nn.Parameters become views,
+    so names / shapes / state_dict are unchanged.  Every tensor starts on a 16-byte boundary (float4 kernels and
+    all-reduce bucket boundaries).  Device-agnostic (the data-parallel host logic is tested on CPU with gloo)."""
+
+    def __init__(self, groups):
+        flat = [p for g in groups for p in g]
+        dev = flat[0].device
+        for p in flat:
+            if p.dtype != torch.float32 or p.device != dev:
+                raise RuntimeError("FlatArena: all parameters must be fp32 on one device")
+        self.param_list = flat
+        self.offsets, self.group_ranges, total = {}, [], 0
+        for g in groups:
+            start = total
+            for p in g:
+                self.offsets[id(p)] = (total, p.numel())
+                total += (p.numel() + 3) // 4 * 4
+            self.group_ranges.append((start, total))
+        self.params = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.grads = torch.zeros(total, device=dev, dtype=torch.float32)
+        with torch.no_grad():
+            for p in flat:
+                off, n = self.offsets[id(p)]
+                self.params[off: off + n].copy_(p.detach().reshape(-1))
+                old_grad = p.grad
+                p.data = self.params[off: off + n].view(p.shape)
+                p.grad = self.grads[off: off + n].view(p.shape)
+                if old_grad is not None:
+                    p.grad.copy_(old_grad)
+
+
 class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=True, clamp=0.0,
                  grad_scale=1.0):
@@ -27,40 +59,19 @@ class FusedAdam(torch.optim.Optimizer):
 
     # ---- arena construction ---------------------------------------------------------------------------------
     def _flatten(self):
-        all_params = [p for g in self.param_groups for p in g["params"]]
-        if not all_params:
+        groups = [g["params"] for g in self.param_groups]
+        if not any(groups):
             raise ValueError("FusedAdam: no parameters")
-        dev = all_params[0].device
+        dev = groups[0][0].device
         if dev.type != "cuda":
             raise RuntimeError("FusedAdam needs CUDA parameters (move the model to the GPU first; there is no CPU path)")
-        for p in all_params:
-            if p.dtype != torch.float32 or p.device != dev:
-                raise RuntimeError("FusedAdam: all parameters must be fp32 on one CUDA device")
-        # every tensor starts on a 16-byte boundary (float4 kernel, and bucket boundaries for all-reduce)
-        offsets, total = [], 0
-        self._group_ranges = []
-        for g in self.param_groups:
-            start = total
-            for p in g["params"]:
-                offsets.append(total)
-                total += (p.numel() + 3) // 4 * 4
-            self._group_ranges.append((start, total))
-        self.param_arena = torch.zeros(total, device=dev, dtype=torch.float32)
-        self.grad_arena = torch.zeros(total, device=dev, dtype=torch.float32)
-        self.exp_avg = torch.zeros(total, device=dev, dtype=torch.float32)
-        self.exp_avg_sq = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.arena = FlatArena(groups)
+        self.param_arena, self.grad_arena = self.arena.params, self.arena.grads
+        self._group_ranges = self.arena.group_ranges
+        self._offsets = self.arena.offsets
+        self.exp_avg = torch.zeros_like(self.param_arena)
+        self.exp_avg_sq = torch.zeros_like(self.param_arena)
         self.bf16_arena = None
-        self._offsets = {}
-        with torch.no_grad():
-            for p, off in zip(all_params, offsets):
-                n = p.numel()
-                self.param_arena[off: off + n].copy_(p.detach().reshape(-1))
-                old_grad = p.grad
-                p.data = self.param_arena[off: off + n].view(p.shape)
-                p.grad = self.grad_arena[off: off + n].view(p.shape)
-                if old_grad is not None:
-                    p.grad.copy_(old_grad)
-                self._offsets[id(p)] = (off, n)
         self._step = 0
 
     def offset_of(self, p):
