@@ -334,6 +334,255 @@ __global__ void __launch_bounds__(BT) attn_bwd_bf16_kernel(AttnGeom g, const bf1
     }
 }
 
+
+// =========================================================================================================
+// Single-tile (N <= 64) fast path: one CTA per slot group loops over ALL heads; the Q/K/V(/dO) tiles of head h+1 are
+// prefetched with cp.async into a second buffer while head h is computed, and everything that only depends on the
+// slot geometry (row addresses, block-diagonal mask bits) is computed once per CTA instead of once per (CTA, head).
+// =========================================================================================================
+__device__ __forceinline__ void cp_async16(bf16* dst, const bf16* src, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    const int sz = valid ? 16 : 0;   // src-size 0 -> the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+struct HeadsShared {
+    int64_t row[TS];     // global row of each slot (or -1)
+    int seq[TS];         // local sequence id of each slot (or -1)
+    int pos[TS];
+};
+
+__device__ __forceinline__ void heads_setup(const AttnGeom& g, int64_t group, HeadsShared& hs) {
+    if (threadIdx.x < TS) {
+        int64_t seq; int pos;
+        const bool ok = slot_to(g, group, 0, threadIdx.x, seq, pos);
+        hs.seq[threadIdx.x] = ok ? (int)(seq - group * g.G) : -1;
+        hs.pos[threadIdx.x] = pos;
+        hs.row[threadIdx.x] = ok ? row_of(g, seq, pos) : -1;
+    }
+}
+// this thread's 4 chunks of a [64 x 64] tile: rows (tid>>3) + 16k, column chunk (tid&7)*8
+__device__ __forceinline__ void prefetch_tile(bf16* dst, const bf16* __restrict__ base, int64_t ld, int col0, const HeadsShared& hs) {
+    const int c = (threadIdx.x & 7) * 8;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = (threadIdx.x >> 3) + 16 * k;
+        const int64_t row = hs.row[r];
+        cp_async16(dst + r * PITCH + c, base + (row < 0 ? 0 : row) * ld + col0 + c, row >= 0);
+    }
+}
+__device__ __forceinline__ void store_rows16_hs(const bf16* src, int row0, bf16* __restrict__ base, int64_t ld, int col0,
+                                                const HeadsShared& hs, int lane) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = lane + 32 * k;
+        const int r = row0 + (i >> 3), c = (i & 7) * 8;
+        const int64_t row = hs.row[r];
+        if (row >= 0) *reinterpret_cast<uint4*>(base + row * ld + col0 + c) = *reinterpret_cast<const uint4*>(src + r * PITCH + c);
+    }
+}
+// bit (4*nt + e) set when element e of n-tile nt of this thread's C fragment pairs a query and a key of the same sequence
+__device__ __forceinline__ uint32_t fragment_mask(const HeadsShared& hs, int r0, int r1, int tq) {
+    const int qs0 = hs.seq[r0], qs1 = hs.seq[r1];
+    uint32_t m = 0;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const int c = nt * 8 + 2 * tq;
+        const int ks0 = hs.seq[c], ks1 = hs.seq[c + 1];
+        m |= (uint32_t)(qs0 >= 0 && qs0 == ks0) << (4 * nt);
+        m |= (uint32_t)(qs0 >= 0 && qs0 == ks1) << (4 * nt + 1);
+        m |= (uint32_t)(qs1 >= 0 && qs1 == ks0) << (4 * nt + 2);
+        m |= (uint32_t)(qs1 >= 0 && qs1 == ks1) << (4 * nt + 3);
+    }
+    return m;
+}
+
+constexpr size_t kFwdHeadsSmem = sizeof(bf16) * 2 * 3 * TS * PITCH + sizeof(HeadsShared);
+constexpr size_t kBwdHeadsSmem = sizeof(bf16) * (2 * 4 + 1) * TS * PITCH + sizeof(HeadsShared);
+
+__global__ void __launch_bounds__(BT, 4) attn_fwd_bf16_heads_kernel(AttnGeom g, const bf16* __restrict__ qkv, bf16* __restrict__ out,
+                                                                    float* __restrict__ lse, Drop drop) {
+    extern __shared__ __align__(16) uint8_t smem_h[];
+    bf16* buf = reinterpret_cast<bf16*>(smem_h);                                   // [2][3][TS*PITCH]
+    HeadsShared& hs = *reinterpret_cast<HeadsShared*>(smem_h + sizeof(bf16) * 6 * TS * PITCH);
+    const int I = g.H * 64;
+    const int64_t ld = 3 * (int64_t)I, group = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+    const int r0 = warp * 16 + gq, r1 = r0 + 8;
+    const float sl2 = g.scale * 1.4426950408889634f;
+    heads_setup(g, group, hs);
+    __syncthreads();
+    const uint32_t mask = fragment_mask(hs, r0, r1, tq);
+    const int64_t grow0 = hs.row[r0], grow1 = hs.row[r1];
+    auto prefetch = [&](int h, int b) {
+        bf16* t = buf + (size_t)b * 3 * TS * PITCH;
+        prefetch_tile(t, qkv, ld, h * 64, hs);
+        prefetch_tile(t + TS * PITCH, qkv, ld, I + h * 64, hs);
+        prefetch_tile(t + 2 * TS * PITCH, qkv, ld, 2 * I + h * 64, hs);
+        cp_async_commit();
+    };
+    prefetch(0, 0);
+    for (int h = 0; h < g.H; ++h) {
+        const int b = h & 1;
+        cp_async_wait_all();
+        __syncthreads();
+        if (h + 1 < g.H) prefetch(h + 1, b ^ 1);
+        bf16* Qs = buf + (size_t)b * 3 * TS * PITCH; bf16* Ks = Qs + TS * PITCH; bf16* Vs = Ks + TS * PITCH;
+        float s[8][4] = {};
+        gemm_a_bnk(s, Qs, warp * 16, Ks, lane);
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) s[nt][e] = (mask >> (4 * nt + e)) & 1u ? s[nt][e] * sl2 : -INFINITY;
+            mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1])); mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float sub0 = mx0 == -INFINITY ? 0.f : mx0, sub1 = mx1 == -INFINITY ? 0.f : mx1;
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            s[nt][0] = exp2f(s[nt][0] - sub0); s[nt][1] = exp2f(s[nt][1] - sub0);
+            s[nt][2] = exp2f(s[nt][2] - sub1); s[nt][3] = exp2f(s[nt][3] - sub1);
+            l0 += s[nt][0] + s[nt][1]; l1 += s[nt][2] + s[nt][3];
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
+        if (drop.on()) {
+            const uint64_t base = tile_pair_base(g, group, h, 0, 0);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                float f0, f1;
+                pair_factors(drop, base + (uint64_t)(r0 * 32 + nt * 4 + tq), f0, f1); s[nt][0] *= f0 * i0; s[nt][1] *= f1 * i0;
+                pair_factors(drop, base + (uint64_t)(r1 * 32 + nt * 4 + tq), f0, f1); s[nt][2] *= f0 * i1; s[nt][3] *= f1 * i1;
+            }
+        } else {
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) { s[nt][0] *= i0; s[nt][1] *= i0; s[nt][2] *= i1; s[nt][3] *= i1; }
+        }
+        float o[8][4] = {};
+        gemm_p_bkn(o, s, Vs, lane);
+        // stage this warp's 16 output rows in its own Q rows (only this warp reads them), then coalesced stores
+        __syncwarp();
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            *reinterpret_cast<uint32_t*>(Qs + r0 * PITCH + nt * 8 + 2 * tq) = pack2(o[nt][0], o[nt][1]);
+            *reinterpret_cast<uint32_t*>(Qs + r1 * PITCH + nt * 8 + 2 * tq) = pack2(o[nt][2], o[nt][3]);
+        }
+        __syncwarp();
+        store_rows16_hs(Qs, warp * 16, out, I, h * 64, hs, lane);
+        if (tq == 0) {
+            if (grow0 >= 0) lse[grow0 * g.H + h] = (mx0 + log2f(l0)) * 0.6931471805599453f;
+            if (grow1 >= 0) lse[grow1 * g.H + h] = (mx1 + log2f(l1)) * 0.6931471805599453f;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(BT, 2) attn_bwd_bf16_heads_kernel(AttnGeom g, const bf16* __restrict__ qkv, const float* __restrict__ lse,
+                                                                    const bf16* __restrict__ d_out, bf16* __restrict__ d_qkv, Drop drop) {
+    extern __shared__ __align__(16) uint8_t smem_h[];
+    bf16* buf = reinterpret_cast<bf16*>(smem_h);                                   // [2][4][TS*PITCH]: Q K V dO
+    bf16* dSs = buf + (size_t)8 * TS * PITCH;
+    HeadsShared& hs = *reinterpret_cast<HeadsShared*>(smem_h + sizeof(bf16) * 9 * TS * PITCH);
+    const int I = g.H * 64;
+    const int64_t ld = 3 * (int64_t)I, group = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+    const int r0 = warp * 16 + gq, r1 = r0 + 8;
+    const float sl2 = g.scale * 1.4426950408889634f;
+    heads_setup(g, group, hs);
+    __syncthreads();
+    const uint32_t mask = fragment_mask(hs, r0, r1, tq);
+    const int64_t grow0 = hs.row[r0], grow1 = hs.row[r1];
+    auto prefetch = [&](int h, int b) {
+        bf16* t = buf + (size_t)b * 4 * TS * PITCH;
+        prefetch_tile(t, qkv, ld, h * 64, hs);
+        prefetch_tile(t + TS * PITCH, qkv, ld, I + h * 64, hs);
+        prefetch_tile(t + 2 * TS * PITCH, qkv, ld, 2 * I + h * 64, hs);
+        prefetch_tile(t + 3 * TS * PITCH, d_out, I, h * 64, hs);
+        cp_async_commit();
+    };
+    prefetch(0, 0);
+    for (int h = 0; h < g.H; ++h) {
+        const int b = h & 1;
+        cp_async_wait_all();
+        __syncthreads();
+        if (h + 1 < g.H) prefetch(h + 1, b ^ 1);
+        bf16* Qs = buf + (size_t)b * 4 * TS * PITCH; bf16* Ks = Qs + TS * PITCH; bf16* Vs = Ks + TS * PITCH; bf16* dOs = Vs + TS * PITCH;
+        const float L0 = grow0 >= 0 ? lse[grow0 * g.H + h] * 1.4426950408889634f : 0.f;
+        const float L1 = grow1 >= 0 ? lse[grow1 * g.H + h] * 1.4426950408889634f : 0.f;
+        float s[8][4] = {}, dp[8][4] = {};
+        gemm_a_bnk(s, Qs, warp * 16, Ks, lane);
+        gemm_a_bnk(dp, dOs, warp * 16, Vs, lane);
+        // P, Pf = P*f (kept in dp[]), D_i = sum_j Pf_ij dP_ij  (== dO_i . O_i), dS (kept in s[])
+        float D0 = 0.f, D1 = 0.f;
+        uint32_t pf_pack[8][2];
+        const uint64_t base = tile_pair_base(g, group, h, 0, 0);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            float f[4] = {1.f, 1.f, 1.f, 1.f};
+            if (drop.on()) {
+                pair_factors(drop, base + (uint64_t)(r0 * 32 + nt * 4 + tq), f[0], f[1]);
+                pair_factors(drop, base + (uint64_t)(r1 * 32 + nt * 4 + tq), f[2], f[3]);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float p = (mask >> (4 * nt + e)) & 1u ? exp2f(s[nt][e] * sl2 - (e < 2 ? L0 : L1)) : 0.f;
+                const float pf = p * f[e];
+                const float t = pf * dp[nt][e];
+                if (e < 2) D0 += t; else D1 += t;
+                s[nt][e] = p;          // P
+                dp[nt][e] = f[e] * dp[nt][e];   // f * dP
+                f[e] = pf;
+            }
+            // f[] now holds Pf for this n-tile; keep it as bf16 pairs for the smem write after barrier (A)
+            pf_pack[nt][0] = pack2(f[0], f[1]);
+            pf_pack[nt][1] = pack2(f[2], f[3]);
+        }
+        D0 += __shfl_xor_sync(0xffffffffu, D0, 1); D0 += __shfl_xor_sync(0xffffffffu, D0, 2);
+        D1 += __shfl_xor_sync(0xffffffffu, D1, 1); D1 += __shfl_xor_sync(0xffffffffu, D1, 2);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            s[nt][0] = s[nt][0] * (dp[nt][0] - D0) * g.scale; s[nt][1] = s[nt][1] * (dp[nt][1] - D0) * g.scale;
+            s[nt][2] = s[nt][2] * (dp[nt][2] - D1) * g.scale; s[nt][3] = s[nt][3] * (dp[nt][3] - D1) * g.scale;
+        }
+        __syncthreads();   // (A) every warp has finished reading V: its region now receives Pf
+        bf16* Ps = Vs;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int c = nt * 8 + 2 * tq;
+            *reinterpret_cast<uint32_t*>(Ps + r0 * PITCH + c) = pf_pack[nt][0];
+            *reinterpret_cast<uint32_t*>(Ps + r1 * PITCH + c) = pf_pack[nt][1];
+            *reinterpret_cast<uint32_t*>(dSs + r0 * PITCH + c) = pack2(s[nt][0], s[nt][1]);
+            *reinterpret_cast<uint32_t*>(dSs + r1 * PITCH + c) = pack2(s[nt][2], s[nt][3]);
+        }
+        float dq[8][4] = {};
+        gemm_p_bkn(dq, s, Ks, lane);                       // dQ[16 rows] = dS . K
+        __syncthreads();   // (B) Pf / dS tiles complete
+        float dv[8][4] = {}, dk[8][4] = {};
+        gemm_at_bkn(dv, Ps, warp * 16, dOs, lane);         // dV[16 keys] = (P f)^T . dO
+        gemm_at_bkn(dk, dSs, warp * 16, Qs, lane);         // dK[16 keys] = dS^T . Q
+        __syncthreads();   // (C) Q / K / Pf tiles are dead: reuse them as staging for coalesced stores
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int c = nt * 8 + 2 * tq;
+            *reinterpret_cast<uint32_t*>(Qs + r0 * PITCH + c) = pack2(dq[nt][0], dq[nt][1]);
+            *reinterpret_cast<uint32_t*>(Qs + r1 * PITCH + c) = pack2(dq[nt][2], dq[nt][3]);
+            *reinterpret_cast<uint32_t*>(Ks + r0 * PITCH + c) = pack2(dk[nt][0], dk[nt][1]);
+            *reinterpret_cast<uint32_t*>(Ks + r1 * PITCH + c) = pack2(dk[nt][2], dk[nt][3]);
+            *reinterpret_cast<uint32_t*>(Vs + r0 * PITCH + c) = pack2(dv[nt][0], dv[nt][1]);
+            *reinterpret_cast<uint32_t*>(Vs + r1 * PITCH + c) = pack2(dv[nt][2], dv[nt][3]);
+        }
+        __syncwarp();
+        store_rows16_hs(Qs, warp * 16, d_qkv, ld, h * 64, hs, lane);
+        store_rows16_hs(Ks, warp * 16, d_qkv, ld, I + h * 64, hs, lane);
+        store_rows16_hs(Vs, warp * 16, d_qkv, ld, 2 * I + h * 64, hs, lane);
+    }
+}
+
 constexpr size_t kBwdSmem = sizeof(bf16) * 6 * TS * PITCH + sizeof(float) * 2 * TS + sizeof(AttnSmemIdx);
 
 int attention_fwd_bf16(const msst_attn_dims* d, const bf16* qkv, bf16* out, float* lse, cudaStream_t st) {
@@ -341,6 +590,16 @@ int attention_fwd_bf16(const msst_attn_dims* d, const bf16* qkv, bf16* out, floa
     if (int rc = make_attn_geom(d, g, false)) return rc;
     if (g.n_seq == 0) return MSST_OK;
     const Drop drop = make_drop(d->drop_p, d->seed, d->site, d->seed_dev);
+    if (g.tiles == 1) {   // N <= 64: head-looping, cp.async double-buffered kernel
+        static bool attr_set = false;
+        if (!attr_set) {
+            MSST_CUDA(cudaFuncSetAttribute(attn_fwd_bf16_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdHeadsSmem));
+            attr_set = true;
+        }
+        attn_fwd_bf16_heads_kernel<<<(unsigned)g.groups, BT, kFwdHeadsSmem, st>>>(g, qkv, out, lse, drop);
+        MSST_LAUNCH_CHECK();
+        return MSST_OK;
+    }
     attn_fwd_bf16_kernel<<<dim3((unsigned)(g.groups * g.tiles), g.H), BT, 0, st>>>(g, qkv, out, lse, drop);
     MSST_LAUNCH_CHECK();
     return MSST_OK;
@@ -361,7 +620,12 @@ int attention_bwd_bf16(const msst_attn_dims* d, const bf16* qkv, const bf16* out
         attr_set = true;
     }
     if (g.tiles == 1) {
-        attn_bwd_bf16_kernel<0><<<grid, BT, kBwdSmem, st>>>(g, qkv, out, lse, d_out, d_qkv, drop);
+        static bool hattr = false;
+        if (!hattr) {
+            MSST_CUDA(cudaFuncSetAttribute(attn_bwd_bf16_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdHeadsSmem));
+            hattr = true;
+        }
+        attn_bwd_bf16_heads_kernel<<<(unsigned)g.groups, BT, kBwdHeadsSmem, st>>>(g, qkv, lse, d_out, d_qkv, drop);
         MSST_LAUNCH_CHECK();
     } else {   // long sequences: dQ pass over key tiles, dK/dV pass over query tiles (no atomics)
         attn_bwd_bf16_kernel<1><<<grid, BT, kBwdSmem, st>>>(g, qkv, out, lse, d_out, d_qkv, drop);

@@ -114,8 +114,7 @@ int layernorm_bwd(const float* x, const float* w, const float* stats, const floa
     MSST_REQUIRE(D >= 1 && D <= 256, "layernorm: D=%d out of range [1,256]", D);
     if (rows == 0) return MSST_OK;
     const int nj = (D + 31) / 32;
-    int grid = ln_grid(rows);
-    if (grid > 2 * kNumSMs) grid = 2 * kNumSMs;   // fewer CTAs -> fewer dw/db atomics
+    const int grid = ln_grid(rows);   // up to 8 CTAs/SM: the row loop is a dependent chain, memory-level parallelism comes from warps
 #define MSST_LN(NJ)                                                                                  \
     if (nj <= NJ) {                                                                                  \
         ln_bwd_kernel<NJ><<<grid, kLnThreads, 0, st>>>(x, w, stats, dy, dx_add, dx, dw, db, rows, D); \
