@@ -8,21 +8,24 @@
 //
 // Reference call sites: nn.Linear to_qkv / to_out / net.0 / net.3 (src/vit_spatial_spectral.py:35-41,59-65) and their
 // autograd.  Structure: persistent warp-specialised CTA (1 per SM): warp 0 = TMA producer, warp 1 = MMA issuer
-// (one elected thread), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> global).
+// (one elected thread), warp 2 = TMEM allocator, warps 4-11 = epilogue (TMEM -> registers -> smem transpose -> global).
 // smem ring of 4 stages (A 128x64 + B BNx64 bf16, SWIZZLE_128B), two TMEM accumulator stages so the epilogue of
 // tile i overlaps the loads + MMAs of tile i+1.  K is tiny in this model (64..512, 1536 for one dgrad), the kernels
 // are HBM-bound: algorithmic bytes per launch = 2(MK + NK) + out_bytes*MN (+ 4MN residual).
 #include "common.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
+#include <stdlib.h>
 
 namespace msst {
 using namespace ptx;
 
 constexpr int GB_M = 128;          // UMMA M (rows of A per tile) -- accumulator row i lives in TMEM lane i
 constexpr int GB_K = 64;           // bf16 elements per k-block = 128 B = one SWIZZLE_128B row
-constexpr int GB_STAGES = 4;
-constexpr int GB_THREADS = 256;
+constexpr int GB_STAGES = 3;            // 3 x (16 KB A + <=32 KB B) + 36 KB epilogue staging < 227 KB
+constexpr int GB_THREADS = 384;       // TMA, MMA, TMEM-alloc, spare + 8 epilogue warps
+constexpr int GB_EPI_PITCH = 36;       // floats per staged row (32 + 4: keeps float4 alignment, conflict-free)
+constexpr int GB_EPI_SMEM = 8 * 32 * GB_EPI_PITCH * 4;
 constexpr uint32_t GB_A_BYTES = GB_M * GB_K * 2;   // 16 KB
 
 struct GemmTnParams {
@@ -31,6 +34,7 @@ struct GemmTnParams {
     uint32_t idesc, tmem_cols;
     const float* bias; const float* residual; void* out; int out_fp32;
     __nv_bfloat16* pre_act; const __nv_bfloat16* aux; int act; Drop drop;
+    int debug;   // MSST_GEMM_DEBUG bits (profiling experiments only): 1 skip global stores, 2 skip epilogue body, 4 skip MMA issue
 };
 
 struct alignas(8) GemmBars {
@@ -43,6 +47,129 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+
+// Epilogue body for one staged chunk (32 rows x 32 fp32 in smem): lane -> (row sub_r + 4i, columns c4..c4+3).
+// MODE selects a compile-time specialisation of the common operator shapes (lean instruction stream -- the epilogue is
+// the throughput limiter of these small-K GEMMs); MODE 5 is the fully general path.
+//   0: bf16 out                         (QKV projection, dO data-gradient)
+//   1: fp32 out                         (data-gradients that feed LayerNorm backward)
+//   2: fp32 out = acc + bias [dropout] + residual      (out-projection, MLP second linear)
+//   3: bf16 out = [dropout] gelu(acc + bias), pre_act = acc + bias   (MLP first linear)
+//   4: bf16 out = acc * gelu'(aux) [dropout]            (data-gradient through the MLP hidden layer)
+// residual (MODE 2) / GELU' argument (MODE 4) of this lane's 8 row segments, fetched BEFORE the accumulator is waited for:
+// the loads must not sit between the stores of the main loop (possible aliasing would serialise them on DRAM latency).
+template <int MODE>
+__device__ __forceinline__ void epilogue_prefetch(const GemmTnParams& p, int64_t row_base, int col0, int sub_r, int c4, float4 (&pre)[8]) {
+    if (MODE != 2 && MODE != 4) return;
+    const int col = col0 + c4;
+    const int64_t rows_left = p.M - row_base;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + sub_r;
+        pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rr < rows_left && col < p.N) {
+            const int64_t off = (row_base + rr) * p.N + col;
+            if (MODE == 2) pre[i] = *reinterpret_cast<const float4*>(p.residual + off);
+            else { const uint2 u = *reinterpret_cast<const uint2*>(p.aux + off); pre[i].x = __uint_as_float(u.x); pre[i].y = __uint_as_float(u.y); }
+        }
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void epilogue_rows(const GemmTnParams& p, const float* stg, int64_t row_base, int col0, int sub_r, int c4,
+                                              const float4 (&pre)[8]) {
+    const int col = col0 + c4;
+    if (MODE != 5) {
+        if (col >= p.N) return;            // N % 4 == 0 in the specialised modes: a float4 is all-in or all-out
+        float b4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (MODE == 2 || MODE == 3) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+            b4[0] = t.x; b4[1] = t.y; b4[2] = t.z; b4[3] = t.w;
+        }
+        const bool drop_on = (MODE >= 2) && p.drop.on();
+        const int64_t rows_left = p.M - row_base;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + sub_r;
+            if (rr >= rows_left) continue;
+            const float4 a4 = *reinterpret_cast<const float4*>(stg + rr * GB_EPI_PITCH + c4);
+            float f[4] = {a4.x + b4[0], a4.y + b4[1], a4.z + b4[2], a4.w + b4[3]};
+            const int64_t off = (row_base + rr) * p.N + col;
+            if (MODE == 3) {
+                *reinterpret_cast<uint2*>(p.pre_act + off) = make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
+#pragma unroll
+                for (int t = 0; t < 4; ++t) f[t] = gelu_erf(f[t]);
+            }
+            if (MODE == 4) {
+                const uint32_t ux = __float_as_uint(pre[i].x), uy = __float_as_uint(pre[i].y);
+                const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&ux), h1 = *reinterpret_cast<const __nv_bfloat162*>(&uy);
+                f[0] *= gelu_erf_grad(__low2float(h0)); f[1] *= gelu_erf_grad(__high2float(h0));
+                f[2] *= gelu_erf_grad(__low2float(h1)); f[3] *= gelu_erf_grad(__high2float(h1));
+            }
+            if (drop_on) {
+                float d4[4];
+                drop_factor4(p.drop, (uint64_t)off >> 2, d4);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) f[t] *= d4[t];
+            }
+            if (MODE == 2) { f[0] += pre[i].x; f[1] += pre[i].y; f[2] += pre[i].z; f[3] += pre[i].w; }
+            if (p.debug & 1) continue;
+            if (MODE == 1 || MODE == 2) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = make_float4(f[0], f[1], f[2], f[3]);
+            else *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
+        }
+        return;
+    }
+    // ---- general path ----
+    const bool n4 = (p.N & 3) == 0;
+    const bool cfull = n4 && (col + 4 <= p.N);
+    float bias4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.bias) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) if (col + t < p.N) bias4[t] = __ldg(p.bias + col + t);
+    }
+#pragma unroll 2
+    for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + sub_r;
+        const int64_t row = row_base + rr;
+        if (row >= p.M || col >= p.N) continue;
+        const float4 a4 = *reinterpret_cast<const float4*>(stg + rr * GB_EPI_PITCH + c4);
+        float f[4] = {a4.x + bias4[0], a4.y + bias4[1], a4.z + bias4[2], a4.w + bias4[3]};
+        const int64_t off = row * p.N + col;
+        if (p.pre_act) {
+            if (cfull) *reinterpret_cast<uint2*>(p.pre_act + off) = make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
+            else for (int t = 0; t < 4; ++t) if (col + t < p.N) p.pre_act[off + t] = __float2bfloat16(f[t]);
+        }
+        if (p.act == 1) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) f[t] = gelu_erf(f[t]);
+        } else if (p.act == 2) {
+            for (int t = 0; t < 4; ++t) if (col + t < p.N) f[t] *= gelu_erf_grad(__bfloat162float(p.aux[off + t]));
+        }
+        if (p.drop.on()) {
+            if (n4) {
+                float d4[4];
+                drop_factor4(p.drop, (uint64_t)off >> 2, d4);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) f[t] *= d4[t];
+            } else {
+                for (int t = 0; t < 4; ++t) if (col + t < p.N) f[t] *= drop_factor(p.drop, (uint64_t)(off + t));
+            }
+        }
+        if (p.residual) for (int t = 0; t < 4; ++t) if (col + t < p.N) f[t] += p.residual[off + t];
+        if (p.debug & 1) continue;
+        if (p.out_fp32) {
+            float* o = reinterpret_cast<float*>(p.out) + off;
+            if (cfull) *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+            else for (int t = 0; t < 4; ++t) if (col + t < p.N) o[t] = f[t];
+        } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
+            if (cfull) *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
+            else for (int t = 0; t < 4; ++t) if (col + t < p.N) o[t] = __float2bfloat16(f[t]);
+        }
+    }
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(GB_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmTnParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -56,7 +183,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (warp == 0 && elect_one()) { prefetch_tmap(&tma_a); prefetch_tmap(&tma_b); }
     if (warp == 1 && elect_one()) {
         for (int s = 0; s < GB_STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&bars->tmem_full[s], 1); mbar_init(&bars->tmem_empty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars->tmem_full[s], 1); mbar_init(&bars->tmem_empty[s], 8); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(&bars->tmem_base, p.tmem_cols);
@@ -98,6 +225,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     const uint64_t da = make_smem_desc(sa, 16, 1024), db = make_smem_desc(sa + GB_A_BYTES, 16, 1024);
                     const int rem = p.K - kb * GB_K;
                     const int ksteps = rem >= GB_K ? GB_K / 16 : (rem + 15) / 16;
+                    if (!(p.debug & 4))
                     for (int k = 0; k < ksteps; ++k)   // +32 B per UMMA_K step inside the 128 B swizzle row
                         umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, (kb | k) != 0);
                     umma_commit(&bars->empty[stage]);
@@ -107,108 +235,39 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: TMEM -> registers -> global =====
-        const int q = warp - 4;   // TMEM lane quarter == warp_idx % 4
+        // ===== epilogue: TMEM -> registers -> smem transpose -> coalesced global =====
+        // 8 warps: warp (4 + q + 4*half) owns TMEM lane quarter q and the 32-column chunks c == half (mod 2).
+        // A chunk (32 rows x 32 fp32) is written row-per-thread into a padded smem tile and read back with 8 lanes per
+        // row (float4 each), so every global access of the epilogue (residual / aux loads, stores) covers whole 128-byte
+        // (fp32) or 64-byte (bf16) row segments instead of 32 scattered 16-byte pieces.
+        const int q = (warp - 4) & 3, half = (warp - 4) >> 2;
+        float* stg = reinterpret_cast<float*>(smem + (size_t)GB_STAGES * stage_bytes + 256) + (size_t)(warp - 4) * (32 * GB_EPI_PITCH);
+        const int sub_r = lane >> 3, c4 = (lane & 7) * 4;
         int it = 0;
-        const bool vec_ok = (p.N % 8 == 0);
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
             const int n_blk = (int)(tile % p.tiles_n);
             const int64_t m_blk = tile / p.tiles_n;
-            mbar_wait(&bars->tmem_full[acc], acc_phase);
-            tc_fence_after();
-            const int64_t row = m_blk * GB_M + q * 32 + lane;
-            for (int c = 0; c < p.block_n / 32; ++c) {
+            bool first_chunk = true;     // the accumulator is waited for after the first chunk's operand prefetch is in flight
+            const int64_t row_base = m_blk * GB_M + q * 32;
+            for (int c = half; c < ((p.debug & 2) ? 0 : p.block_n / 32); c += 2) {
+                const int col0 = n_blk * p.block_n + c * 32;
+                float4 pre[8];
+                epilogue_prefetch<MODE>(p, row_base, col0, sub_r, c4, pre);
+                if (first_chunk) { mbar_wait(&bars->tmem_full[acc], acc_phase); tc_fence_after(); first_chunk = false; }
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n + c * 32), v);
                 tmem_ld_wait();
-                const int col0 = n_blk * p.block_n + c * 32;
-                if (row >= p.M || col0 >= p.N) continue;
-                float f[32];
+                if (row_base >= p.M || col0 >= p.N) continue;      // warp-uniform
+                __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                const int64_t off = row * p.N + col0;
-                const bool full = vec_ok && (col0 + 32 <= p.N);
-                if (p.bias) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) if (full || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
-                }
-                if (p.pre_act) {
-                    if (full) {
-#pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            *reinterpret_cast<uint4*>(p.pre_act + off + g * 8) =
-                                make_uint4(pack_bf16(f[g * 8], f[g * 8 + 1]), pack_bf16(f[g * 8 + 2], f[g * 8 + 3]),
-                                           pack_bf16(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16(f[g * 8 + 6], f[g * 8 + 7]));
-                    } else {
-                        for (int j = 0; j < 32; ++j) if (col0 + j < p.N) p.pre_act[off + j] = __float2bfloat16(f[j]);
-                    }
-                }
-                if (p.act == 1) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-                } else if (p.act == 2) {
-                    if (full) {
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const uint4 u = *reinterpret_cast<const uint4*>(p.aux + off + g * 8);
-                            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[t]);
-                                f[g * 8 + 2 * t] *= gelu_erf_grad(__low2float(h));
-                                f[g * 8 + 2 * t + 1] *= gelu_erf_grad(__high2float(h));
-                            }
-                        }
-                    } else {
-                        for (int j = 0; j < 32; ++j) if (col0 + j < p.N) f[j] *= gelu_erf_grad(__bfloat162float(p.aux[off + j]));
-                    }
-                }
-                if (p.drop.on()) {
-                    if ((p.N & 3) == 0) {
-#pragma unroll
-                        for (int g = 0; g < 8; ++g) {
-                            float d4[4];
-                            drop_factor4(p.drop, (uint64_t)(off + g * 4) >> 2, d4);
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) f[g * 4 + t] *= d4[t];
-                        }
-                    } else {
-                        for (int j = 0; j < 32; ++j) if (col0 + j < p.N) f[j] *= drop_factor(p.drop, (uint64_t)(off + j));
-                    }
-                }
-                if (p.residual) {
-                    if (full) {
-#pragma unroll
-                        for (int g = 0; g < 8; ++g) {
-                            const float4 r = *reinterpret_cast<const float4*>(p.residual + off + g * 4);
-                            f[g * 4] += r.x; f[g * 4 + 1] += r.y; f[g * 4 + 2] += r.z; f[g * 4 + 3] += r.w;
-                        }
-                    } else {
-                        for (int j = 0; j < 32; ++j) if (col0 + j < p.N) f[j] += p.residual[off + j];
-                    }
-                }
-                if (p.out_fp32) {
-                    float* o = reinterpret_cast<float*>(p.out) + off;
-                    if (full) {
-#pragma unroll
-                        for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(o + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
-                    } else {
-                        for (int j = 0; j < 32; ++j) if (col0 + j < p.N) o[j] = f[j];
-                    }
-                } else {
-                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
-                    if (full) {
-#pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            *reinterpret_cast<uint4*>(o + g * 8) =
-                                make_uint4(pack_bf16(f[g * 8], f[g * 8 + 1]), pack_bf16(f[g * 8 + 2], f[g * 8 + 3]),
-                                           pack_bf16(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16(f[g * 8 + 6], f[g * 8 + 7]));
-                    } else {
-                        for (int j = 0; j < 32; ++j) if (col0 + j < p.N) o[j] = __float2bfloat16(f[j]);
-                    }
-                }
+                for (int g8 = 0; g8 < 8; ++g8)
+                    *reinterpret_cast<float4*>(stg + lane * GB_EPI_PITCH + g8 * 4) =
+                        make_float4(__uint_as_float(v[g8 * 4]), __uint_as_float(v[g8 * 4 + 1]), __uint_as_float(v[g8 * 4 + 2]), __uint_as_float(v[g8 * 4 + 3]));
+                __syncwarp();
+                epilogue_rows<MODE>(p, stg, row_base, col0, sub_r, c4, pre);
             }
+            if (first_chunk) { mbar_wait(&bars->tmem_full[acc], acc_phase); tc_fence_after(); }   // warp had no chunk in this tile
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
@@ -235,7 +294,8 @@ struct WgradParams {
     float* dW;
 };
 
-__global__ void __launch_bounds__(GB_THREADS, 1)
+constexpr int WG_THREADS = 256;   // TMA, MMA, TMEM-alloc, spare + 4 epilogue warps
+__global__ void __launch_bounds__(WG_THREADS, 1)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tma_dy, const __grid_constant__ CUtensorMap tma_x, const WgradParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -365,18 +425,37 @@ int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st) {
     p.tmem_cols = pow2_cols(2 * p.block_n);
     p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.out_fp32 = a.out_fp32; p.pre_act = a.pre_act; p.aux = a.aux;
     p.act = a.act; p.drop = a.drop;
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MSST_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
     CUtensorMap ta, tb;
     if (int rc = make_tmap(&ta, a.A, a.M, a.K, a.K, GB_M)) return rc;
     if (int rc = make_tmap(&tb, a.B, a.N, a.K, a.K, p.block_n)) return rc;
-    const size_t smem = (size_t)GB_STAGES * (GB_A_BYTES + (size_t)p.block_n * GB_K * 2) + sizeof(GemmBars) + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MSST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
+    const size_t smem = (size_t)GB_STAGES * (GB_A_BYTES + (size_t)p.block_n * GB_K * 2) + 256 + GB_EPI_SMEM + 1024;
+    int mode = 5;
+    const bool vec = (a.N % 4 == 0);
+    if (vec && !a.pre_act && !a.bias && !a.residual && a.act == 0 && !a.drop.on()) mode = a.out_fp32 ? 1 : 0;
+    else if (vec && a.out_fp32 && a.bias && a.residual && a.act == 0 && !a.pre_act) mode = 2;
+    else if (vec && !a.out_fp32 && a.bias && a.act == 1 && a.pre_act && !a.residual) mode = 3;
+    else if (vec && !a.out_fp32 && !a.bias && a.act == 2 && a.aux && !a.residual && !a.pre_act) mode = 4;
     const int64_t tiles = p.tiles_m * p.tiles_n;
     const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-    gemm_tn_kernel<<<grid, GB_THREADS, smem, st>>>(ta, tb, p);
+    static bool attr_set = false;
+    if (!attr_set) {
+        MSST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MSST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MSST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MSST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MSST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MSST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    switch (mode) {
+        case 0: gemm_tn_kernel<0><<<grid, GB_THREADS, smem, st>>>(ta, tb, p); break;
+        case 1: gemm_tn_kernel<1><<<grid, GB_THREADS, smem, st>>>(ta, tb, p); break;
+        case 2: gemm_tn_kernel<2><<<grid, GB_THREADS, smem, st>>>(ta, tb, p); break;
+        case 3: gemm_tn_kernel<3><<<grid, GB_THREADS, smem, st>>>(ta, tb, p); break;
+        case 4: gemm_tn_kernel<4><<<grid, GB_THREADS, smem, st>>>(ta, tb, p); break;
+        default: gemm_tn_kernel<5><<<grid, GB_THREADS, smem, st>>>(ta, tb, p); break;
+    }
     MSST_LAUNCH_CHECK();
     return MSST_OK;
 }
@@ -409,7 +488,7 @@ int gemm_wgrad_bf16(const __nv_bfloat16* dy, const __nv_bfloat16* x, float* dW, 
         MSST_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    gemm_wgrad_kernel<<<dim3(out_tiles, (unsigned)splits), GB_THREADS, smem, st>>>(ta, tb, p);
+    gemm_wgrad_kernel<<<dim3(out_tiles, (unsigned)splits), WG_THREADS, smem, st>>>(ta, tb, p);
     MSST_LAUNCH_CHECK();
     return MSST_OK;
 }
