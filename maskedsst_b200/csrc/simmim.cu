@@ -63,13 +63,17 @@ __global__ void __launch_bounds__(1024) loss_reduce_kernel(const float* __restri
     }
 }
 
-template <int NJ>
+// Backward.  Each warp walks a CONTIGUOUS run of (sample, masked-token) items; gradients of the decoder weights are
+// accumulated in registers for the current spectral block and flushed (shared-memory atomics when the [n_wb][P][D] table
+// fits, else global atomics) only when the block changes -- with the reference's mask generators the indices of a row are
+// ascending, so a run of ~nm/C items shares one block.  d_enc is a scatter-add (duplicate indices are legal).
+template <int NJ, int PMAX>
 __global__ void __launch_bounds__(DT) decode_bwd_kernel(DecGeom g, const float* __restrict__ enc, const int64_t* __restrict__ idx,
                                                         const float* __restrict__ img, const float* __restrict__ tgt_tok,
                                                         const float* __restrict__ W, const float* __restrict__ bias,
                                                         const float* __restrict__ d_loss, float coef, float* __restrict__ d_enc,
                                                         float* __restrict__ d_W, float* __restrict__ d_bias,
-                                                        float* __restrict__ d_tgt, int use_smem) {
+                                                        float* __restrict__ d_tgt, int use_smem, int items_per_warp) {
     extern __shared__ float acc[];     // [n_wb][P][D] + [n_wb][P] when use_smem
     const int nacc = g.n_wb * g.P * g.D, nb = g.n_wb * g.P;
     if (use_smem) {
@@ -81,37 +85,61 @@ __global__ void __launch_bounds__(DT) decode_bwd_kernel(DecGeom g, const float* 
     const int lane = threadIdx.x & 31;
     const float gscale = coef * d_loss[0];
     const int64_t total = (int64_t)g.B * g.nm;
-    for (int64_t it = (int64_t)blockIdx.x * (DT / 32) + (threadIdx.x >> 5); it < total; it += (int64_t)gridDim.x * (DT / 32)) {
+    const int64_t warp_id = (int64_t)blockIdx.x * (DT / 32) + (threadIdx.x >> 5);
+    const int64_t it0 = warp_id * items_per_warp;
+    const int64_t it1 = it0 + items_per_warp < total ? it0 + items_per_warp : total;
+    float aW[PMAX][NJ], aB[PMAX];
+#pragma unroll
+    for (int p = 0; p < PMAX; ++p) {
+        aB[p] = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) aW[p][j] = 0.f;
+    }
+    int cur_blk = -1;
+    auto flush = [&]() {
+        if (cur_blk < 0) return;
+#pragma unroll
+        for (int p = 0; p < PMAX; ++p) {
+            if (p < g.P) {
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    if (aW[p][j] != 0.f) atomicAdd(accW + ((int64_t)cur_blk * g.P + p) * g.D + lane + 32 * j, aW[p][j]);
+                    aW[p][j] = 0.f;
+                }
+                if (lane == 0 && aB[p] != 0.f) atomicAdd(accB + cur_blk * g.P + p, aB[p]);
+                aB[p] = 0.f;
+            }
+        }
+    };
+    for (int64_t it = it0; it < it1; ++it) {
         const int b = (int)(it / g.nm);
         const int t = (int)idx[it];
         const int blk = g.n_wb == 1 ? 0 : t / g.S;
+        if (blk != cur_blk) { flush(); cur_blk = blk; }
         float e[NJ], de[NJ];
 #pragma unroll
         for (int j = 0; j < NJ; ++j) { e[j] = enc[((int64_t)b * g.T + t) * g.D + lane + 32 * j]; de[j] = 0.f; }
-        for (int p = 0; p < g.P; ++p) {
-            const float* w = W + ((int64_t)blk * g.P + p) * g.D;
-            float wv[NJ], a = 0.f;
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) { wv[j] = __ldg(w + lane + 32 * j); a = fmaf(e[j], wv[j], a); }
-            a = warp_sum(a) + bias[blk * g.P + p];
-            const float tg = tgt_tok ? tgt_tok[((int64_t)b * g.T + t) * g.P + p] : target_pixel(g, img, b, t, p);
-            const float diff = a - tg;
-            const float gp = diff > 0.f ? gscale : (diff < 0.f ? -gscale : 0.f);
-            if (gp != 0.f) {
+        for (int p = 0; p < PMAX; ++p) {
+            if (p < g.P) {
+                const float* w = W + ((int64_t)blk * g.P + p) * g.D;
+                float wv[NJ], a = 0.f;
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) {
-                    atomicAdd(accW + ((int64_t)blk * g.P + p) * g.D + lane + 32 * j, gp * e[j]);
-                    de[j] = fmaf(gp, wv[j], de[j]);
-                }
-                if (lane == 0) {
-                    atomicAdd(accB + blk * g.P + p, gp);
-                    if (d_tgt) atomicAdd(d_tgt + ((int64_t)b * g.T + t) * g.P + p, -gp);
-                }
+                for (int j = 0; j < NJ; ++j) { wv[j] = __ldg(w + lane + 32 * j); a = fmaf(e[j], wv[j], a); }
+                a = warp_sum(a) + bias[blk * g.P + p];
+                const float tg = tgt_tok ? tgt_tok[((int64_t)b * g.T + t) * g.P + p] : target_pixel(g, img, b, t, p);
+                const float diff = a - tg;
+                const float gp = diff > 0.f ? gscale : (diff < 0.f ? -gscale : 0.f);
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) { aW[p][j] = fmaf(gp, e[j], aW[p][j]); de[j] = fmaf(gp, wv[j], de[j]); }
+                aB[p] += gp;
+                if (d_tgt && lane == 0 && gp != 0.f) atomicAdd(d_tgt + ((int64_t)b * g.T + t) * g.P + p, -gp);
             }
         }
 #pragma unroll
         for (int j = 0; j < NJ; ++j) atomicAdd(d_enc + ((int64_t)b * g.T + t) * g.D + lane + 32 * j, de[j]);
     }
+    flush();
     if (use_smem) {
         __syncthreads();
         for (int i = threadIdx.x; i < nacc; i += DT) if (acc[i] != 0.f) atomicAdd(d_W + i, acc[i]);
@@ -159,18 +187,21 @@ extern "C" int msst_simmim_decode_l1_bwd(const msst_decode_dims* d, const float*
     if (int rc = make_geom(d, g)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t total = (int64_t)g.B * g.nm;
+    MSST_REQUIRE(g.P <= 16, "simmim_decode_bwd: pixels per patch %d > 16 unsupported", g.P);
     const size_t smem = sizeof(float) * ((size_t)g.n_wb * g.P * g.D + (size_t)g.n_wb * g.P);
-    const int use_smem = smem <= 200 * 1024;
-    int64_t grid = ceil_div(total, DT / 32);
-    if (grid > kNumSMs) grid = kNumSMs;
+    const int use_smem = smem <= 100 * 1024;     // two CTAs per SM
+    // contiguous runs of items per warp: long enough to amortise the flushes, short enough to fill 2 CTAs x 148 SMs
+    int64_t ipw = ceil_div(total, (int64_t)2 * kNumSMs * (DT / 32));
+    if (ipw < 8) ipw = 8;
+    const int64_t grid = ceil_div(ceil_div(total, ipw), DT / 32);
     const float coef = (float)(1.0 / ((double)total * g.P) / (double)g.nm);
 #define MSST_D(NJ)                                                                                                              \
     case NJ:                                                                                                                    \
-        if (use_smem) MSST_CUDA(cudaFuncSetAttribute(decode_bwd_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        decode_bwd_kernel<NJ><<<(int)grid, DT, use_smem ? smem : 0, st>>>(g, enc, idx, img, target_tokens, W, bias, d_loss, coef, \
-                                                                         d_enc, d_W, d_bias, d_target_tokens, use_smem);        \
+        if (use_smem) MSST_CUDA(cudaFuncSetAttribute(decode_bwd_kernel<NJ, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        decode_bwd_kernel<NJ, 16><<<(int)grid, DT, use_smem ? smem : 0, st>>>(g, enc, idx, img, target_tokens, W, bias, d_loss, coef, \
+                                                                             d_enc, d_W, d_bias, d_target_tokens, use_smem, (int)ipw); \
         break;
-    switch (g.D / 32) { MSST_D(1) MSST_D(2) MSST_D(3) MSST_D(4) MSST_D(6) MSST_D(8) default: set_error("simmim_decode: D unsupported"); return MSST_ERR_ARG; }
+    switch (g.D / 32) { MSST_D(1) MSST_D(2) MSST_D(3) MSST_D(4) default: set_error("simmim_decode: D unsupported"); return MSST_ERR_ARG; }
 #undef MSST_D
     MSST_LAUNCH_CHECK();
     return MSST_OK;

@@ -17,7 +17,7 @@ static inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 struct TfLayout {
     int64_t R; int I;
-    size_t o_stats1, o_stats2, o_qkv, o_o, o_lse, o_xmid, o_u, o_g, o_xout, layer_bytes;
+    size_t o_stats1, o_stats2, o_qkv, o_o, o_lse, o_xmid, o_u, o_g, o_xout, o_h1, o_h2, layer_bytes;
     size_t o_wq, o_wqT, o_wo, o_woT, o_w1, o_w1T, o_w2, o_w2T, wlayer_bytes, w_base;   // bf16 mode: per-layer bf16 weight copies
     size_t s_h, s_dqkv, s_do, s_du, s_dh, s_dy, s_dxa, s_dxb, total;
     int layer_slots;
@@ -33,6 +33,10 @@ static TfLayout make_layout(const msst_tf_dims* d) {
     L.o_stats1 = take(R * 2 * f); L.o_stats2 = take(R * 2 * f);
     L.o_qkv = take(R * 3 * L.I * a); L.o_o = take(R * L.I * a); L.o_lse = take(R * d->H * f);
     L.o_xmid = take(R * d->D * f); L.o_u = take(R * d->M * a); L.o_g = take(R * d->M * a); L.o_xout = take(R * d->D * f);
+    L.o_h1 = L.o_h2 = 0;
+    if (d->prec == MSST_PREC_BF16 && d->save_for_backward) {   // LN outputs (bf16): 2 x 2D B/token saves 2 LN passes in backward
+        L.o_h1 = take(R * d->D * a); L.o_h2 = take(R * d->D * a);
+    }
     L.layer_bytes = off;
     L.layer_slots = d->save_for_backward ? d->L : 1;
     off = L.layer_bytes * L.layer_slots;
@@ -108,15 +112,17 @@ static int tf_fwd_bf16(const msst_tf_dims* d, const msst_layer_params* layers, c
         float* xmid = (float*)(lw + L.o_xmid); bf16* u = (bf16*)(lw + L.o_u); bf16* g = (bf16*)(lw + L.o_g);
         float* y = (l == d->L - 1) ? x_out : (float*)(lw + L.o_xout);
         const uint32_t site = d->site_base + 8u * l;
-        if (int rc = layernorm_fwd(x, p.ln1_w, p.ln1_b, h, 1, stats1, R, D, 1e-5f, st)) return rc;
-        if (int rc = gemm_tn_bf16(gemm_args(h, w.wq, R, 3 * I, D, qkv, 0), st)) return rc;
+        bf16* h1 = d->save_for_backward ? (bf16*)(lw + L.o_h1) : h;
+        bf16* h2 = d->save_for_backward ? (bf16*)(lw + L.o_h2) : h;
+        if (int rc = layernorm_fwd(x, p.ln1_w, p.ln1_b, h1, 1, stats1, R, D, 1e-5f, st)) return rc;
+        if (int rc = gemm_tn_bf16(gemm_args(h1, w.wq, R, 3 * I, D, qkv, 0), st)) return rc;
         msst_attn_dims ad{d->n_seq, d->N, d->inner, d->H, d->dh, d->drop_p, d->seed, site + kSiteAttnProb, d->prec, d->seed_dev};
         if (int rc = attention_fwd_bf16(&ad, qkv, o, lse, st)) return rc;
         GemmBf16Args a = gemm_args(o, w.wo, R, D, I, xmid, 1);
         a.bias = p.b_out; a.residual = x; a.drop = make_drop(d->drop_p, d->seed, site + kSiteAttnOut, d->seed_dev);
         if (int rc = gemm_tn_bf16(a, st)) return rc;
-        if (int rc = layernorm_fwd(xmid, p.ln2_w, p.ln2_b, h, 1, stats2, R, D, 1e-5f, st)) return rc;
-        a = gemm_args(h, w.w1, R, M, D, g, 0);
+        if (int rc = layernorm_fwd(xmid, p.ln2_w, p.ln2_b, h2, 1, stats2, R, D, 1e-5f, st)) return rc;
+        a = gemm_args(h2, w.w1, R, M, D, g, 0);
         a.bias = p.b1; a.pre_act = u; a.act = 1; a.drop = make_drop(d->drop_p, d->seed, site + kSiteMlpHidden, d->seed_dev);
         if (int rc = gemm_tn_bf16(a, st)) return rc;
         a = gemm_args(g, w.w2, R, D, M, y, 1);
@@ -132,7 +138,7 @@ static int tf_bwd_bf16(const msst_tf_dims* d, const msst_layer_params* layers, c
     const TfLayout L = make_layout(d);
     const int64_t R = L.R;
     const int D = d->D, I = L.I, M = d->M;
-    bf16* h = (bf16*)(ws + L.s_h); bf16* dqkv = (bf16*)(ws + L.s_dqkv); bf16* dO = (bf16*)(ws + L.s_do);
+    bf16* dqkv = (bf16*)(ws + L.s_dqkv); bf16* dO = (bf16*)(ws + L.s_do);
     bf16* du = (bf16*)(ws + L.s_du); float* dh = (float*)(ws + L.s_dh); bf16* dyb = (bf16*)(ws + L.s_dy);
     float* dxa = (float*)(ws + L.s_dxa); float* dxb = (float*)(ws + L.s_dxb);
     const float* dcur = d_x_out;
@@ -154,8 +160,7 @@ static int tf_bwd_bf16(const msst_tf_dims* d, const msst_layer_params* layers, c
         a.aux = u; a.act = 2; a.drop = make_drop(d->drop_p, d->seed, site + kSiteMlpHidden, d->seed_dev);
         if (int rc = gemm_tn_bf16(a, st)) return rc;
         if (int rc = cast_rows_bf16(du, nullptr, gr.b1, R, M, none, st)) return rc;
-        if (int rc = layernorm_fwd(xmid, p.ln2_w, p.ln2_b, h, 1, nullptr, R, D, 1e-5f, st)) return rc;
-        if (int rc = gemm_wgrad_bf16(du, h, gr.w1, R, M, D, st)) return rc;
+        if (int rc = gemm_wgrad_bf16(du, (const bf16*)(lw + L.o_h2), gr.w1, R, M, D, st)) return rc;
         if (int rc = gemm_tn_bf16(gemm_args(du, w.w1T, R, D, M, dh, 1), st)) return rc;
         if (int rc = layernorm_bwd(xmid, p.ln2_w, stats2, dh, dcur, dxa, gr.ln2_w, gr.ln2_b, R, D, st)) return rc;
         // ---- attention branch ----
@@ -164,8 +169,7 @@ static int tf_bwd_bf16(const msst_tf_dims* d, const msst_layer_params* layers, c
         if (int rc = gemm_tn_bf16(gemm_args(dyb, w.woT, R, I, D, dO, 0), st)) return rc;
         msst_attn_dims ad{d->n_seq, d->N, d->inner, d->H, d->dh, d->drop_p, d->seed, site + kSiteAttnProb, d->prec, d->seed_dev};
         if (int rc = attention_bwd_bf16(&ad, qkv, o, lse, dO, dqkv, st)) return rc;
-        if (int rc = layernorm_fwd(x, p.ln1_w, p.ln1_b, h, 1, nullptr, R, D, 1e-5f, st)) return rc;
-        if (int rc = gemm_wgrad_bf16(dqkv, h, gr.w_qkv, R, 3 * I, D, st)) return rc;
+        if (int rc = gemm_wgrad_bf16(dqkv, (const bf16*)(lw + L.o_h1), gr.w_qkv, R, 3 * I, D, st)) return rc;
         if (int rc = gemm_tn_bf16(gemm_args(dqkv, w.wqT, R, D, 3 * I, dh, 1), st)) return rc;
         float* dx = (l == 0) ? d_x_in : dxb;
         if (int rc = layernorm_bwd(x, p.ln1_w, stats1, dh, dxa, dx, gr.ln1_w, gr.ln1_b, R, D, st)) return rc;
