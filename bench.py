@@ -37,6 +37,8 @@ def parse():
     ap.add_argument("--dataset", default="houston", choices=["houston", "enmap"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dropout", type=float, default=0.1)
+    ap.add_argument("--workload", default="pretrain", choices=["pretrain", "finetune"],
+                    help="pretrain = BASELINE configs[1] (default); finetune = CE classification step with Adam (configs[2])")
     return ap.parse_args()
 
 
@@ -164,7 +166,15 @@ def run_ours(args):
                                precision=args.precision)
     model = M.SimMIMSpatialSpectral(encoder=enc, masking_ratio=0.7, mask_patch_size=4, tube_masking=True,
                                     to_pixels_per_spectral_block=True).to(dev).train()
-    opt = FusedAdam(model.parameters(), lr=0.008, weight_decay=0.05, decoupled=True, clamp=1.0, grad_scale=1.0 / world)
+    if args.workload == "finetune":   # finetune.py:116-135: Adam + L2, head lr .005 / rest .0005, CE(ignore_index=-1)
+        from maskedsst_b200.dp import cross_entropy_dp
+        model = enc.to(dev).train()
+        head = [p for n, p in model.named_parameters() if "mlp_head" in n]
+        rest = [p for n, p in model.named_parameters() if "mlp_head" not in n]
+        opt = FusedAdam([{"params": head, "lr": 0.005}, {"params": rest, "lr": 0.0005}], lr=0.0005, weight_decay=0.005,
+                        decoupled=False, grad_scale=1.0 / world)
+    else:
+        opt = FusedAdam(model.parameters(), lr=0.008, weight_decay=0.05, decoupled=True, clamp=1.0, grad_scale=1.0 / world)
     if args.precision == "bf16" and hasattr(model, "attach_optimizer"):
         model.attach_optimizer(opt)
 
@@ -176,7 +186,11 @@ def run_ours(args):
         for t in host_x:
             t[:, 48:] = 0
     dev_x = [t.to(dev) for t in host_x]
-    dev_masks = [model.draw_masks(B, dev) for _ in range(pool)]
+    if args.workload == "finetune":
+        host_y = [torch.randint(-1, ncls, (B, 8, 8), generator=g).pin_memory() for _ in range(pool)]
+        dev_y = [t.to(dev) for t in host_y]
+    else:
+        dev_masks = [model.draw_masks(B, dev) for _ in range(pool)]
 
     from maskedsst_b200.dp import GradSync
     sync = GradSync(opt.arena, num_buckets=3) if world > 1 else None
@@ -187,7 +201,10 @@ def run_ours(args):
 
     def step_resident(i):
         opt.zero_grad()
-        loss = model(dev_x[i % pool], masks=dev_masks[i % pool])
+        if args.workload == "finetune":
+            loss = cross_entropy_dp(model(dev_x[i % pool]), dev_y[i % pool], ignore_index=-1)
+        else:
+            loss = model(dev_x[i % pool], masks=dev_masks[i % pool])
         loss.backward()
         allreduce_grads()
         opt.step()
@@ -196,7 +213,10 @@ def run_ours(args):
     def step_e2e(i):
         x = host_x[i % pool].to(dev, non_blocking=True)      # H2D from pinned memory, inside the timed region
         opt.zero_grad()
-        loss = model(x)                                      # public API: masks drawn on the host like the reference
+        if args.workload == "finetune":
+            loss = cross_entropy_dp(model(x), host_y[i % pool].to(dev, non_blocking=True), ignore_index=-1)
+        else:
+            loss = model(x)                                  # public API: model(img); masks drawn inside (see mask_backend)
         loss.backward()
         allreduce_grads()
         opt.step()
@@ -228,20 +248,23 @@ def run_ours(args):
     ms = float(t.item())
     final_loss = float(loss.item())
 
-    # e2e leg
+    # e2e leg: (a) masks drawn on the device (module option mask_backend="device"), (b) the reference-compatible host generator
     e2e_steps = max(3, min(args.steps, 10))
-    for i in range(2):
-        step_e2e(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        step_e2e(i)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    e2e_res = {}
+    for backend in ("device", "host"):
+        model.mask_backend = backend
+        for i in range(2):
+            step_e2e(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            step_e2e(i)
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_res[backend] = float(t.item())
+    e2e_s = e2e_res["device"]
 
     if rank != 0:
         if world > 1:
@@ -256,21 +279,25 @@ def run_ours(args):
     value = world * B * args.steps / (ms / 1e3)
     roof = roofline(args, B, dev, model, peaks)
     line = {
-        "metric": "simmim_pretrain_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "metric": "simmim_pretrain_samples_per_sec" if args.workload == "pretrain" else "finetune_samples_per_sec",
+        "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": f"SimMIM pretrain step (fwd+bwd+AdamW+clamp), ViTSpatialSpectral {ds} shape "
+        "config": {"workload": ("SimMIM pretrain step (fwd+bwd+AdamW+clamp)" if args.workload == "pretrain" else
+                                "finetune step (fwd+CE+bwd+Adam, 2 lr groups)") + f", ViTSpatialSpectral {ds} shape "
                                f"[B,{channels},8,8], dim 96 depth 4+4 heads 8 mlp 64, dropout {args.dropout}, tube mask 0.7/4",
                    "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
                    "l2_policy": "per-step working set (activations ~%.1f GB) exceeds the 126 MB L2; input pool of %d batches"
                                 % (B * (320 if ds == "houston" else 1280) * 37e3 / 1e9, pool),
                    "model_tflops_per_s": value * FLOP_PER_SAMPLE_TRAIN[ds] / 1e12, "final_loss": final_loss},
         "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": "samples/s",
-                "h2d_bytes_per_step": host_x[0].numel() * 4 + B * (channels // 10) * 64 + B * int(0.7 * (channels // 10) * 64) * 8,
-                "d2h_bytes_per_step": 4, "steps": e2e_steps},
+                "h2d_bytes_per_step": host_x[0].numel() * 4, "d2h_bytes_per_step": 4, "steps": e2e_steps,
+                "masks": "drawn on the device inside model(img) (mask_backend='device')",
+                "value_host_masks": world * B * e2e_steps / e2e_res["host"],
+                "host_masks_note": "reference-compatible numpy generator on the host: +B*(T + 8*nm) H2D bytes per step"},
         "gpu_launches": int(launches), "clocks": clk, "roofline": roof,
     }
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and args.workload == "pretrain":
         med, cores, n = cpu_step_time(ds, 32, 8, 1, args.dropout, budget_s=20.0)
         line["cpu_baseline"] = {"value": 32 / med, "unit": "samples/s", "cores": cores, "kind": "port",
                                 "sample": f"{n} timed steps of batch 32 (median) of the same step, torch CPU fp32 oracle port"}

@@ -86,6 +86,59 @@ ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
     }
 }
 
+// ---- generic row width (D > 256, e.g. the spectral-MLP head's LayerNorm(D*C)): lanes stride over the row, re-reading it
+// from L1/L2 instead of caching it in registers ----
+template <bool BF16>
+__global__ void __launch_bounds__(kLnThreads)
+ln_fwd_wide_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, void* __restrict__ y,
+                   float* __restrict__ stats, int64_t rows, int D, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (kLnThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kLnThreads / 32);
+    for (int64_t r = warp0; r < rows; r += nwarps) {
+        const float* xr = x + r * D;
+        float s = 0.f;
+        for (int f = lane; f < D; f += 32) s += xr[f];
+        const float mean = warp_sum(s) / D;
+        float sq = 0.f;
+        for (int f = lane; f < D; f += 32) { const float dl = xr[f] - mean; sq += dl * dl; }
+        const float rstd = rsqrtf(warp_sum(sq) / D + eps);
+        if (stats && lane == 0) { stats[2 * r] = mean; stats[2 * r + 1] = rstd; }
+        for (int f = lane; f < D; f += 32) {
+            const float o = (xr[f] - mean) * rstd * w[f] + b[f];
+            if (BF16) reinterpret_cast<__nv_bfloat16*>(y)[r * D + f] = __float2bfloat16(o);
+            else reinterpret_cast<float*>(y)[r * D + f] = o;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kLnThreads)
+ln_bwd_wide_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ stats,
+                   const float* __restrict__ dy, const float* __restrict__ dx_add, float* __restrict__ dx,
+                   float* __restrict__ dw, float* __restrict__ db, int64_t rows, int D) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (kLnThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kLnThreads / 32);
+    for (int64_t r = warp0; r < rows; r += nwarps) {
+        const float mean = stats[2 * r], rstd = stats[2 * r + 1];
+        const float* xr = x + r * D; const float* dr = dy + r * D;
+        float c1 = 0.f, c2 = 0.f;
+        for (int f = lane; f < D; f += 32) {
+            const float xh = (xr[f] - mean) * rstd, g = dr[f] * w[f];
+            c1 += g; c2 += g * xh;
+            atomicAdd(dw + f, dr[f] * xh);     // wide rows are a rarely used head variant: plain atomics
+            atomicAdd(db + f, dr[f]);
+        }
+        c1 = warp_sum(c1) / D; c2 = warp_sum(c2) / D;
+        for (int f = lane; f < D; f += 32) {
+            const float xh = (xr[f] - mean) * rstd;
+            float o = rstd * (dr[f] * w[f] - c1 - xh * c2);
+            if (dx_add) o += dx_add[r * D + f];
+            dx[r * D + f] = o;
+        }
+    }
+}
+
 static inline int ln_grid(int64_t rows) {
     int64_t blocks = ceil_div(rows, kLnThreads / 32);
     const int64_t cap = (int64_t)kNumSMs * 8;   // 8 resident CTAs of 256 threads per SM
@@ -94,9 +147,15 @@ static inline int ln_grid(int64_t rows) {
 
 int layernorm_fwd(const float* x, const float* w, const float* b, void* y, int y_bf16, float* stats, int64_t rows, int D,
                   float eps, cudaStream_t st) {
-    MSST_REQUIRE(D >= 1 && D <= 256, "layernorm: D=%d out of range [1,256]", D);
+    MSST_REQUIRE(D >= 1, "layernorm: D=%d out of range", D);
     if (rows == 0) return MSST_OK;
     const int nj = (D + 31) / 32, grid = ln_grid(rows);
+    if (D > 256) {
+        if (y_bf16) ln_fwd_wide_kernel<true><<<grid, kLnThreads, 0, st>>>(x, w, b, y, stats, rows, D, eps);
+        else ln_fwd_wide_kernel<false><<<grid, kLnThreads, 0, st>>>(x, w, b, y, stats, rows, D, eps);
+        MSST_LAUNCH_CHECK();
+        return MSST_OK;
+    }
 #define MSST_LN(NJ)                                                                                            \
     if (nj <= NJ) {                                                                                            \
         if (y_bf16) ln_fwd_kernel<NJ, true><<<grid, kLnThreads, 0, st>>>(x, w, b, y, stats, rows, D, eps);      \
@@ -111,9 +170,14 @@ int layernorm_fwd(const float* x, const float* w, const float* b, void* y, int y
 
 int layernorm_bwd(const float* x, const float* w, const float* stats, const float* dy, const float* dx_add, float* dx,
                   float* dw, float* db, int64_t rows, int D, cudaStream_t st) {
-    MSST_REQUIRE(D >= 1 && D <= 256, "layernorm: D=%d out of range [1,256]", D);
+    MSST_REQUIRE(D >= 1, "layernorm: D=%d out of range", D);
     if (rows == 0) return MSST_OK;
     const int nj = (D + 31) / 32;
+    if (D > 256) {
+        ln_bwd_wide_kernel<<<ln_grid(rows), kLnThreads, 0, st>>>(x, w, stats, dy, dx_add, dx, dw, db, rows, D);
+        MSST_LAUNCH_CHECK();
+        return MSST_OK;
+    }
     const int grid = ln_grid(rows);   // up to 8 CTAs/SM: the row loop is a dependent chain, memory-level parallelism comes from warps
 #define MSST_LN(NJ)                                                                                  \
     if (nj <= NJ) {                                                                                  \

@@ -61,12 +61,22 @@ class MaskGenerator:
         flat = torch.from_numpy(np.ascontiguousarray(cells.reshape(batch_size, -1)).astype(bool))
         return flat.to(device), self.bool_mask_to_indices(flat, batch_size, num_masked, device)
 
+    def _draw(self, n):
+        """n masks [n, size, size] (bool).  Same RNG call sequence as n calls of __call__ (one np.random.permutation each,
+        so np.random.seed reproduces the reference's draws); everything after the draw is vectorised."""
+        chosen = np.stack([np.random.permutation(self.token_count)[: self.mask_count] for _ in range(n)])
+        cells = np.zeros((n, self.token_count), dtype=bool)
+        cells[np.arange(n)[:, None], chosen] = True
+        cells = cells.reshape(n, self.rand_size, self.rand_size)
+        return cells.repeat(self.scale, axis=1).repeat(self.scale, axis=2)
+
     def get_batch(self, batch_size, channel_tokens, num_masked, device):
-        cells = np.stack([self() for _ in range(batch_size * channel_tokens)])
+        cells = self._draw(batch_size * channel_tokens)
         return self._finish(cells.reshape(batch_size, channel_tokens, *cells.shape[1:]), batch_size, num_masked, device)
 
     def get_batch_tube_masked(self, batch_size, channel_tokens, num_masked, device):
-        cells = np.stack([self() for _ in range(batch_size)])[:, None].repeat(channel_tokens, axis=1)
+        cells = np.broadcast_to(self._draw(batch_size)[:, None], (batch_size, channel_tokens, self.input_size // self.model_patch_size,
+                                                                 self.input_size // self.model_patch_size))
         return self._finish(cells, batch_size, num_masked, device)
 
 
@@ -87,6 +97,10 @@ class SimMIMSpatialSpectral(nn.Module):
         if self.mask_patch_size != 1:
             self.mask_generator = MaskGenerator(input_size=encoder.image_size, mask_patch_size=mask_patch_size,
                                                 model_patch_size=encoder.patch_height, mask_ratio=self.masking_ratio)
+        # "host": the reference's numpy generator, bit-compatible given np.random.seed (default);
+        # "device": same distribution and the same mask/index semantics (incl. quirk C3), drawn with torch on the GPU --
+        # no host work and no synchronisation per step.
+        self.mask_backend = "host"
         self.encoder = encoder
         encoder_dim = encoder.dim
         # reference :181-182 -- with PatchEmbed these are sub-modules and add alias keys to the state_dict
@@ -110,8 +124,31 @@ class SimMIMSpatialSpectral(nn.Module):
             idx = torch.rand(batch, num_patches, device=device).topk(k=num_masked, dim=-1).indices
             mask = torch.zeros((batch, num_patches), device=device).scatter_(-1, idx, 1).bool()
             return mask, idx
+        if self.mask_backend == "device":
+            return self._draw_masks_device(batch, num_masked, device)
         fn = self.mask_generator.get_batch_tube_masked if self.tube_masking else self.mask_generator.get_batch
         return fn(batch_size=batch, channel_tokens=enc.num_spectral_patches, num_masked=num_masked, device=device)
+
+    def _draw_masks_device(self, batch, num_masked, device):
+        """MaskGenerator.get_batch / get_batch_tube_masked (+ bool_mask_to_indices) with static shapes on the device:
+        a uniformly random subset of mask_count cells per draw, upsampled by `scale`; the index list is the row-major
+        list of set positions cut into consecutive runs of num_masked (the reference's slicing, quirk C3)."""
+        g, enc = self.mask_generator, self.encoder
+        C, T = enc.num_spectral_patches, enc.num_patches
+        n = batch if self.tube_masking else batch * C
+        chosen = torch.rand(n, g.token_count, device=device).argsort(dim=1)[:, : g.mask_count]
+        cells = torch.zeros(n, g.token_count, dtype=torch.bool, device=device).scatter_(1, chosen, True)
+        cells = cells.view(n, g.rand_size, g.rand_size).repeat_interleave(g.scale, 1).repeat_interleave(g.scale, 2)
+        size = g.rand_size * g.scale
+        cells = cells[:, None].expand(batch, C, size, size) if self.tube_masking else cells.view(batch, C, size, size)
+        mask = cells.reshape(batch, T)
+        per_row = g.mask_count * g.scale * g.scale * C                     # set positions per sample (static)
+        ar = torch.arange(T, device=device)
+        cols = torch.where(mask, ar, ar + T).sort(dim=1).values[:, :per_row]   # ascending set positions of every row
+        if batch * num_masked > batch * per_row:
+            raise RuntimeError("mask has fewer set positions than batch * num_masked")
+        idx = cols.reshape(-1)[: batch * num_masked].view(batch, num_masked)
+        return mask, idx
 
     # ---- forward ------------------------------------------------------------------------------------------
     def forward(self, img, masks=None):

@@ -151,3 +151,68 @@ def test_simmim_external_masks_inconsistent_and_duplicate_indices():
         if p[k].grad is None:
             continue
         assert rel_l2(v.grad, p[k].grad) < GTOL or float(p[k].grad.norm()) < 1e-9, k
+
+
+def _head_variant_oracle(x, sd, spec, kind):
+    """pixelwise (vit_spatial_spectral.py:467-479) / spectral_mlp_head (:441-453) heads on top of the oracle features."""
+    feats = O.transformer_forward(O.encoder_tokens(x, sd, spec), sd, spec)
+    B, g, D, C = x.shape[0], spec.S_sqrt, spec.dim, spec.C
+    if kind == "pixelwise":
+        z = feats.reshape(B, C, g, g, D).mean(dim=1)
+        z = O._ln(z, sd["mlp_head.0.weight"], sd["mlp_head.0.bias"]).reshape(B, g * g * D)
+        y = z @ sd["mlp_head.2.weight"].T + sd["mlp_head.2.bias"]
+        return y.reshape(B, 1, 1, -1).permute(0, 3, 1, 2).squeeze()
+    z = feats.reshape(B, C, g, g, D).permute(0, 2, 3, 1, 4).reshape(B, g, g, C * D)
+    z = O._ln(z, sd["mlp_head.0.weight"], sd["mlp_head.0.bias"])
+    y = z @ sd["mlp_head.1.weight"].T + sd["mlp_head.1.bias"]
+    return y.permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("kind", ["pixelwise", "spectral_mlp_head"])
+def test_head_variants_vs_oracle(kind):
+    """second-tier heads: LN / Linear through msst_layernorm / msst_linear, forward + gradients."""
+    spec = O.Spec(**O.HOUSTON, depth=1)
+    torch.manual_seed(0)
+    m = M.ViTSpatialSpectral(image_size=8, spatial_patch_size=1, spectral_patch_size=10, num_classes=20, dim=96, depth=1, heads=8,
+                             mlp_dim=64, channels=50, spectral_pos_embed=False, pixelwise=kind == "pixelwise",
+                             spectral_mlp_head=kind == "spectral_mlp_head")
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m.to(DEV).train()
+    x = O.synthetic_cube(spec, 3, seed=2)
+    got = m(x.to(DEV))
+    p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    want = _head_variant_oracle(x, p, spec, kind)
+    assert got.shape == want.shape
+    assert rel_l2(got, want) < TOL
+    got.square().sum().backward()
+    want.square().sum().backward()
+    for k, v in m.named_parameters():
+        if p[k].grad is not None and float(p[k].grad.norm()) > 1e-9:
+            assert rel_l2(v.grad, p[k].grad) < GTOL, k
+
+
+def test_reference_calling_conventions():
+    """to_patch / embed / get_pos_embeddings / forward_features / transformer_forward as the reference's callers use them
+    (vit_simmim_original.py:181-182,207-298), and the mask_patch_size == 1 random-mask path (:254-264)."""
+    spec = O.Spec(**O.HOUSTON, spectral_pos_embed=True)
+    sd = O.synthetic_state_dict(spec, seed=3)
+    m = make_encoder(spec).eval()
+    m.load_state_dict(sd)
+    m.to(DEV)
+    x = O.synthetic_cube(spec, 2, seed=3)
+    with torch.no_grad():
+        patches = m.to_patch_embedding.to_patch(x.to(DEV))
+        assert rel_l2(patches, O.to_patch(x, spec)) == 0.0
+        tok = m.to_patch_embedding.embed(patches)
+        assert rel_l2(tok, O.embed(O.to_patch(x, spec), sd, spec)) < TOL
+        assert rel_l2(m.get_pos_embeddings(), O.pos_table(sd, spec)) < 1e-7
+        enc = m.transformer_forward(tok + m.get_pos_embeddings())
+        assert rel_l2(enc, O.transformer_forward(O.encoder_tokens(x, sd, spec), sd, spec)) < TOL
+    sim = M.SimMIMSpatialSpectral(encoder=make_encoder(O.Spec(**O.HOUSTON)), masking_ratio=0.5, mask_patch_size=1).to(DEV).train()
+    torch.manual_seed(0)
+    mask, idx = sim.draw_masks(4, DEV)
+    assert mask.shape == (4, 320) and idx.shape == (4, 160) and int(mask.sum()) == 4 * 160
+    assert torch.equal(torch.zeros_like(mask).scatter_(1, idx, True), mask)
+    loss = sim(x.to(DEV)[:, :50])
+    loss.backward()
+    assert torch.isfinite(loss) and sim.mask_token.grad is not None and sim.to_pixels.weight.grad is not None

@@ -83,3 +83,24 @@ def test_reference_import_paths():
     from src.vit_simmim_original import SimMIMSpatialSpectral
     assert ViTSpatialSpectral is M.ViTSpatialSpectral and SimMIMSpatialSpectral is M.SimMIMSpatialSpectral
     assert get_pos_for_spectral_embedding(10, list(range(400, 600)), list(range(400, 1000)))[:3] == [0, 1, 2]
+
+
+def test_device_mask_backend_semantics_on_cpu():
+    """mask_backend='device' (torch ops, runs on any device): same counts / structure / index slicing as the host generator."""
+    for kw, tube in [(dict(**O.HOUSTON), True), (dict(**O.ENMAP), False)]:
+        spec = O.Spec(**kw)
+        m = M.SimMIMSpatialSpectral(encoder=make_encoder(spec), masking_ratio=0.7, mask_patch_size=4, tube_masking=tube,
+                                    to_pixels_per_spectral_block=True)
+        m.mask_backend = "device"
+        torch.manual_seed(0)
+        B = 6
+        mask, idx = m.draw_masks(B, "cpu")
+        nm = int(0.7 * spec.T)
+        assert mask.shape == (B, spec.T) and mask.dtype == torch.bool and idx.shape == (B, nm) and idx.dtype == torch.int64
+        assert int(mask.sum()) == B * 3 * 16 * spec.C                          # ceil(4 * .7) = 3 of 4 cells, 16 tokens each
+        cells = mask.view(B, spec.C, 2, 4, 2, 4)
+        assert torch.equal(cells, cells[:, :, :, :1, :, :1].expand_as(cells))   # 4x4 blocks are uniform
+        if tube:
+            assert torch.equal(mask.view(B, spec.C, 64), mask.view(B, spec.C, 64)[:, :1].expand(B, spec.C, 64))
+        want = torch.from_numpy(O.MaskGen.indices(mask.numpy(), nm))             # the reference's slicing of nonzero()
+        assert torch.equal(idx, want)
