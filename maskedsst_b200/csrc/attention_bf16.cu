@@ -107,9 +107,8 @@ __device__ __forceinline__ void store_rows16(const AttnGeom& g, const bf16* src,
 // attention-probability dropout: one 32-bit hash decides two neighbouring key slots (16 bits each)
 __device__ __forceinline__ uint32_t pair_hash(const Drop& d, uint64_t idx) {
     const uint64_t s = d.seed + (d.seed_dev ? __ldg(d.seed_dev) : 0ull);
-    uint32_t x = (uint32_t)idx * 0x9E3779B1u ^ ((uint32_t)(idx >> 32) * 0x85EBCA77u) ^ (uint32_t)s ^ (d.site * 0xC2B2AE3Du);
-    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
-    x += (uint32_t)(s >> 32);
+    // one round of the lowbias32 integer hash over (index, seed, site): full avalanche, ~12 instructions per key pair
+    uint32_t x = ((uint32_t)idx + (uint32_t)(s >> 32)) * 0x9E3779B1u ^ ((uint32_t)(idx >> 32) * 0x85EBCA77u) ^ (uint32_t)s ^ (d.site * 0xC2B2AE3Du);
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
     return x;
 }
@@ -415,6 +414,7 @@ __global__ void __launch_bounds__(BT, 4) attn_fwd_bf16_heads_kernel(AttnGeom g, 
     heads_setup(g, group, hs);
     __syncthreads();
     const uint32_t mask = fragment_mask(hs, r0, r1, tq);
+    const bool full_tile = __syncthreads_and(mask == 0xFFFFFFFFu);   // e.g. the spatial stack (one 64-token sequence per tile)
     const int64_t grow0 = hs.row[r0], grow1 = hs.row[r1];
     auto prefetch = [&](int h, int b) {
         bf16* t = buf + (size_t)b * 3 * TS * PITCH;
@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(BT, 4) attn_fwd_bf16_heads_kernel(AttnGeom g, 
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) s[nt][e] = (mask >> (4 * nt + e)) & 1u ? s[nt][e] * sl2 : -INFINITY;
+            for (int e = 0; e < 4; ++e) s[nt][e] = (full_tile || ((mask >> (4 * nt + e)) & 1u)) ? s[nt][e] * sl2 : -INFINITY;
             mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1])); mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
         }
         mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
@@ -496,6 +496,7 @@ __global__ void __launch_bounds__(BT, 2) attn_bwd_bf16_heads_kernel(AttnGeom g, 
     heads_setup(g, group, hs);
     __syncthreads();
     const uint32_t mask = fragment_mask(hs, r0, r1, tq);
+    const bool full_tile = __syncthreads_and(mask == 0xFFFFFFFFu);
     const int64_t grow0 = hs.row[r0], grow1 = hs.row[r1];
     auto prefetch = [&](int h, int b) {
         bf16* t = buf + (size_t)b * 4 * TS * PITCH;
@@ -530,7 +531,7 @@ __global__ void __launch_bounds__(BT, 2) attn_bwd_bf16_heads_kernel(AttnGeom g, 
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float p = (mask >> (4 * nt + e)) & 1u ? exp2f(s[nt][e] * sl2 - (e < 2 ? L0 : L1)) : 0.f;
+                const float p = (full_tile || ((mask >> (4 * nt + e)) & 1u)) ? exp2f(s[nt][e] * sl2 - (e < 2 ? L0 : L1)) : 0.f;
                 const float pf = p * f[e];
                 const float t = pf * dp[nt][e];
                 if (e < 2) D0 += t; else D1 += t;

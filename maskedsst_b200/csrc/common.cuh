@@ -52,7 +52,22 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
     return cdf + x * pdf;
 }
 
-// ---- counter-based dropout RNG (Philox4x32-10) ----
+// bf16-mode variants: erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below bf16 resolution), ~3x fewer instructions
+__device__ __forceinline__ float erf_as(float x) {
+    const float ax = fabsf(x);
+    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f); p = fmaf(p, t, -0.284496736f); p = fmaf(p, t, 0.254829592f);
+    const float r = 1.0f - p * t * __expf(-ax * ax);
+    return copysignf(r, x);
+}
+__device__ __forceinline__ float gelu_fast(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_fast_grad(float x) {
+    const float cdf = 0.5f * (1.0f + erf_as(x * 0.70710678118654752440f));
+    return fmaf(x * 0.39894228040143267794f, __expf(-0.5f * x * x), cdf);
+}
+
+// ---- counter-based dropout RNG (Philox4x32-7: the 7-round variant of Salmon et al., passes BigCrush) ----
 // Masks are never stored: forward and backward regenerate them from (seed, site, element index).
 // One call yields four 32-bit words for elements 4q..4q+3 of site `site`.
 struct Philox {
@@ -71,7 +86,7 @@ struct Philox {
         uint32_t c[4] = {(uint32_t)quad, (uint32_t)(quad >> 32), site, 0x5e5eed5u};
         uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
-        for (int r = 0; r < 10; ++r) { round(c, k0, k1); k0 += kW0; k1 += kW1; }
+        for (int r = 0; r < 7; ++r) { round(c, k0, k1); k0 += kW0; k1 += kW1; }
         out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
     }
 };

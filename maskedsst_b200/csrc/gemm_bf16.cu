@@ -98,13 +98,13 @@ __device__ __forceinline__ void epilogue_rows(const GemmTnParams& p, const float
             if (MODE == 3) {
                 *reinterpret_cast<uint2*>(p.pre_act + off) = make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
 #pragma unroll
-                for (int t = 0; t < 4; ++t) f[t] = gelu_erf(f[t]);
+                for (int t = 0; t < 4; ++t) f[t] = gelu_fast(f[t]);
             }
             if (MODE == 4) {
                 const uint32_t ux = __float_as_uint(pre[i].x), uy = __float_as_uint(pre[i].y);
                 const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&ux), h1 = *reinterpret_cast<const __nv_bfloat162*>(&uy);
-                f[0] *= gelu_erf_grad(__low2float(h0)); f[1] *= gelu_erf_grad(__high2float(h0));
-                f[2] *= gelu_erf_grad(__low2float(h1)); f[3] *= gelu_erf_grad(__high2float(h1));
+                f[0] *= gelu_fast_grad(__low2float(h0)); f[1] *= gelu_fast_grad(__high2float(h0));
+                f[2] *= gelu_fast_grad(__low2float(h1)); f[3] *= gelu_fast_grad(__high2float(h1));
             }
             if (drop_on) {
                 float d4[4];

@@ -7,8 +7,10 @@ namespace msst {
 // layernorm.cu
 int layernorm_fwd(const float* x, const float* w, const float* b, void* y, int y_bf16, float* stats, int64_t rows, int D,
                   float eps, cudaStream_t st);
+// cast_out / cast_drop / cast_colsum (optional, D % 4 == 0 && D <= 128): also emit bf16(dropout(dx)) and its column sums
 int layernorm_bwd(const float* x, const float* w, const float* stats, const float* dy, const float* dx_add, float* dx,
-                  float* dw, float* db, int64_t rows, int D, cudaStream_t st);
+                  float* dw, float* db, int64_t rows, int D, cudaStream_t st, __nv_bfloat16* cast_out = nullptr,
+                  Drop cast_drop = Drop{0, nullptr, 0, 0, 1.f}, float* cast_colsum = nullptr);
 
 // gemm_f32.cu
 int linear_fwd_f32(const float* x, const float* W, const float* bias, const float* residual, float* y, float* pre_act,

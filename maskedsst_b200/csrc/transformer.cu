@@ -143,6 +143,7 @@ static int tf_bwd_bf16(const msst_tf_dims* d, const msst_layer_params* layers, c
     float* dxa = (float*)(ws + L.s_dxa); float* dxb = (float*)(ws + L.s_dxb);
     const float* dcur = d_x_out;
     const Drop none = make_drop(0.f, 0, 0);
+    bool dyb_ready = false;
     for (int l = d->L - 1; l >= 0; --l) {
         char* lw = ws + L.layer_bytes * l;
         const msst_layer_params& p = layers[l];
@@ -154,7 +155,11 @@ static int tf_bwd_bf16(const msst_tf_dims* d, const msst_layer_params* layers, c
         const float* x = (l == 0) ? x_in : (const float*)(ws + L.layer_bytes * (l - 1) + L.o_xout);
         const uint32_t site = d->site_base + 8u * l;
         // ---- MLP branch ----
-        if (int rc = cast_rows_f32(dcur, dyb, gr.b2, R, D, make_drop(d->drop_p, d->seed, site + kSiteMlpOut, d->seed_dev), st)) return rc;
+        // dyb = bf16(dropout_mlp_out(dcur)) and db2: produced by the previous layer-iteration's LN1 backward (fused), or by a
+        // stand-alone cast for the gradient that enters the stack
+        if (!dyb_ready) {
+            if (int rc = cast_rows_f32(dcur, dyb, gr.b2, R, D, make_drop(d->drop_p, d->seed, site + kSiteMlpOut, d->seed_dev), st)) return rc;
+        }
         if (int rc = gemm_wgrad_bf16(dyb, g, gr.w2, R, D, M, st)) return rc;
         GemmBf16Args a = gemm_args(dyb, w.w2T, R, M, D, du, 0);        // du = (dy . W2) * gelu'(u) * hidden-dropout
         a.aux = u; a.act = 2; a.drop = make_drop(d->drop_p, d->seed, site + kSiteMlpHidden, d->seed_dev);
@@ -162,9 +167,10 @@ static int tf_bwd_bf16(const msst_tf_dims* d, const msst_layer_params* layers, c
         if (int rc = cast_rows_bf16(du, nullptr, gr.b1, R, M, none, st)) return rc;
         if (int rc = gemm_wgrad_bf16(du, (const bf16*)(lw + L.o_h2), gr.w1, R, M, D, st)) return rc;
         if (int rc = gemm_tn_bf16(gemm_args(du, w.w1T, R, D, M, dh, 1), st)) return rc;
-        if (int rc = layernorm_bwd(xmid, p.ln2_w, stats2, dh, dcur, dxa, gr.ln2_w, gr.ln2_b, R, D, st)) return rc;
+        // LN2 backward -> dxa (fp32) + fused: dyb = bf16(dropout_attn_out(dxa)), db_out += colsum
+        if (int rc = layernorm_bwd(xmid, p.ln2_w, stats2, dh, dcur, dxa, gr.ln2_w, gr.ln2_b, R, D, st, dyb,
+                                   make_drop(d->drop_p, d->seed, site + kSiteAttnOut, d->seed_dev), gr.b_out)) return rc;
         // ---- attention branch ----
-        if (int rc = cast_rows_f32(dxa, dyb, gr.b_out, R, D, make_drop(d->drop_p, d->seed, site + kSiteAttnOut, d->seed_dev), st)) return rc;
         if (int rc = gemm_wgrad_bf16(dyb, o, gr.w_out, R, D, I, st)) return rc;
         if (int rc = gemm_tn_bf16(gemm_args(dyb, w.woT, R, I, D, dO, 0), st)) return rc;
         msst_attn_dims ad{d->n_seq, d->N, d->inner, d->H, d->dh, d->drop_p, d->seed, site + kSiteAttnProb, d->prec, d->seed_dev};
@@ -172,7 +178,14 @@ static int tf_bwd_bf16(const msst_tf_dims* d, const msst_layer_params* layers, c
         if (int rc = gemm_wgrad_bf16(dqkv, (const bf16*)(lw + L.o_h1), gr.w_qkv, R, 3 * I, D, st)) return rc;
         if (int rc = gemm_tn_bf16(gemm_args(dqkv, w.wqT, R, D, 3 * I, dh, 1), st)) return rc;
         float* dx = (l == 0) ? d_x_in : dxb;
-        if (int rc = layernorm_bwd(x, p.ln1_w, stats1, dh, dxa, dx, gr.ln1_w, gr.ln1_b, R, D, st)) return rc;
+        // LN1 backward -> dx (fp32) + fused for the next iteration (layer l-1): dyb = bf16(dropout_mlp_out(dx)), db2(l-1)
+        if (l > 0) {
+            if (int rc = layernorm_bwd(x, p.ln1_w, stats1, dh, dxa, dx, gr.ln1_w, gr.ln1_b, R, D, st, dyb,
+                                       make_drop(d->drop_p, d->seed, site - 8u + kSiteMlpOut, d->seed_dev), grads[l - 1].b2)) return rc;
+            dyb_ready = true;
+        } else {
+            if (int rc = layernorm_bwd(x, p.ln1_w, stats1, dh, dxa, dx, gr.ln1_w, gr.ln1_b, R, D, st)) return rc;
+        }
         dcur = dx;
     }
     return MSST_OK;
