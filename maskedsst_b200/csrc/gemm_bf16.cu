@@ -8,7 +8,7 @@
 //
 // Reference call sites: nn.Linear to_qkv / to_out / net.0 / net.3 (src/vit_spatial_spectral.py:35-41,59-65) and their
 // autograd.  Structure: persistent warp-specialised CTA (1 per SM): warp 0 = TMA producer, warp 1 = MMA issuer
-// (one elected thread), warp 2 = TMEM allocator, warps 4-11 = epilogue (TMEM -> registers -> smem transpose -> global).
+// (one elected thread), warp 2 = TMEM allocator, warps 4-19 = epilogue (TMEM -> registers -> smem transpose -> global).
 // smem ring of 4 stages (A 128x64 + B BNx64 bf16, SWIZZLE_128B), two TMEM accumulator stages so the epilogue of
 // tile i overlaps the loads + MMAs of tile i+1.  K is tiny in this model (64..512, 1536 for one dgrad), the kernels
 // are HBM-bound: algorithmic bytes per launch = 2(MK + NK) + out_bytes*MN (+ 4MN residual).
@@ -23,9 +23,12 @@ using namespace ptx;
 constexpr int GB_M = 128;          // UMMA M (rows of A per tile) -- accumulator row i lives in TMEM lane i
 constexpr int GB_K = 64;           // bf16 elements per k-block = 128 B = one SWIZZLE_128B row
 constexpr int GB_STAGES = 3;            // 3 x (16 KB A + <=32 KB B) + 36 KB epilogue staging < 227 KB
-constexpr int GB_THREADS = 384;       // TMA, MMA, TMEM-alloc, spare + 8 epilogue warps
-constexpr int GB_EPI_PITCH = 36;       // floats per staged row (32 + 4: keeps float4 alignment, conflict-free)
-constexpr int GB_EPI_SMEM = 8 * 32 * GB_EPI_PITCH * 4;
+constexpr int GB_EPI_WARPS = 16;      // 4 per TMEM lane quarter: the epilogue math (GELU, Philox) is the throughput limiter
+constexpr int GB_THREADS = 128 + 32 * GB_EPI_WARPS;   // TMA, MMA, TMEM-alloc, spare + epilogue warps
+// accumulator columns per epilogue step: 16 for the math-heavy epilogues (GELU / Philox / residual: more warps busy on the
+// N = 64 / 96 tiles), 32 for the store-only ones (whole 64/128-byte row segments per store instruction)
+__host__ __device__ constexpr int gb_chunk(int mode) { return (mode == 2 || mode == 3 || mode == 4) ? 16 : 32; }
+__host__ __device__ constexpr int gb_epi_smem(int mode) { return GB_EPI_WARPS * 32 * (gb_chunk(mode) + 4) * 4; }
 constexpr uint32_t GB_A_BYTES = GB_M * GB_K * 2;   // 16 KB
 
 struct GemmTnParams {
@@ -48,7 +51,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 
-// Epilogue body for one staged chunk (32 rows x 32 fp32 in smem): lane -> (row sub_r + 4i, columns c4..c4+3).
+// Epilogue body for one staged chunk (32 rows x 16 fp32 in smem): lane -> (row sub_r + 8i, columns c4..c4+3).
 // MODE selects a compile-time specialisation of the common operator shapes (lean instruction stream -- the epilogue is
 // the throughput limiter of these small-K GEMMs); MODE 5 is the fully general path.
 //   0: bf16 out                         (QKV projection, dO data-gradient)
@@ -59,13 +62,15 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // residual (MODE 2) / GELU' argument (MODE 4) of this lane's 8 row segments, fetched BEFORE the accumulator is waited for:
 // the loads must not sit between the stores of the main loop (possible aliasing would serialise them on DRAM latency).
 template <int MODE>
-__device__ __forceinline__ void epilogue_prefetch(const GemmTnParams& p, int64_t row_base, int col0, int sub_r, int c4, float4 (&pre)[8]) {
+__device__ __forceinline__ void epilogue_prefetch(const GemmTnParams& p, int64_t row_base, int col0, int sub_r, int c4,
+                                                  float4 (&pre)[gb_chunk(MODE) / 4]) {
     if (MODE != 2 && MODE != 4) return;
+    constexpr int ITER = gb_chunk(MODE) / 4, RPI = 128 / gb_chunk(MODE);   // row iterations, rows per iteration
     const int col = col0 + c4;
     const int64_t rows_left = p.M - row_base;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int rr = i * 4 + sub_r;
+    for (int i = 0; i < ITER; ++i) {
+        const int rr = i * RPI + sub_r;
         pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (rr < rows_left && col < p.N) {
             const int64_t off = (row_base + rr) * p.N + col;
@@ -77,7 +82,8 @@ __device__ __forceinline__ void epilogue_prefetch(const GemmTnParams& p, int64_t
 
 template <int MODE>
 __device__ __forceinline__ void epilogue_rows(const GemmTnParams& p, const float* stg, int64_t row_base, int col0, int sub_r, int c4,
-                                              const float4 (&pre)[8]) {
+                                              const float4 (&pre)[gb_chunk(MODE) / 4]) {
+    constexpr int ITER = gb_chunk(MODE) / 4, RPI = 128 / gb_chunk(MODE), PITCH = gb_chunk(MODE) + 4;
     const int col = col0 + c4;
     if (MODE != 5) {
         if (col >= p.N) return;            // N % 4 == 0 in the specialised modes: a float4 is all-in or all-out
@@ -89,10 +95,10 @@ __device__ __forceinline__ void epilogue_rows(const GemmTnParams& p, const float
         const bool drop_on = (MODE >= 2) && p.drop.on();
         const int64_t rows_left = p.M - row_base;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int rr = i * 4 + sub_r;
+        for (int i = 0; i < ITER; ++i) {
+            const int rr = i * RPI + sub_r;
             if (rr >= rows_left) continue;
-            const float4 a4 = *reinterpret_cast<const float4*>(stg + rr * GB_EPI_PITCH + c4);
+            const float4 a4 = *reinterpret_cast<const float4*>(stg + rr * PITCH + c4);
             float f[4] = {a4.x + b4[0], a4.y + b4[1], a4.z + b4[2], a4.w + b4[3]};
             const int64_t off = (row_base + rr) * p.N + col;
             if (MODE == 3) {
@@ -128,11 +134,11 @@ __device__ __forceinline__ void epilogue_rows(const GemmTnParams& p, const float
         for (int t = 0; t < 4; ++t) if (col + t < p.N) bias4[t] = __ldg(p.bias + col + t);
     }
 #pragma unroll 2
-    for (int i = 0; i < 8; ++i) {
-        const int rr = i * 4 + sub_r;
+    for (int i = 0; i < ITER; ++i) {
+        const int rr = i * RPI + sub_r;
         const int64_t row = row_base + rr;
         if (row >= p.M || col >= p.N) continue;
-        const float4 a4 = *reinterpret_cast<const float4*>(stg + rr * GB_EPI_PITCH + c4);
+        const float4 a4 = *reinterpret_cast<const float4*>(stg + rr * PITCH + c4);
         float f[4] = {a4.x + bias4[0], a4.y + bias4[1], a4.z + bias4[2], a4.w + bias4[3]};
         const int64_t off = row * p.N + col;
         if (p.pre_act) {
@@ -183,7 +189,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (warp == 0 && elect_one()) { prefetch_tmap(&tma_a); prefetch_tmap(&tma_b); }
     if (warp == 1 && elect_one()) {
         for (int s = 0; s < GB_STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&bars->tmem_full[s], 1); mbar_init(&bars->tmem_empty[s], 8); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars->tmem_full[s], 1); mbar_init(&bars->tmem_empty[s], GB_EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(&bars->tmem_base, p.tmem_cols);
@@ -236,13 +242,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> smem transpose -> coalesced global =====
-        // 8 warps: warp (4 + q + 4*half) owns TMEM lane quarter q and the 32-column chunks c == half (mod 2).
-        // A chunk (32 rows x 32 fp32) is written row-per-thread into a padded smem tile and read back with 8 lanes per
-        // row (float4 each), so every global access of the epilogue (residual / aux loads, stores) covers whole 128-byte
-        // (fp32) or 64-byte (bf16) row segments instead of 32 scattered 16-byte pieces.
-        const int q = (warp - 4) & 3, half = (warp - 4) >> 2;
-        float* stg = reinterpret_cast<float*>(smem + (size_t)GB_STAGES * stage_bytes + 256) + (size_t)(warp - 4) * (32 * GB_EPI_PITCH);
-        const int sub_r = lane >> 3, c4 = (lane & 7) * 4;
+        // 16 warps: warp (4 + q + 4*sub) owns TMEM lane quarter q and the 16-column chunks c == sub (mod 4).
+        // A chunk (32 rows x 16 fp32) is written row-per-thread into a padded smem tile and read back with 4 lanes per
+        // row (float4 each), so every global access of the epilogue (residual / aux loads, stores) covers whole 64-byte
+        // (fp32) or 32-byte (bf16) row segments instead of 32 scattered 16-byte pieces.
+        constexpr int CH = gb_chunk(MODE), PITCH = CH + 4, LPR = CH / 4;   // lanes per row in the read-back phase
+        const int q = (warp - 4) & 3, sub = (warp - 4) >> 2;
+        float* stg = reinterpret_cast<float*>(smem + (size_t)GB_STAGES * stage_bytes + 256) + (size_t)(warp - 4) * (32 * PITCH);
+        const int sub_r = lane / LPR, c4 = (lane % LPR) * 4;
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
@@ -250,19 +257,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const int64_t m_blk = tile / p.tiles_n;
             bool first_chunk = true;     // the accumulator is waited for after the first chunk's operand prefetch is in flight
             const int64_t row_base = m_blk * GB_M + q * 32;
-            for (int c = half; c < ((p.debug & 2) ? 0 : p.block_n / 32); c += 2) {
-                const int col0 = n_blk * p.block_n + c * 32;
-                float4 pre[8];
+            for (int c = sub; c < ((p.debug & 2) ? 0 : p.block_n / CH); c += GB_EPI_WARPS / 4) {
+                const int col0 = n_blk * p.block_n + c * CH;
+                float4 pre[CH / 4];
                 epilogue_prefetch<MODE>(p, row_base, col0, sub_r, c4, pre);
                 if (first_chunk) { mbar_wait(&bars->tmem_full[acc], acc_phase); tc_fence_after(); first_chunk = false; }
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n + c * 32), v);
+                uint32_t v[CH];
+                if (CH == 16) tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n + c * CH), reinterpret_cast<uint32_t(&)[16]>(v));
+                else tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n + c * CH), reinterpret_cast<uint32_t(&)[32]>(v));
                 tmem_ld_wait();
                 if (row_base >= p.M || col0 >= p.N) continue;      // warp-uniform
                 __syncwarp();
 #pragma unroll
-                for (int g8 = 0; g8 < 8; ++g8)
-                    *reinterpret_cast<float4*>(stg + lane * GB_EPI_PITCH + g8 * 4) =
+                for (int g8 = 0; g8 < CH / 4; ++g8)
+                    *reinterpret_cast<float4*>(stg + lane * PITCH + g8 * 4) =
                         make_float4(__uint_as_float(v[g8 * 4]), __uint_as_float(v[g8 * 4 + 1]), __uint_as_float(v[g8 * 4 + 2]), __uint_as_float(v[g8 * 4 + 3]));
                 __syncwarp();
                 epilogue_rows<MODE>(p, stg, row_base, col0, sub_r, c4, pre);
@@ -429,13 +437,14 @@ int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st) {
     CUtensorMap ta, tb;
     if (int rc = make_tmap(&ta, a.A, a.M, a.K, a.K, GB_M)) return rc;
     if (int rc = make_tmap(&tb, a.B, a.N, a.K, a.K, p.block_n)) return rc;
-    const size_t smem = (size_t)GB_STAGES * (GB_A_BYTES + (size_t)p.block_n * GB_K * 2) + 256 + GB_EPI_SMEM + 1024;
+    
     int mode = 5;
     const bool vec = (a.N % 4 == 0);
     if (vec && !a.pre_act && !a.bias && !a.residual && a.act == 0 && !a.drop.on()) mode = a.out_fp32 ? 1 : 0;
     else if (vec && a.out_fp32 && a.bias && a.residual && a.act == 0 && !a.pre_act) mode = 2;
     else if (vec && !a.out_fp32 && a.bias && a.act == 1 && a.pre_act && !a.residual) mode = 3;
     else if (vec && !a.out_fp32 && !a.bias && a.act == 2 && a.aux && !a.residual && !a.pre_act) mode = 4;
+    const size_t smem = (size_t)GB_STAGES * (GB_A_BYTES + (size_t)p.block_n * GB_K * 2) + 256 + gb_epi_smem(mode) + 1024;
     const int64_t tiles = p.tiles_m * p.tiles_n;
     const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
     static bool attr_set = false;

@@ -158,6 +158,17 @@ patch_embed_bwd_kernel(EmbedGeom g, int n_wb, const float* __restrict__ img, con
     for (int p = 0; p < PMAX; ++p) a_prew[p] = a_preb[p] = 0.f;
 
     for (int b = blockIdx.y; b < g.B; b += gridDim.y) {
+        // this warp's 8 token gradients + mask bytes are fetched up front: their DRAM latency overlaps the slab load / pre-norm
+        float dt_all[TPW][NJ];
+        bool masked_all[TPW];
+#pragma unroll
+        for (int k = 0; k < TPW; ++k) {
+            const int s = s0 + warp * TPW + k;
+            const int64_t row = (int64_t)b * g.T + c * g.S + s;
+            masked_all[k] = s < g.S && mask && mask[row];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) dt_all[k][j] = s < g.S ? d_tokens[row * D + lane + 32 * j] : 0.f;
+        }
         __syncthreads();
         load_and_prenorm(g, img, b, c, s0, pre_w, pre_b, xs, hs, rstd_s);
 #pragma unroll
@@ -170,11 +181,11 @@ patch_embed_bwd_kernel(EmbedGeom g, int n_wb, const float* __restrict__ img, con
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
                 const int f = lane + 32 * j;
-                dt[j] = d_tokens[row * D + f];
+                dt[j] = dt_all[k][j];
                 if (drop.on()) dt[j] *= drop_factor(drop, (uint64_t)row * D + f);
                 a_pos[k][j] += dt[j];
             }
-            const bool masked = mask && mask[row];
+            const bool masked = masked_all[k];
             if (masked) {
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) a_mt[j] += dt[j];
