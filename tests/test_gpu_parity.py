@@ -216,3 +216,22 @@ def test_reference_calling_conventions():
     loss = sim(x.to(DEV)[:, :50])
     loss.backward()
     assert torch.isfinite(loss) and sim.mask_token.grad is not None and sim.to_pixels.weight.grad is not None
+
+
+def test_whole_tile_inference_equals_window_loop():
+    from maskedsst_b200.inference import predict_tiles, tile_accuracy
+    spec = O.Spec(**O.HOUSTON, depth=1)
+    m = make_encoder(spec).eval()
+    m.load_state_dict(O.synthetic_state_dict(spec, seed=61))
+    m.to(DEV)
+    tiles = torch.randn(2, 50, 24, 16, device=DEV)
+    full = predict_tiles(m, tiles)
+    assert full.shape == (2, 20, 24, 16)
+    with torch.no_grad():
+        for (i, j) in [(0, 0), (2, 1), (1, 0)]:
+            win = m(tiles[:, :, 8 * i:8 * i + 8, 8 * j:8 * j + 8].contiguous())
+            assert rel_l2(full[:, :, 8 * i:8 * i + 8, 8 * j:8 * j + 8], win) < 1e-6
+    labels = full.argmax(1)
+    labels[0, :4] = -1
+    acc, n = tile_accuracy(full, labels)
+    assert float(acc) == 1.0 and int(n) == 2 * 24 * 16 - 4 * 16
