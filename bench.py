@@ -338,6 +338,9 @@ def roofline(args, B, dev, model, peaks):
         return {"error": str(e)}
     flops = 2.0 * R * N * D
     bytes_ = R * D * x.element_size() + R * N * y.element_size() + N * D * W.element_size()
+    # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed `ncu --set full` capture
+    # (profiles/r01_ncu_full_final_kernels.txt, gemm_tn_kernel<0>, B = 1024 Houston shape): 63.2 MB + 951.5 MB
+    traffic = 1014752768 if (args.precision == "bf16" and R == 327680) else None
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     tf_peak = peaks.get("bf16_tflops", 1590.0)
     src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback"
@@ -345,10 +348,10 @@ def roofline(args, B, dev, model, peaks):
     t_tensor, t_hbm = flops / (tf_peak * 1e12), bytes_ / (hbm_peak * 1e9)
     if t_hbm >= t_tensor:
         return {"kernel": "qkv projection GEMM [R,96]x[96,1536]", "bound": "hbm", "achieved": bytes_ / sec / 1e9, "peak": hbm_peak,
-                "unit": "GB/s", "frac": bytes_ / sec / 1e9 / hbm_peak, "traffic": None, "peak_source": src,
+                "unit": "GB/s", "frac": bytes_ / sec / 1e9 / hbm_peak, "traffic": traffic, "algorithmic_bytes": bytes_, "peak_source": src,
                 "tflops": flops / sec / 1e12, "us_per_launch": sec * 1e6}
     return {"kernel": "qkv projection GEMM [R,96]x[96,1536]", "bound": "tensor", "achieved": flops / sec / 1e12, "peak": tf_peak,
-            "unit": "TFLOP/s", "frac": flops / sec / 1e12 / tf_peak, "traffic": None, "peak_source": src, "us_per_launch": sec * 1e6}
+            "unit": "TFLOP/s", "frac": flops / sec / 1e12 / tf_peak, "traffic": traffic, "peak_source": src, "us_per_launch": sec * 1e6}
 
 
 if __name__ == "__main__":

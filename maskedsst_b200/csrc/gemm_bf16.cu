@@ -84,6 +84,24 @@ template <int MODE>
 __device__ __forceinline__ void epilogue_rows(const GemmTnParams& p, const float* stg, int64_t row_base, int col0, int sub_r, int c4,
                                               const float4 (&pre)[gb_chunk(MODE) / 4]) {
     constexpr int ITER = gb_chunk(MODE) / 4, RPI = 128 / gb_chunk(MODE), PITCH = gb_chunk(MODE) + 4;
+    if (MODE == 0 && (p.N & 7) == 0) {
+        // store-only bf16 epilogue: lane -> 8 consecutive columns (one 16-byte store), 4 lanes per row, 8 rows per instruction
+        const int lane = threadIdx.x & 31, r8 = lane >> 2, c8 = (lane & 3) * 8;
+        const int col8 = col0 + c8;
+        if (col8 >= p.N) return;
+        const int64_t rows_left = p.M - row_base;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int rr = i * 8 + r8;
+            if (rr >= rows_left) continue;
+            const float4 a = *reinterpret_cast<const float4*>(stg + rr * PITCH + c8);
+            const float4 b = *reinterpret_cast<const float4*>(stg + rr * PITCH + c8 + 4);
+            if (p.debug & 1) continue;
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (row_base + rr) * p.N + col8) =
+                make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+        }
+        return;
+    }
     const int col = col0 + c4;
     if (MODE != 5) {
         if (col >= p.N) return;            // N % 4 == 0 in the specialised modes: a float4 is all-in or all-out
