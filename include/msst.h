@@ -13,7 +13,8 @@
  *   - return value: 0 = ok, otherwise an MSST_ERR_* code; msst_last_error() gives the message
  *   - token order t = c*S + s (spectral block major), patch vector order (p0 p1 p2), qkv rows q|k|v each
  *     head-major (h d)  -- reference vit_spatial_spectral.py:198,218,68-69
- *   - dropout masks are never stored: (seed, site, element index) -> Philox4x32-7; p = 0 disables
+ *   - dropout masks are never stored: (seed, site, element index) -> Philox4x32-7; p = 0 disables;
+ *     `seed_dev` (optional device uint64) is added to the seed so a captured CUDA graph draws fresh masks per replay
  */
 #ifndef MSST_H_
 #define MSST_H_
@@ -205,6 +206,7 @@ typedef struct {
     float clamp;            /* > 0: g = clamp(g, -clamp, clamp) after scaling; <= 0 off */
     float grad_scale;       /* e.g. 1/world_size */
     int step;
+    const int* step_dev;    /* optional: device int32 holding the 1-based step (CUDA-graph capturable optimiser); overrides step */
 } msst_adam_args;
 MSST_API int msst_adam_step(const msst_adam_args* a, float* p, const float* g, float* m, float* v, void* bf16_out, int64_t n,
                    msst_stream_t stream);

@@ -49,7 +49,7 @@ class DecodeDims(C.Structure):
 class AdamArgs(C.Structure):
     _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
                 ("weight_decay", C.c_float), ("decoupled", C.c_int), ("clamp", C.c_float), ("grad_scale", C.c_float),
-                ("step", C.c_int)]
+                ("step", C.c_int), ("step_dev", vp)]
 
 
 # name -> (restype, argtypes); kept in sync with include/msst.h (tests/test_abi.py checks the export list)

@@ -6,7 +6,7 @@
 
 namespace msst {
 
-struct AdamK { float lr, b1, b2, eps, wd, clamp, gscale, inv_bc1, inv_sqrt_bc2; int decoupled; };
+struct AdamK { float lr, b1, b2, eps, wd, clamp, gscale, inv_bc1, inv_sqrt_bc2; int decoupled; const int* step_dev; };
 
 __device__ __forceinline__ void adam_one(const AdamK& a, float& p, float g, float& m, float& v) {
     g *= a.gscale;
@@ -21,6 +21,11 @@ __device__ __forceinline__ void adam_one(const AdamK& a, float& p, float g, floa
 __global__ void __launch_bounds__(256) adam_kernel(AdamK a, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, __nv_bfloat16* __restrict__ bf, int64_t n, int vec) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    if (a.step_dev) {   // graph-capturable mode: bias corrections from the device-resident step counter
+        const float t = (float)__ldg(a.step_dev);
+        a.inv_bc1 = 1.f / (-expm1f(t * log1pf(a.b1 - 1.f)));          // 1 - b^t without cancellation
+        a.inv_sqrt_bc2 = rsqrtf(-expm1f(t * log1pf(a.b2 - 1.f)));
+    }
     if (vec) {
         const int64_t n4 = n >> 2;
         for (int64_t q = tid; q < n4; q += nth) {
@@ -55,13 +60,15 @@ using namespace msst;
 
 extern "C" int msst_adam_step(const msst_adam_args* a, float* p, const float* g, float* m, float* v, void* bf16_out, int64_t n,
                               msst_stream_t stream) {
-    MSST_REQUIRE(a && a->step >= 1, "adam_step: step must be >= 1");
+    MSST_REQUIRE(a && (a->step >= 1 || a->step_dev), "adam_step: step must be >= 1");
     if (n == 0) return MSST_OK;
     AdamK k;
     k.lr = a->lr; k.b1 = a->beta1; k.b2 = a->beta2; k.eps = a->eps; k.wd = a->weight_decay; k.clamp = a->clamp;
     k.gscale = a->grad_scale; k.decoupled = a->decoupled;
-    k.inv_bc1 = (float)(1.0 / (1.0 - pow((double)a->beta1, (double)a->step)));
-    k.inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)a->beta2, (double)a->step)));
+    const int st = a->step >= 1 ? a->step : 1;
+    k.inv_bc1 = (float)(1.0 / (1.0 - pow((double)a->beta1, (double)st)));
+    k.inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)a->beta2, (double)st)));
+    k.step_dev = a->step_dev;
     auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     const int vec = al(p) && al(g) && al(m) && al(v) && (!bf16_out || (reinterpret_cast<uintptr_t>(bf16_out) & 7u) == 0);
     int64_t blocks = ceil_div(vec ? n / 4 + 1 : n, 256);

@@ -20,6 +20,20 @@ def next_seed() -> int:
     return (torch.initial_seed() * 0x9E3779B97F4A7C15 + next(_seed_counter) * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
 
 
+_device_seed = None   # optional uint64-as-int64 device tensor added to every dropout seed (CUDA-graph replays)
+
+
+def set_device_seed(t):
+    """t: 0-dim int64 CUDA tensor (or None).  When set, kernels add its CURRENT device value to their dropout seed, so a
+    captured graph that increments it once per replay draws fresh masks every step."""
+    global _device_seed
+    _device_seed = t
+
+
+def _seed_dev():
+    return None if _device_seed is None else _device_seed.data_ptr()
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -58,7 +72,7 @@ class PatchEmbedFn(torch.autograd.Function):
         mask_u8 = None
         if mask is not None:
             mask_u8 = _c(mask.to(torch.uint8))
-        dims = _lib.EmbedDims(B, C_, G, p0, p1, D, W.shape[0], float(drop_p), seed, None)
+        dims = _lib.EmbedDims(B, C_, G, p0, p1, D, W.shape[0], float(drop_p), seed, _seed_dev())
         tokens = torch.empty(B, T, D, device=img.device, dtype=torch.float32)
         pln = torch.empty(B, T, p0 * p1 * p1, device=img.device, dtype=torch.float32) if want_ln else None
         pos_c = _c(pos)
@@ -117,7 +131,7 @@ class TransformerStackFn(torch.autograd.Function):
             _chk(t, "transformer parameter")
         R, D = x.shape
         assert R == n_seq * N, (R, n_seq, N)
-        dims = _lib.TfDims(n_seq, N, inner, D, H, dh, M, L, float(drop_p), seed, site_base, prec, int(need_grad), None)
+        dims = _lib.TfDims(n_seq, N, inner, D, H, dh, M, L, float(drop_p), seed, site_base, prec, int(need_grad), _seed_dev())
         nbytes = _lib.lib().msst_transformer_workspace_bytes(C.byref(dims))
         if nbytes < 0:
             check(1)

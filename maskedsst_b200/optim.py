@@ -51,11 +51,14 @@ class FlatArena:
 
 class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=True, clamp=0.0,
-                 grad_scale=1.0):
+                 grad_scale=1.0, capturable=False):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, decoupled=decoupled, clamp=clamp)
         super().__init__(params, defaults)
         self.grad_scale = grad_scale
         self._flatten()
+        # capturable: the step counter lives on the device so step() can be recorded into a CUDA graph
+        # (learning rates are still baked in at capture time: re-capture after a scheduler changes them)
+        self._step_t = torch.zeros((), dtype=torch.int32, device=self.param_arena.device) if capturable else None
 
     # ---- arena construction ---------------------------------------------------------------------------------
     def _flatten(self):
@@ -95,6 +98,10 @@ class FusedAdam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         self._step += 1
+        step_dev = None
+        if self._step_t is not None:
+            self._step_t += 1
+            step_dev = self._step_t.data_ptr()
         stream = torch.cuda.current_stream().cuda_stream
         lib = _lib.lib()
         for g, (a, b) in zip(self.param_groups, self._group_ranges):
@@ -102,7 +109,7 @@ class FusedAdam(torch.optim.Optimizer):
                 continue
             args = _lib.AdamArgs(float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
                                  float(g["weight_decay"]), int(bool(g["decoupled"])), float(g["clamp"]),
-                                 float(self.grad_scale), self._step)
+                                 float(self.grad_scale), self._step, step_dev)
             bf = None if self.bf16_arena is None else self.bf16_arena[a:b].data_ptr()
             check(lib.msst_adam_step(C.byref(args), self.param_arena[a:b].data_ptr(), self.grad_arena[a:b].data_ptr(),
                                      self.exp_avg[a:b].data_ptr(), self.exp_avg_sq[a:b].data_ptr(), bf, b - a, stream))

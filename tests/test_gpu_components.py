@@ -172,3 +172,37 @@ def test_larger_image_long_sequences():
     x = O.synthetic_cube(spec, 2, seed=51)
     with torch.no_grad():
         assert rel_l2(m(x.to(DEV)), O.encoder_forward(x, sd, spec)) < 1e-5
+
+
+def test_cuda_graph_step_matches_eager():
+    """A captured training step (GraphedStep) replays to the same parameters as eager steps (dropout off), and with
+    dropout on it draws different masks per replay."""
+    from maskedsst_b200.graph import GraphedStep
+    from oracle import maskedsst_oracle as O
+
+    def build(p):
+        torch.manual_seed(0)
+        enc = M.ViTSpatialSpectral(image_size=8, spatial_patch_size=1, spectral_patch_size=10, num_classes=20, dim=96, depth=1,
+                                   heads=8, mlp_dim=64, channels=50, spectral_pos_embed=False, dropout=p, emb_dropout=p)
+        return enc.to(DEV).train()
+
+    x = torch.randn(6, 50, 8, 8, device=DEV)
+    y = torch.randint(-1, 20, (6, 8, 8), device=DEV)
+    loss_fn = lambda m, xi, yi: M.cross_entropy(m(xi), yi, ignore_index=-1)
+    a, b = build(0.0), build(0.0)
+    oa = FusedAdam(a.parameters(), lr=0.01, weight_decay=0.05, clamp=1.0)
+    ob = FusedAdam(b.parameters(), lr=0.01, weight_decay=0.05, clamp=1.0, capturable=True)
+    g = GraphedStep(b, ob, (x, y), loss_fn=loss_fn, warmup=2)        # 2 eager warm-up steps applied; the capture itself executes nothing
+    for _ in range(2):
+        oa.zero_grad(); loss_fn(a, x, y).backward(); oa.step()
+    lg = g(x, y)                                                     # 3rd step, replayed
+    oa.zero_grad(); le = loss_fn(a, x, y); le.backward(); oa.step()
+    torch.cuda.synchronize()
+    assert abs(float(lg) - float(le)) < 1e-5 * abs(float(le))
+    assert rel_l2(ob.param_arena, oa.param_arena) < 1e-5
+    # dropout: two replays on the same input give different losses (fresh masks), and training state stays finite
+    c = build(0.2)
+    oc = FusedAdam(c.parameters(), lr=0.0, weight_decay=0.0, capturable=True)   # lr 0: parameters frozen, only masks change
+    gc = GraphedStep(c, oc, (x, y), loss_fn=loss_fn, warmup=1)
+    l1 = float(gc(x, y)); l2 = float(gc(x, y))
+    assert l1 != l2 and np.isfinite(l1) and np.isfinite(l2)
