@@ -15,7 +15,12 @@
 namespace msst {
 
 constexpr int BT = 128;         // threads per CTA (4 warps)
-constexpr int PITCH = 72;       // bf16 elements per smem row (64 + 8 pad -> conflict-free ldmatrix)
+// smem tiles are [64 rows][64 bf16] with the 16-byte chunks of a row XOR-swizzled by (row & 7): conflict-free ldmatrix /
+// cp.async / fragment stores without padding (8 KB per tile -> the backward kernel fits three CTAs per SM)
+// Two layouts: padded rows (cheapest addressing; forward kernels) and XOR-swizzled (no padding: 8 KB tiles; backward).
+struct Pad { static constexpr int TILE = TS * 72; static __device__ __forceinline__ int at(int r, int c) { return r * 72 + c; } };
+struct Swz { static constexpr int TILE = TS * 64;
+             static __device__ __forceinline__ int at(int r, int c) { return r * 64 + ((((c >> 3) ^ r) & 7) << 3) + (c & 7); } };
 typedef __nv_bfloat16 bf16;
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const bf16* p) {
@@ -37,21 +42,23 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 }
 
 // C[16 x 64] (8 n-tiles) += A[16 rows of As starting at row0][64] . B^T, B stored [n][k] in Bs (rows = n, 64 k each)
+template <class L>
 __device__ __forceinline__ void gemm_a_bnk(float (&c)[8][4], const bf16* As, int row0, const bf16* Bs, int lane) {
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
         uint32_t a[4];
-        ldsm_x4(a, As + (row0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * PITCH + ks * 16 + 8 * (lane >> 4));
+        ldsm_x4(a, As + L::at(row0 + (lane & 7) + 8 * ((lane >> 3) & 1), ks * 16 + 8 * (lane >> 4)));
 #pragma unroll
         for (int np = 0; np < 4; ++np) {
             uint32_t b[4];
-            ldsm_x4(b, Bs + (np * 16 + (lane & 7) + 8 * (lane >> 4)) * PITCH + ks * 16 + 8 * ((lane >> 3) & 1));
+            ldsm_x4(b, Bs + L::at(np * 16 + (lane & 7) + 8 * (lane >> 4), ks * 16 + 8 * ((lane >> 3) & 1)));
             mma16816(c[2 * np], a, b[0], b[1]);
             mma16816(c[2 * np + 1], a, b[2], b[3]);
         }
     }
 }
 // C[16 x 64] += P[16 x 64 (regs, C-fragment layout)] . B, B stored [k][n] in Bs (rows = k, 64 n each)
+template <class L>
 __device__ __forceinline__ void gemm_p_bkn(float (&c)[8][4], const float (&p)[8][4], const bf16* Bs, int lane) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -60,22 +67,23 @@ __device__ __forceinline__ void gemm_p_bkn(float (&c)[8][4], const float (&p)[8]
 #pragma unroll
         for (int np = 0; np < 4; ++np) {
             uint32_t b[4];
-            ldsm_x4_t(b, Bs + (j * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * PITCH + np * 16 + 8 * (lane >> 4));
+            ldsm_x4_t(b, Bs + L::at(j * 16 + (lane & 7) + 8 * ((lane >> 3) & 1), np * 16 + 8 * (lane >> 4)));
             mma16816(c[2 * np], a, b[0], b[1]);
             mma16816(c[2 * np + 1], a, b[2], b[3]);
         }
     }
 }
 // C[16 x 64] += A^T . B with A stored [k][m] in As (this warp's m = col0..col0+15), B stored [k][n] in Bs; k = 0..63
+template <class L>
 __device__ __forceinline__ void gemm_at_bkn(float (&c)[8][4], const bf16* As, int col0, const bf16* Bs, int lane) {
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
         uint32_t a[4];
-        ldsm_x4_t(a, As + (ks * 16 + (lane & 7) + 8 * (lane >> 4)) * PITCH + col0 + 8 * ((lane >> 3) & 1));
+        ldsm_x4_t(a, As + L::at(ks * 16 + (lane & 7) + 8 * (lane >> 4), col0 + 8 * ((lane >> 3) & 1)));
 #pragma unroll
         for (int np = 0; np < 4; ++np) {
             uint32_t b[4];
-            ldsm_x4_t(b, Bs + (ks * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * PITCH + np * 16 + 8 * (lane >> 4));
+            ldsm_x4_t(b, Bs + L::at(ks * 16 + (lane & 7) + 8 * ((lane >> 3) & 1), np * 16 + 8 * (lane >> 4)));
             mma16816(c[2 * np], a, b[0], b[1]);
             mma16816(c[2 * np + 1], a, b[2], b[3]);
         }
@@ -83,6 +91,7 @@ __device__ __forceinline__ void gemm_at_bkn(float (&c)[8][4], const bf16* As, in
 }
 
 // [64 slots x 64] bf16 tile of one of q/k/v/o (column offset col0) -> smem, zero rows for invalid slots
+template <class L>
 __device__ __forceinline__ void load_tile_bf16(const AttnGeom& g, const bf16* __restrict__ base, int64_t ld, int col0, int64_t group,
                                                int tile, bf16* dst) {
     for (int i = threadIdx.x; i < TS * 8; i += BT) {
@@ -90,17 +99,18 @@ __device__ __forceinline__ void load_tile_bf16(const AttnGeom& g, const bf16* __
         int64_t seq; int pos;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (slot_to(g, group, tile, r, seq, pos)) v = *reinterpret_cast<const uint4*>(base + row_of(g, seq, pos) * ld + col0 + c);
-        *reinterpret_cast<uint4*>(dst + r * PITCH + c) = v;
+        *reinterpret_cast<uint4*>(dst + L::at(r, c)) = v;
     }
 }
 // smem tile rows [row0, row0+16) (bf16) -> global rows (one warp, coalesced 16-byte stores)
+template <class L>
 __device__ __forceinline__ void store_rows16(const AttnGeom& g, const bf16* src, int row0, bf16* __restrict__ base, int64_t ld, int col0,
                                              const int* seq_s, const int* pos_s, int64_t group, int lane) {
     for (int i = lane; i < 16 * 8; i += 32) {
         const int r = row0 + (i >> 3), c = (i & 7) * 8;
         if (seq_s[r] < 0) continue;
         const int64_t row = row_of(g, group * g.G + seq_s[r], pos_s[r]);
-        *reinterpret_cast<uint4*>(base + row * ld + col0 + c) = *reinterpret_cast<const uint4*>(src + r * PITCH + c);
+        *reinterpret_cast<uint4*>(base + row * ld + col0 + c) = *reinterpret_cast<const uint4*>(src + L::at(r, c));
     }
 }
 
@@ -134,9 +144,10 @@ __device__ __forceinline__ void fill_idx(const AttnGeom& g, int64_t group, int t
 
 __global__ void __launch_bounds__(BT) attn_fwd_bf16_kernel(AttnGeom g, const bf16* __restrict__ qkv, bf16* __restrict__ out,
                                                            float* __restrict__ lse, Drop drop) {
-    __shared__ __align__(16) bf16 Qs[TS * PITCH];
-    __shared__ __align__(16) bf16 Ks[TS * PITCH];
-    __shared__ __align__(16) bf16 Vs[TS * PITCH];
+    using L = Pad;
+    __shared__ __align__(16) bf16 Qs[L::TILE];
+    __shared__ __align__(16) bf16 Ks[L::TILE];
+    __shared__ __align__(16) bf16 Vs[L::TILE];
     __shared__ AttnSmemIdx ix;
     const int I = g.H * 64, h = blockIdx.y;
     const int64_t ld = 3 * (int64_t)I;
@@ -146,18 +157,18 @@ __global__ void __launch_bounds__(BT) attn_fwd_bf16_kernel(AttnGeom g, const bf1
     const int r0 = warp * 16 + gq, r1 = r0 + 8;
     const float sl2 = g.scale * 1.4426950408889634f;   // scores are kept in log2 units: exp2f(s*scale*log2e - m)
 
-    load_tile_bf16(g, qkv, ld, h * 64, group, qt, Qs);
+    load_tile_bf16<L>(g, qkv, ld, h * 64, group, qt, Qs);
     fill_idx(g, group, qt, ix.qseq, ix.qpos, -1);
     float o[8][4] = {};
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
     for (int kt = 0; kt < g.tiles; ++kt) {
         __syncthreads();
-        load_tile_bf16(g, qkv, ld, I + h * 64, group, kt, Ks);
-        load_tile_bf16(g, qkv, ld, 2 * I + h * 64, group, kt, Vs);
+        load_tile_bf16<L>(g, qkv, ld, I + h * 64, group, kt, Ks);
+        load_tile_bf16<L>(g, qkv, ld, 2 * I + h * 64, group, kt, Vs);
         fill_idx(g, group, kt, ix.kseq, ix.kpos, -2);
         __syncthreads();
         float s[8][4] = {};
-        gemm_a_bnk(s, Qs, warp * 16, Ks, lane);
+        gemm_a_bnk<L>(s, Qs, warp * 16, Ks, lane);
         const int qs0 = ix.qseq[r0], qs1 = ix.qseq[r1];
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
@@ -194,18 +205,18 @@ __global__ void __launch_bounds__(BT) attn_fwd_bf16_kernel(AttnGeom g, const bf1
         }
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) { o[nt][0] *= c0; o[nt][1] *= c0; o[nt][2] *= c1; o[nt][3] *= c1; }
-        gemm_p_bkn(o, s, Vs, lane);
+        gemm_p_bkn<L>(o, s, Vs, lane);
     }
     // normalise, stage this warp's 16 rows through its own Q rows (no other warp reads them), coalesced store
     const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
     __syncwarp();
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-        *reinterpret_cast<uint32_t*>(Qs + r0 * PITCH + nt * 8 + 2 * tq) = pack2(o[nt][0] * i0, o[nt][1] * i0);
-        *reinterpret_cast<uint32_t*>(Qs + r1 * PITCH + nt * 8 + 2 * tq) = pack2(o[nt][2] * i1, o[nt][3] * i1);
+        *reinterpret_cast<uint32_t*>(Qs + L::at(r0, nt * 8 + 2 * tq)) = pack2(o[nt][0] * i0, o[nt][1] * i0);
+        *reinterpret_cast<uint32_t*>(Qs + L::at(r1, nt * 8 + 2 * tq)) = pack2(o[nt][2] * i1, o[nt][3] * i1);
     }
     __syncwarp();
-    store_rows16(g, Qs, warp * 16, out, I, h * 64, ix.qseq, ix.qpos, group, lane);
+    store_rows16<L>(g, Qs, warp * 16, out, I, h * 64, ix.qseq, ix.qpos, group, lane);
     if (tq == 0) {
         if (ix.qseq[r0] >= 0) lse[row_of(g, group * g.G + ix.qseq[r0], ix.qpos[r0]) * g.H + h] = (m0 + log2f(l0)) * 0.6931471805599453f;
         if (ix.qseq[r1] >= 0) lse[row_of(g, group * g.G + ix.qseq[r1], ix.qpos[r1]) * g.H + h] = (m1 + log2f(l1)) * 0.6931471805599453f;
@@ -218,14 +229,15 @@ template <int MODE>
 __global__ void __launch_bounds__(BT) attn_bwd_bf16_kernel(AttnGeom g, const bf16* __restrict__ qkv, const bf16* __restrict__ out,
                                                            const float* __restrict__ lse, const bf16* __restrict__ d_out,
                                                            bf16* __restrict__ d_qkv, Drop drop) {
+    using L = Pad;
     extern __shared__ __align__(16) uint8_t smem_bwd[];
     bf16* Qs = reinterpret_cast<bf16*>(smem_bwd);
-    bf16* Ks = Qs + TS * PITCH;
-    bf16* Vs = Ks + TS * PITCH;
-    bf16* dOs = Vs + TS * PITCH;
-    bf16* Ps = dOs + TS * PITCH;     // P * dropout factor   [q][key]
-    bf16* dSs = Ps + TS * PITCH;     // dS                   [q][key]
-    float* Drow = reinterpret_cast<float*>(dSs + TS * PITCH);
+    bf16* Ks = Qs + L::TILE;
+    bf16* Vs = Ks + L::TILE;
+    bf16* dOs = Vs + L::TILE;
+    bf16* Ps = dOs + L::TILE;     // P * dropout factor   [q][key]
+    bf16* dSs = Ps + L::TILE;     // dS                   [q][key]
+    float* Drow = reinterpret_cast<float*>(dSs + L::TILE);
     float* lse_s = Drow + TS;
     AttnSmemIdx& ix = *reinterpret_cast<AttnSmemIdx*>(lse_s + TS);
 
@@ -243,13 +255,13 @@ __global__ void __launch_bounds__(BT) attn_bwd_bf16_kernel(AttnGeom g, const bf1
         const int qt = MODE == 2 ? it : own, kt = MODE == 1 ? it : own;
         __syncthreads();
         if (MODE != 2 || it == 0) {
-            load_tile_bf16(g, qkv, ld, I + h * 64, group, kt, Ks);
-            load_tile_bf16(g, qkv, ld, 2 * I + h * 64, group, kt, Vs);
+            load_tile_bf16<L>(g, qkv, ld, I + h * 64, group, kt, Ks);
+            load_tile_bf16<L>(g, qkv, ld, 2 * I + h * 64, group, kt, Vs);
             fill_idx(g, group, kt, ix.kseq, ix.kpos, -2);
         }
         if (MODE != 1 || it == 0) {
-            load_tile_bf16(g, qkv, ld, h * 64, group, qt, Qs);
-            load_tile_bf16(g, d_out, I, h * 64, group, qt, dOs);
+            load_tile_bf16<L>(g, qkv, ld, h * 64, group, qt, Qs);
+            load_tile_bf16<L>(g, d_out, I, h * 64, group, qt, dOs);
             fill_idx(g, group, qt, ix.qseq, ix.qpos, -1);
         }
         __syncthreads();
@@ -262,7 +274,7 @@ __global__ void __launch_bounds__(BT) attn_bwd_bf16_kernel(AttnGeom g, const bf1
                     const int64_t row = row_of(g, group * g.G + ix.qseq[r], ix.qpos[r]);
                     const uint2 ov = *reinterpret_cast<const uint2*>(out + row * I + h * 64 + c);
                     const __nv_bfloat162 o01 = *reinterpret_cast<const __nv_bfloat162*>(&ov.x), o23 = *reinterpret_cast<const __nv_bfloat162*>(&ov.y);
-                    const bf16* dp = dOs + r * PITCH + c;
+                    const bf16* dp = dOs + L::at(r, c);
                     dsum = __bfloat162float(dp[0]) * __low2float(o01) + __bfloat162float(dp[1]) * __high2float(o01) +
                            __bfloat162float(dp[2]) * __low2float(o23) + __bfloat162float(dp[3]) * __high2float(o23);
                     l = lse[row * g.H + h];
@@ -274,8 +286,8 @@ __global__ void __launch_bounds__(BT) attn_bwd_bf16_kernel(AttnGeom g, const bf1
             __syncthreads();
         }
         float s[8][4] = {}, dp[8][4] = {};
-        gemm_a_bnk(s, Qs, warp * 16, Ks, lane);
-        gemm_a_bnk(dp, dOs, warp * 16, Vs, lane);
+        gemm_a_bnk<L>(s, Qs, warp * 16, Ks, lane);
+        gemm_a_bnk<L>(dp, dOs, warp * 16, Vs, lane);
         const int qs0 = ix.qseq[r0], qs1 = ix.qseq[r1];
         const float L0 = lse_s[r0], L1 = lse_s[r1], D0 = Drow[r0], D1 = Drow[r1];
         const uint64_t base = tile_pair_base(g, group, h, qt, kt);
@@ -294,17 +306,17 @@ __global__ void __launch_bounds__(BT) attn_bwd_bf16_kernel(AttnGeom g, const bf1
             s[nt][0] = p0 * (f0 * dp[nt][0] - D0) * g.scale; s[nt][1] = p1 * (f1 * dp[nt][1] - D0) * g.scale;
             s[nt][2] = p2 * (f2 * dp[nt][2] - D1) * g.scale; s[nt][3] = p3 * (f3 * dp[nt][3] - D1) * g.scale;
             if (MODE != 1) {
-                *reinterpret_cast<uint32_t*>(Ps + r0 * PITCH + c) = pack2(p0 * f0, p1 * f1);
-                *reinterpret_cast<uint32_t*>(Ps + r1 * PITCH + c) = pack2(p2 * f2, p3 * f3);
-                *reinterpret_cast<uint32_t*>(dSs + r0 * PITCH + c) = pack2(s[nt][0], s[nt][1]);
-                *reinterpret_cast<uint32_t*>(dSs + r1 * PITCH + c) = pack2(s[nt][2], s[nt][3]);
+                *reinterpret_cast<uint32_t*>(Ps + L::at(r0, c)) = pack2(p0 * f0, p1 * f1);
+                *reinterpret_cast<uint32_t*>(Ps + L::at(r1, c)) = pack2(p2 * f2, p3 * f3);
+                *reinterpret_cast<uint32_t*>(dSs + L::at(r0, c)) = pack2(s[nt][0], s[nt][1]);
+                *reinterpret_cast<uint32_t*>(dSs + L::at(r1, c)) = pack2(s[nt][2], s[nt][3]);
             }
         }
-        if (MODE != 2) gemm_p_bkn(dq, s, Ks, lane);          // dQ[16 rows] += dS . K
+        if (MODE != 2) gemm_p_bkn<L>(dq, s, Ks, lane);          // dQ[16 rows] += dS . K
         if (MODE != 1) {
             __syncthreads();
-            gemm_at_bkn(dv, Ps, warp * 16, dOs, lane);       // dV[16 keys] += (P f)^T . dO
-            gemm_at_bkn(dk, dSs, warp * 16, Qs, lane);       // dK[16 keys] += dS^T . Q
+            gemm_at_bkn<L>(dv, Ps, warp * 16, dOs, lane);       // dV[16 keys] += (P f)^T . dO
+            gemm_at_bkn<L>(dk, dSs, warp * 16, Qs, lane);       // dK[16 keys] += dS^T . Q
         }
     }
     __syncthreads();
@@ -312,24 +324,24 @@ __global__ void __launch_bounds__(BT) attn_bwd_bf16_kernel(AttnGeom g, const bf1
     if (MODE != 2) {
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-            *reinterpret_cast<uint32_t*>(Qs + r0 * PITCH + nt * 8 + 2 * tq) = pack2(dq[nt][0], dq[nt][1]);
-            *reinterpret_cast<uint32_t*>(Qs + r1 * PITCH + nt * 8 + 2 * tq) = pack2(dq[nt][2], dq[nt][3]);
+            *reinterpret_cast<uint32_t*>(Qs + L::at(r0, nt * 8 + 2 * tq)) = pack2(dq[nt][0], dq[nt][1]);
+            *reinterpret_cast<uint32_t*>(Qs + L::at(r1, nt * 8 + 2 * tq)) = pack2(dq[nt][2], dq[nt][3]);
         }
     }
     if (MODE != 1) {
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-            *reinterpret_cast<uint32_t*>(Ks + r0 * PITCH + nt * 8 + 2 * tq) = pack2(dk[nt][0], dk[nt][1]);
-            *reinterpret_cast<uint32_t*>(Ks + r1 * PITCH + nt * 8 + 2 * tq) = pack2(dk[nt][2], dk[nt][3]);
-            *reinterpret_cast<uint32_t*>(Vs + r0 * PITCH + nt * 8 + 2 * tq) = pack2(dv[nt][0], dv[nt][1]);
-            *reinterpret_cast<uint32_t*>(Vs + r1 * PITCH + nt * 8 + 2 * tq) = pack2(dv[nt][2], dv[nt][3]);
+            *reinterpret_cast<uint32_t*>(Ks + L::at(r0, nt * 8 + 2 * tq)) = pack2(dk[nt][0], dk[nt][1]);
+            *reinterpret_cast<uint32_t*>(Ks + L::at(r1, nt * 8 + 2 * tq)) = pack2(dk[nt][2], dk[nt][3]);
+            *reinterpret_cast<uint32_t*>(Vs + L::at(r0, nt * 8 + 2 * tq)) = pack2(dv[nt][0], dv[nt][1]);
+            *reinterpret_cast<uint32_t*>(Vs + L::at(r1, nt * 8 + 2 * tq)) = pack2(dv[nt][2], dv[nt][3]);
         }
     }
     __syncwarp();
-    if (MODE != 2) store_rows16(g, Qs, warp * 16, d_qkv, ld, h * 64, ix.qseq, ix.qpos, group, lane);
+    if (MODE != 2) store_rows16<L>(g, Qs, warp * 16, d_qkv, ld, h * 64, ix.qseq, ix.qpos, group, lane);
     if (MODE != 1) {
-        store_rows16(g, Ks, warp * 16, d_qkv, ld, I + h * 64, ix.kseq, ix.kpos, group, lane);
-        store_rows16(g, Vs, warp * 16, d_qkv, ld, 2 * I + h * 64, ix.kseq, ix.kpos, group, lane);
+        store_rows16<L>(g, Ks, warp * 16, d_qkv, ld, I + h * 64, ix.kseq, ix.kpos, group, lane);
+        store_rows16<L>(g, Vs, warp * 16, d_qkv, ld, 2 * I + h * 64, ix.kseq, ix.kpos, group, lane);
     }
 }
 
@@ -363,15 +375,17 @@ __device__ __forceinline__ void heads_setup(const AttnGeom& g, int64_t group, He
     }
 }
 // this thread's 4 chunks of a [64 x 64] tile: rows (tid>>3) + 16k, column chunk (tid&7)*8
+template <class L>
 __device__ __forceinline__ void prefetch_tile(bf16* dst, const bf16* __restrict__ base, int64_t ld, int col0, const HeadsShared& hs) {
     const int c = (threadIdx.x & 7) * 8;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int r = (threadIdx.x >> 3) + 16 * k;
         const int64_t row = hs.row[r];
-        cp_async16(dst + r * PITCH + c, base + (row < 0 ? 0 : row) * ld + col0 + c, row >= 0);
+        cp_async16(dst + L::at(r, c), base + (row < 0 ? 0 : row) * ld + col0 + c, row >= 0);
     }
 }
+template <class L>
 __device__ __forceinline__ void store_rows16_hs(const bf16* src, int row0, bf16* __restrict__ base, int64_t ld, int col0,
                                                 const HeadsShared& hs, int lane) {
 #pragma unroll
@@ -379,7 +393,7 @@ __device__ __forceinline__ void store_rows16_hs(const bf16* src, int row0, bf16*
         const int i = lane + 32 * k;
         const int r = row0 + (i >> 3), c = (i & 7) * 8;
         const int64_t row = hs.row[r];
-        if (row >= 0) *reinterpret_cast<uint4*>(base + row * ld + col0 + c) = *reinterpret_cast<const uint4*>(src + r * PITCH + c);
+        if (row >= 0) *reinterpret_cast<uint4*>(base + row * ld + col0 + c) = *reinterpret_cast<const uint4*>(src + L::at(r, c));
     }
 }
 // bit (4*nt + e) set when element e of n-tile nt of this thread's C fragment pairs a query and a key of the same sequence
@@ -398,14 +412,15 @@ __device__ __forceinline__ uint32_t fragment_mask(const HeadsShared& hs, int r0,
     return m;
 }
 
-constexpr size_t kFwdHeadsSmem = sizeof(bf16) * 2 * 3 * TS * PITCH + sizeof(HeadsShared);
-constexpr size_t kBwdHeadsSmem = sizeof(bf16) * (2 * 4 + 1) * TS * PITCH + sizeof(HeadsShared);
+constexpr size_t kFwdHeadsSmem = sizeof(bf16) * 2 * 3 * Pad::TILE + sizeof(HeadsShared);
+constexpr size_t kBwdHeadsSmem = sizeof(bf16) * (2 * 4 + 1) * Swz::TILE + sizeof(HeadsShared);
 
 __global__ void __launch_bounds__(BT, 4) attn_fwd_bf16_heads_kernel(AttnGeom g, const bf16* __restrict__ qkv, bf16* __restrict__ out,
                                                                     float* __restrict__ lse, Drop drop) {
+    using L = Pad;
     extern __shared__ __align__(16) uint8_t smem_h[];
-    bf16* buf = reinterpret_cast<bf16*>(smem_h);                                   // [2][3][TS*PITCH]
-    HeadsShared& hs = *reinterpret_cast<HeadsShared*>(smem_h + sizeof(bf16) * 6 * TS * PITCH);
+    bf16* buf = reinterpret_cast<bf16*>(smem_h);                                   // [2][3][TILE]
+    HeadsShared& hs = *reinterpret_cast<HeadsShared*>(smem_h + sizeof(bf16) * 6 * L::TILE);
     const int I = g.H * 64;
     const int64_t ld = 3 * (int64_t)I, group = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
@@ -417,10 +432,10 @@ __global__ void __launch_bounds__(BT, 4) attn_fwd_bf16_heads_kernel(AttnGeom g, 
     const bool full_tile = __syncthreads_and(mask == 0xFFFFFFFFu);   // e.g. the spatial stack (one 64-token sequence per tile)
     const int64_t grow0 = hs.row[r0], grow1 = hs.row[r1];
     auto prefetch = [&](int h, int b) {
-        bf16* t = buf + (size_t)b * 3 * TS * PITCH;
-        prefetch_tile(t, qkv, ld, h * 64, hs);
-        prefetch_tile(t + TS * PITCH, qkv, ld, I + h * 64, hs);
-        prefetch_tile(t + 2 * TS * PITCH, qkv, ld, 2 * I + h * 64, hs);
+        bf16* t = buf + (size_t)b * 3 * L::TILE;
+        prefetch_tile<L>(t, qkv, ld, h * 64, hs);
+        prefetch_tile<L>(t + L::TILE, qkv, ld, I + h * 64, hs);
+        prefetch_tile<L>(t + 2 * L::TILE, qkv, ld, 2 * I + h * 64, hs);
         cp_async_commit();
     };
     prefetch(0, 0);
@@ -429,9 +444,9 @@ __global__ void __launch_bounds__(BT, 4) attn_fwd_bf16_heads_kernel(AttnGeom g, 
         cp_async_wait_all();
         __syncthreads();
         if (h + 1 < g.H) prefetch(h + 1, b ^ 1);
-        bf16* Qs = buf + (size_t)b * 3 * TS * PITCH; bf16* Ks = Qs + TS * PITCH; bf16* Vs = Ks + TS * PITCH;
+        bf16* Qs = buf + (size_t)b * 3 * L::TILE; bf16* Ks = Qs + L::TILE; bf16* Vs = Ks + L::TILE;
         float s[8][4] = {};
-        gemm_a_bnk(s, Qs, warp * 16, Ks, lane);
+        gemm_a_bnk<L>(s, Qs, warp * 16, Ks, lane);
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
@@ -465,16 +480,16 @@ __global__ void __launch_bounds__(BT, 4) attn_fwd_bf16_heads_kernel(AttnGeom g, 
             for (int nt = 0; nt < 8; ++nt) { s[nt][0] *= i0; s[nt][1] *= i0; s[nt][2] *= i1; s[nt][3] *= i1; }
         }
         float o[8][4] = {};
-        gemm_p_bkn(o, s, Vs, lane);
+        gemm_p_bkn<L>(o, s, Vs, lane);
         // stage this warp's 16 output rows in its own Q rows (only this warp reads them), then coalesced stores
         __syncwarp();
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-            *reinterpret_cast<uint32_t*>(Qs + r0 * PITCH + nt * 8 + 2 * tq) = pack2(o[nt][0], o[nt][1]);
-            *reinterpret_cast<uint32_t*>(Qs + r1 * PITCH + nt * 8 + 2 * tq) = pack2(o[nt][2], o[nt][3]);
+            *reinterpret_cast<uint32_t*>(Qs + L::at(r0, nt * 8 + 2 * tq)) = pack2(o[nt][0], o[nt][1]);
+            *reinterpret_cast<uint32_t*>(Qs + L::at(r1, nt * 8 + 2 * tq)) = pack2(o[nt][2], o[nt][3]);
         }
         __syncwarp();
-        store_rows16_hs(Qs, warp * 16, out, I, h * 64, hs, lane);
+        store_rows16_hs<L>(Qs, warp * 16, out, I, h * 64, hs, lane);
         if (tq == 0) {
             if (grow0 >= 0) lse[grow0 * g.H + h] = (mx0 + log2f(l0)) * 0.6931471805599453f;
             if (grow1 >= 0) lse[grow1 * g.H + h] = (mx1 + log2f(l1)) * 0.6931471805599453f;
@@ -482,12 +497,13 @@ __global__ void __launch_bounds__(BT, 4) attn_fwd_bf16_heads_kernel(AttnGeom g, 
     }
 }
 
-__global__ void __launch_bounds__(BT, 2) attn_bwd_bf16_heads_kernel(AttnGeom g, const bf16* __restrict__ qkv, const float* __restrict__ lse,
+__global__ void __launch_bounds__(BT, 3) attn_bwd_bf16_heads_kernel(AttnGeom g, const bf16* __restrict__ qkv, const float* __restrict__ lse,
                                                                     const bf16* __restrict__ d_out, bf16* __restrict__ d_qkv, Drop drop) {
+    using L = Swz;
     extern __shared__ __align__(16) uint8_t smem_h[];
-    bf16* buf = reinterpret_cast<bf16*>(smem_h);                                   // [2][4][TS*PITCH]: Q K V dO
-    bf16* dSs = buf + (size_t)8 * TS * PITCH;
-    HeadsShared& hs = *reinterpret_cast<HeadsShared*>(smem_h + sizeof(bf16) * 9 * TS * PITCH);
+    bf16* buf = reinterpret_cast<bf16*>(smem_h);                                   // [2][4][TILE]: Q K V dO
+    bf16* dSs = buf + (size_t)8 * L::TILE;
+    HeadsShared& hs = *reinterpret_cast<HeadsShared*>(smem_h + sizeof(bf16) * 9 * L::TILE);
     const int I = g.H * 64;
     const int64_t ld = 3 * (int64_t)I, group = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
@@ -499,11 +515,11 @@ __global__ void __launch_bounds__(BT, 2) attn_bwd_bf16_heads_kernel(AttnGeom g, 
     const bool full_tile = __syncthreads_and(mask == 0xFFFFFFFFu);
     const int64_t grow0 = hs.row[r0], grow1 = hs.row[r1];
     auto prefetch = [&](int h, int b) {
-        bf16* t = buf + (size_t)b * 4 * TS * PITCH;
-        prefetch_tile(t, qkv, ld, h * 64, hs);
-        prefetch_tile(t + TS * PITCH, qkv, ld, I + h * 64, hs);
-        prefetch_tile(t + 2 * TS * PITCH, qkv, ld, 2 * I + h * 64, hs);
-        prefetch_tile(t + 3 * TS * PITCH, d_out, I, h * 64, hs);
+        bf16* t = buf + (size_t)b * 4 * L::TILE;
+        prefetch_tile<L>(t, qkv, ld, h * 64, hs);
+        prefetch_tile<L>(t + L::TILE, qkv, ld, I + h * 64, hs);
+        prefetch_tile<L>(t + 2 * L::TILE, qkv, ld, 2 * I + h * 64, hs);
+        prefetch_tile<L>(t + 3 * L::TILE, d_out, I, h * 64, hs);
         cp_async_commit();
     };
     prefetch(0, 0);
@@ -512,12 +528,12 @@ __global__ void __launch_bounds__(BT, 2) attn_bwd_bf16_heads_kernel(AttnGeom g, 
         cp_async_wait_all();
         __syncthreads();
         if (h + 1 < g.H) prefetch(h + 1, b ^ 1);
-        bf16* Qs = buf + (size_t)b * 4 * TS * PITCH; bf16* Ks = Qs + TS * PITCH; bf16* Vs = Ks + TS * PITCH; bf16* dOs = Vs + TS * PITCH;
+        bf16* Qs = buf + (size_t)b * 4 * L::TILE; bf16* Ks = Qs + L::TILE; bf16* Vs = Ks + L::TILE; bf16* dOs = Vs + L::TILE;
         const float L0 = grow0 >= 0 ? lse[grow0 * g.H + h] * 1.4426950408889634f : 0.f;
         const float L1 = grow1 >= 0 ? lse[grow1 * g.H + h] * 1.4426950408889634f : 0.f;
         float s[8][4] = {}, dp[8][4] = {};
-        gemm_a_bnk(s, Qs, warp * 16, Ks, lane);
-        gemm_a_bnk(dp, dOs, warp * 16, Vs, lane);
+        gemm_a_bnk<L>(s, Qs, warp * 16, Ks, lane);
+        gemm_a_bnk<L>(dp, dOs, warp * 16, Vs, lane);
         // P, Pf = P*f (kept in dp[]), D_i = sum_j Pf_ij dP_ij  (== dO_i . O_i), dS (kept in s[])
         float D0 = 0.f, D1 = 0.f;
         uint32_t pf_pack[8][2];
@@ -555,36 +571,36 @@ __global__ void __launch_bounds__(BT, 2) attn_bwd_bf16_heads_kernel(AttnGeom g, 
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
             const int c = nt * 8 + 2 * tq;
-            *reinterpret_cast<uint32_t*>(Ps + r0 * PITCH + c) = pf_pack[nt][0];
-            *reinterpret_cast<uint32_t*>(Ps + r1 * PITCH + c) = pf_pack[nt][1];
-            *reinterpret_cast<uint32_t*>(dSs + r0 * PITCH + c) = pack2(s[nt][0], s[nt][1]);
-            *reinterpret_cast<uint32_t*>(dSs + r1 * PITCH + c) = pack2(s[nt][2], s[nt][3]);
+            *reinterpret_cast<uint32_t*>(Ps + L::at(r0, c)) = pf_pack[nt][0];
+            *reinterpret_cast<uint32_t*>(Ps + L::at(r1, c)) = pf_pack[nt][1];
+            *reinterpret_cast<uint32_t*>(dSs + L::at(r0, c)) = pack2(s[nt][0], s[nt][1]);
+            *reinterpret_cast<uint32_t*>(dSs + L::at(r1, c)) = pack2(s[nt][2], s[nt][3]);
         }
         float dq[8][4] = {};
-        gemm_p_bkn(dq, s, Ks, lane);                       // dQ[16 rows] = dS . K
+        gemm_p_bkn<L>(dq, s, Ks, lane);                       // dQ[16 rows] = dS . K
         __syncthreads();   // (B) Pf / dS tiles complete
         float dv[8][4] = {}, dk[8][4] = {};
-        gemm_at_bkn(dv, Ps, warp * 16, dOs, lane);         // dV[16 keys] = (P f)^T . dO
-        gemm_at_bkn(dk, dSs, warp * 16, Qs, lane);         // dK[16 keys] = dS^T . Q
+        gemm_at_bkn<L>(dv, Ps, warp * 16, dOs, lane);         // dV[16 keys] = (P f)^T . dO
+        gemm_at_bkn<L>(dk, dSs, warp * 16, Qs, lane);         // dK[16 keys] = dS^T . Q
         __syncthreads();   // (C) Q / K / Pf tiles are dead: reuse them as staging for coalesced stores
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
             const int c = nt * 8 + 2 * tq;
-            *reinterpret_cast<uint32_t*>(Qs + r0 * PITCH + c) = pack2(dq[nt][0], dq[nt][1]);
-            *reinterpret_cast<uint32_t*>(Qs + r1 * PITCH + c) = pack2(dq[nt][2], dq[nt][3]);
-            *reinterpret_cast<uint32_t*>(Ks + r0 * PITCH + c) = pack2(dk[nt][0], dk[nt][1]);
-            *reinterpret_cast<uint32_t*>(Ks + r1 * PITCH + c) = pack2(dk[nt][2], dk[nt][3]);
-            *reinterpret_cast<uint32_t*>(Vs + r0 * PITCH + c) = pack2(dv[nt][0], dv[nt][1]);
-            *reinterpret_cast<uint32_t*>(Vs + r1 * PITCH + c) = pack2(dv[nt][2], dv[nt][3]);
+            *reinterpret_cast<uint32_t*>(Qs + L::at(r0, c)) = pack2(dq[nt][0], dq[nt][1]);
+            *reinterpret_cast<uint32_t*>(Qs + L::at(r1, c)) = pack2(dq[nt][2], dq[nt][3]);
+            *reinterpret_cast<uint32_t*>(Ks + L::at(r0, c)) = pack2(dk[nt][0], dk[nt][1]);
+            *reinterpret_cast<uint32_t*>(Ks + L::at(r1, c)) = pack2(dk[nt][2], dk[nt][3]);
+            *reinterpret_cast<uint32_t*>(Vs + L::at(r0, c)) = pack2(dv[nt][0], dv[nt][1]);
+            *reinterpret_cast<uint32_t*>(Vs + L::at(r1, c)) = pack2(dv[nt][2], dv[nt][3]);
         }
         __syncwarp();
-        store_rows16_hs(Qs, warp * 16, d_qkv, ld, h * 64, hs, lane);
-        store_rows16_hs(Ks, warp * 16, d_qkv, ld, I + h * 64, hs, lane);
-        store_rows16_hs(Vs, warp * 16, d_qkv, ld, 2 * I + h * 64, hs, lane);
+        store_rows16_hs<L>(Qs, warp * 16, d_qkv, ld, h * 64, hs, lane);
+        store_rows16_hs<L>(Ks, warp * 16, d_qkv, ld, I + h * 64, hs, lane);
+        store_rows16_hs<L>(Vs, warp * 16, d_qkv, ld, 2 * I + h * 64, hs, lane);
     }
 }
 
-constexpr size_t kBwdSmem = sizeof(bf16) * 6 * TS * PITCH + sizeof(float) * 2 * TS + sizeof(AttnSmemIdx);
+constexpr size_t kBwdSmem = sizeof(bf16) * 6 * Pad::TILE + sizeof(float) * 2 * TS + sizeof(AttnSmemIdx);
 
 int attention_fwd_bf16(const msst_attn_dims* d, const bf16* qkv, bf16* out, float* lse, cudaStream_t st) {
     AttnGeom g;
