@@ -3,10 +3,13 @@
 // Reference: Attention.forward, src/vit_spatial_spectral.py:67-78 (and its autograd).
 //
 // Same tiling / packing geometry as attention_f32.cu (64 query slots x 64 key slots, short sequences packed with a
-// block-diagonal mask, strided row addressing for the spectral stack).  One CTA = 4 warps, each warp owns 16 query
-// rows (FlashAttention-2 register layout): S and P never leave registers, O / dQ accumulate in registers; the tiles
-// here are 64x64x64 -- too small for a tcgen05 pipeline to pay off (one UMMA M=64 tile per CTA), so the
-// contractions use mma.sync.m16n8k16 with ldmatrix-fed fragments.  Scores never reach HBM.
+// block-diagonal mask, strided row addressing for the spectral stack).  Each warp owns 16 query rows (FlashAttention-2
+// register layout): S and P never leave registers, O / dQ accumulate in registers; the model's tiles are 64x64x64 -- too
+// small for a tcgen05 pipeline to pay off (one UMMA M=64 tile per CTA), so the contractions use
+// mma.sync.m16n8k16 with ldmatrix-fed fragments.  Scores never reach HBM.  Three kernel families:
+//   N <= 64 : *_heads_kernel  -- one CTA per slot group loops over all heads, cp.async double buffer across heads
+//   N  > 64 : *_long_kernel   -- forward: 128 query rows per CTA, K/V tiles streamed through a cp.async double buffer;
+//                                backward: a dQ pass over key tiles and a dK/dV pass over query tiles (no atomics)
 // Algorithmic HBM bytes per (slot, head): fwd 3*128 B in + 128 B out + 4 B lse; bwd 5*128 B in + 3*128 B out.
 #include "common.cuh"
 #include "kernels.h"
@@ -90,30 +93,6 @@ __device__ __forceinline__ void gemm_at_bkn(float (&c)[8][4], const bf16* As, in
     }
 }
 
-// [64 slots x 64] bf16 tile of one of q/k/v/o (column offset col0) -> smem, zero rows for invalid slots
-template <class L>
-__device__ __forceinline__ void load_tile_bf16(const AttnGeom& g, const bf16* __restrict__ base, int64_t ld, int col0, int64_t group,
-                                               int tile, bf16* dst) {
-    for (int i = threadIdx.x; i < TS * 8; i += BT) {
-        const int r = i >> 3, c = (i & 7) * 8;
-        int64_t seq; int pos;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (slot_to(g, group, tile, r, seq, pos)) v = *reinterpret_cast<const uint4*>(base + row_of(g, seq, pos) * ld + col0 + c);
-        *reinterpret_cast<uint4*>(dst + L::at(r, c)) = v;
-    }
-}
-// smem tile rows [row0, row0+16) (bf16) -> global rows (one warp, coalesced 16-byte stores)
-template <class L>
-__device__ __forceinline__ void store_rows16(const AttnGeom& g, const bf16* src, int row0, bf16* __restrict__ base, int64_t ld, int col0,
-                                             const int* seq_s, const int* pos_s, int64_t group, int lane) {
-    for (int i = lane; i < 16 * 8; i += 32) {
-        const int r = row0 + (i >> 3), c = (i & 7) * 8;
-        if (seq_s[r] < 0) continue;
-        const int64_t row = row_of(g, group * g.G + seq_s[r], pos_s[r]);
-        *reinterpret_cast<uint4*>(base + row * ld + col0 + c) = *reinterpret_cast<const uint4*>(src + L::at(r, c));
-    }
-}
-
 // attention-probability dropout: one 32-bit hash decides two neighbouring key slots (16 bits each)
 __device__ __forceinline__ uint32_t pair_hash(const Drop& d, uint64_t idx) {
     const uint64_t s = d.seed + (d.seed_dev ? __ldg(d.seed_dev) : 0ull);
@@ -129,220 +108,6 @@ __device__ __forceinline__ void pair_factors(const Drop& d, uint64_t idx, float&
 }
 __device__ __forceinline__ uint64_t tile_pair_base(const AttnGeom& g, int64_t group, int h, int qt, int kt) {
     return ((((uint64_t)group * g.H + h) * g.tiles + qt) * g.tiles + kt) * (uint64_t)(TS * TS / 2);
-}
-
-struct AttnSmemIdx { int qseq[TS], qpos[TS], kseq[TS], kpos[TS]; };
-
-__device__ __forceinline__ void fill_idx(const AttnGeom& g, int64_t group, int tile, int* seq_s, int* pos_s, int invalid) {
-    if (threadIdx.x < TS) {
-        int64_t seq; int pos;
-        const bool ok = slot_to(g, group, tile, threadIdx.x, seq, pos);
-        seq_s[threadIdx.x] = ok ? (int)(seq - group * g.G) : invalid;
-        pos_s[threadIdx.x] = pos;
-    }
-}
-
-__global__ void __launch_bounds__(BT) attn_fwd_bf16_kernel(AttnGeom g, const bf16* __restrict__ qkv, bf16* __restrict__ out,
-                                                           float* __restrict__ lse, Drop drop) {
-    using L = Pad;
-    __shared__ __align__(16) bf16 Qs[L::TILE];
-    __shared__ __align__(16) bf16 Ks[L::TILE];
-    __shared__ __align__(16) bf16 Vs[L::TILE];
-    __shared__ AttnSmemIdx ix;
-    const int I = g.H * 64, h = blockIdx.y;
-    const int64_t ld = 3 * (int64_t)I;
-    const int64_t group = blockIdx.x / g.tiles;
-    const int qt = blockIdx.x % g.tiles;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
-    const int r0 = warp * 16 + gq, r1 = r0 + 8;
-    const float sl2 = g.scale * 1.4426950408889634f;   // scores are kept in log2 units: exp2f(s*scale*log2e - m)
-
-    load_tile_bf16<L>(g, qkv, ld, h * 64, group, qt, Qs);
-    fill_idx(g, group, qt, ix.qseq, ix.qpos, -1);
-    float o[8][4] = {};
-    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-    for (int kt = 0; kt < g.tiles; ++kt) {
-        __syncthreads();
-        load_tile_bf16<L>(g, qkv, ld, I + h * 64, group, kt, Ks);
-        load_tile_bf16<L>(g, qkv, ld, 2 * I + h * 64, group, kt, Vs);
-        fill_idx(g, group, kt, ix.kseq, ix.kpos, -2);
-        __syncthreads();
-        float s[8][4] = {};
-        gemm_a_bnk<L>(s, Qs, warp * 16, Ks, lane);
-        const int qs0 = ix.qseq[r0], qs1 = ix.qseq[r1];
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            const int c = nt * 8 + 2 * tq;
-            const int ks0 = ix.kseq[c], ks1 = ix.kseq[c + 1];
-            s[nt][0] = qs0 == ks0 ? s[nt][0] * sl2 : -INFINITY; s[nt][1] = qs0 == ks1 ? s[nt][1] * sl2 : -INFINITY;
-            s[nt][2] = qs1 == ks0 ? s[nt][2] * sl2 : -INFINITY; s[nt][3] = qs1 == ks1 ? s[nt][3] * sl2 : -INFINITY;
-            mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1])); mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
-        }
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-        const float c0 = mn0 == -INFINITY ? 1.f : exp2f(m0 - mn0), c1 = mn1 == -INFINITY ? 1.f : exp2f(m1 - mn1);
-        const float sub0 = mn0 == -INFINITY ? 0.f : mn0, sub1 = mn1 == -INFINITY ? 0.f : mn1;
-        float rs0 = 0.f, rs1 = 0.f;
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            s[nt][0] = exp2f(s[nt][0] - sub0); s[nt][1] = exp2f(s[nt][1] - sub0);
-            s[nt][2] = exp2f(s[nt][2] - sub1); s[nt][3] = exp2f(s[nt][3] - sub1);
-            rs0 += s[nt][0] + s[nt][1]; rs1 += s[nt][2] + s[nt][3];
-        }
-        rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1); rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
-        rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1); rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
-        l0 = l0 * c0 + rs0; l1 = l1 * c1 + rs1; m0 = mn0; m1 = mn1;
-        if (drop.on()) {
-            const uint64_t base = tile_pair_base(g, group, h, qt, kt);
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                float f0, f1;
-                pair_factors(drop, base + (uint64_t)(r0 * 32 + nt * 4 + tq), f0, f1); s[nt][0] *= f0; s[nt][1] *= f1;
-                pair_factors(drop, base + (uint64_t)(r1 * 32 + nt * 4 + tq), f0, f1); s[nt][2] *= f0; s[nt][3] *= f1;
-            }
-        }
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) { o[nt][0] *= c0; o[nt][1] *= c0; o[nt][2] *= c1; o[nt][3] *= c1; }
-        gemm_p_bkn<L>(o, s, Vs, lane);
-    }
-    // normalise, stage this warp's 16 rows through its own Q rows (no other warp reads them), coalesced store
-    const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
-    __syncwarp();
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-        *reinterpret_cast<uint32_t*>(Qs + L::at(r0, nt * 8 + 2 * tq)) = pack2(o[nt][0] * i0, o[nt][1] * i0);
-        *reinterpret_cast<uint32_t*>(Qs + L::at(r1, nt * 8 + 2 * tq)) = pack2(o[nt][2] * i1, o[nt][3] * i1);
-    }
-    __syncwarp();
-    store_rows16<L>(g, Qs, warp * 16, out, I, h * 64, ix.qseq, ix.qpos, group, lane);
-    if (tq == 0) {
-        if (ix.qseq[r0] >= 0) lse[row_of(g, group * g.G + ix.qseq[r0], ix.qpos[r0]) * g.H + h] = (m0 + log2f(l0)) * 0.6931471805599453f;
-        if (ix.qseq[r1] >= 0) lse[row_of(g, group * g.G + ix.qseq[r1], ix.qpos[r1]) * g.H + h] = (m1 + log2f(l1)) * 0.6931471805599453f;
-    }
-}
-
-// MODE 0: one tile (N <= 64): dQ, dK, dV in one CTA.  MODE 1: dQ of q tile blockIdx (loops key tiles).
-// MODE 2: dK, dV of key tile blockIdx (loops query tiles).
-template <int MODE>
-__global__ void __launch_bounds__(BT) attn_bwd_bf16_kernel(AttnGeom g, const bf16* __restrict__ qkv, const bf16* __restrict__ out,
-                                                           const float* __restrict__ lse, const bf16* __restrict__ d_out,
-                                                           bf16* __restrict__ d_qkv, Drop drop) {
-    using L = Pad;
-    extern __shared__ __align__(16) uint8_t smem_bwd[];
-    bf16* Qs = reinterpret_cast<bf16*>(smem_bwd);
-    bf16* Ks = Qs + L::TILE;
-    bf16* Vs = Ks + L::TILE;
-    bf16* dOs = Vs + L::TILE;
-    bf16* Ps = dOs + L::TILE;     // P * dropout factor   [q][key]
-    bf16* dSs = Ps + L::TILE;     // dS                   [q][key]
-    float* Drow = reinterpret_cast<float*>(dSs + L::TILE);
-    float* lse_s = Drow + TS;
-    AttnSmemIdx& ix = *reinterpret_cast<AttnSmemIdx*>(lse_s + TS);
-
-    const int I = g.H * 64, h = blockIdx.y;
-    const int64_t ld = 3 * (int64_t)I;
-    const int64_t group = blockIdx.x / g.tiles;
-    const int own = blockIdx.x % g.tiles;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
-    const int r0 = warp * 16 + gq, r1 = r0 + 8;
-    const float sl2 = g.scale * 1.4426950408889634f;
-    const int n_inner = MODE == 0 ? 1 : g.tiles;
-
-    float dq[8][4] = {}, dk[8][4] = {}, dv[8][4] = {};
-    for (int it = 0; it < n_inner; ++it) {
-        const int qt = MODE == 2 ? it : own, kt = MODE == 1 ? it : own;
-        __syncthreads();
-        if (MODE != 2 || it == 0) {
-            load_tile_bf16<L>(g, qkv, ld, I + h * 64, group, kt, Ks);
-            load_tile_bf16<L>(g, qkv, ld, 2 * I + h * 64, group, kt, Vs);
-            fill_idx(g, group, kt, ix.kseq, ix.kpos, -2);
-        }
-        if (MODE != 1 || it == 0) {
-            load_tile_bf16<L>(g, qkv, ld, h * 64, group, qt, Qs);
-            load_tile_bf16<L>(g, d_out, I, h * 64, group, qt, dOs);
-            fill_idx(g, group, qt, ix.qseq, ix.qpos, -1);
-        }
-        __syncthreads();
-        if (MODE != 1 || it == 0) {
-            // D_i = dO_i . O_i, lse_i  (warp: 16 rows, two rows per pass, 16 lanes x 4 elements per row)
-            for (int k = 0; k < 8; ++k) {
-                const int r = warp * 16 + k * 2 + (lane >> 4), c = (lane & 15) * 4;
-                float dsum = 0.f, l = 0.f;
-                if (ix.qseq[r] >= 0) {
-                    const int64_t row = row_of(g, group * g.G + ix.qseq[r], ix.qpos[r]);
-                    const uint2 ov = *reinterpret_cast<const uint2*>(out + row * I + h * 64 + c);
-                    const __nv_bfloat162 o01 = *reinterpret_cast<const __nv_bfloat162*>(&ov.x), o23 = *reinterpret_cast<const __nv_bfloat162*>(&ov.y);
-                    const bf16* dp = dOs + L::at(r, c);
-                    dsum = __bfloat162float(dp[0]) * __low2float(o01) + __bfloat162float(dp[1]) * __high2float(o01) +
-                           __bfloat162float(dp[2]) * __low2float(o23) + __bfloat162float(dp[3]) * __high2float(o23);
-                    l = lse[row * g.H + h];
-                }
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
-                if ((lane & 15) == 0) { Drow[r] = dsum; lse_s[r] = l * 1.4426950408889634f; }
-            }
-            __syncthreads();
-        }
-        float s[8][4] = {}, dp[8][4] = {};
-        gemm_a_bnk<L>(s, Qs, warp * 16, Ks, lane);
-        gemm_a_bnk<L>(dp, dOs, warp * 16, Vs, lane);
-        const int qs0 = ix.qseq[r0], qs1 = ix.qseq[r1];
-        const float L0 = lse_s[r0], L1 = lse_s[r1], D0 = Drow[r0], D1 = Drow[r1];
-        const uint64_t base = tile_pair_base(g, group, h, qt, kt);
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            const int c = nt * 8 + 2 * tq;
-            const int ks0 = ix.kseq[c], ks1 = ix.kseq[c + 1];
-            float p0 = qs0 == ks0 ? exp2f(s[nt][0] * sl2 - L0) : 0.f, p1 = qs0 == ks1 ? exp2f(s[nt][1] * sl2 - L0) : 0.f;
-            float p2 = qs1 == ks0 ? exp2f(s[nt][2] * sl2 - L1) : 0.f, p3 = qs1 == ks1 ? exp2f(s[nt][3] * sl2 - L1) : 0.f;
-            float f0 = 1.f, f1 = 1.f, f2 = 1.f, f3 = 1.f;
-            if (drop.on()) {
-                pair_factors(drop, base + (uint64_t)(r0 * 32 + nt * 4 + tq), f0, f1);
-                pair_factors(drop, base + (uint64_t)(r1 * 32 + nt * 4 + tq), f2, f3);
-            }
-            // dS = P * (f * dP - D) * scale ; Pf = P * f
-            s[nt][0] = p0 * (f0 * dp[nt][0] - D0) * g.scale; s[nt][1] = p1 * (f1 * dp[nt][1] - D0) * g.scale;
-            s[nt][2] = p2 * (f2 * dp[nt][2] - D1) * g.scale; s[nt][3] = p3 * (f3 * dp[nt][3] - D1) * g.scale;
-            if (MODE != 1) {
-                *reinterpret_cast<uint32_t*>(Ps + L::at(r0, c)) = pack2(p0 * f0, p1 * f1);
-                *reinterpret_cast<uint32_t*>(Ps + L::at(r1, c)) = pack2(p2 * f2, p3 * f3);
-                *reinterpret_cast<uint32_t*>(dSs + L::at(r0, c)) = pack2(s[nt][0], s[nt][1]);
-                *reinterpret_cast<uint32_t*>(dSs + L::at(r1, c)) = pack2(s[nt][2], s[nt][3]);
-            }
-        }
-        if (MODE != 2) gemm_p_bkn<L>(dq, s, Ks, lane);          // dQ[16 rows] += dS . K
-        if (MODE != 1) {
-            __syncthreads();
-            gemm_at_bkn<L>(dv, Ps, warp * 16, dOs, lane);       // dV[16 keys] += (P f)^T . dO
-            gemm_at_bkn<L>(dk, dSs, warp * 16, Qs, lane);       // dK[16 keys] += dS^T . Q
-        }
-    }
-    __syncthreads();
-    // stage results through smem (Q/K/V tiles are dead now) and store coalesced
-    if (MODE != 2) {
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            *reinterpret_cast<uint32_t*>(Qs + L::at(r0, nt * 8 + 2 * tq)) = pack2(dq[nt][0], dq[nt][1]);
-            *reinterpret_cast<uint32_t*>(Qs + L::at(r1, nt * 8 + 2 * tq)) = pack2(dq[nt][2], dq[nt][3]);
-        }
-    }
-    if (MODE != 1) {
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            *reinterpret_cast<uint32_t*>(Ks + L::at(r0, nt * 8 + 2 * tq)) = pack2(dk[nt][0], dk[nt][1]);
-            *reinterpret_cast<uint32_t*>(Ks + L::at(r1, nt * 8 + 2 * tq)) = pack2(dk[nt][2], dk[nt][3]);
-            *reinterpret_cast<uint32_t*>(Vs + L::at(r0, nt * 8 + 2 * tq)) = pack2(dv[nt][0], dv[nt][1]);
-            *reinterpret_cast<uint32_t*>(Vs + L::at(r1, nt * 8 + 2 * tq)) = pack2(dv[nt][2], dv[nt][3]);
-        }
-    }
-    __syncwarp();
-    if (MODE != 2) store_rows16<L>(g, Qs, warp * 16, d_qkv, ld, h * 64, ix.qseq, ix.qpos, group, lane);
-    if (MODE != 1) {
-        store_rows16<L>(g, Ks, warp * 16, d_qkv, ld, I + h * 64, ix.kseq, ix.kpos, group, lane);
-        store_rows16<L>(g, Vs, warp * 16, d_qkv, ld, 2 * I + h * 64, ix.kseq, ix.kpos, group, lane);
-    }
 }
 
 
@@ -600,7 +365,257 @@ __global__ void __launch_bounds__(BT, 3) attn_bwd_bf16_heads_kernel(AttnGeom g, 
     }
 }
 
-constexpr size_t kBwdSmem = sizeof(bf16) * 6 * Pad::TILE + sizeof(float) * 2 * TS + sizeof(AttnSmemIdx);
+
+// =========================================================================================================
+// Long sequences (N > 64) forward: one CTA = 128 query rows (8 warps) of one (sequence, head); the 64-key K/V tiles are
+// streamed through a cp.async double buffer (tile kt+1 lands while tile kt is multiplied), online softmax in registers.
+// =========================================================================================================
+constexpr int LQ = 128, LT = 256;
+constexpr size_t kFwdLongSmem = sizeof(bf16) * (LQ * 72 + 4 * Pad::TILE);
+
+__global__ void __launch_bounds__(LT, 2) attn_fwd_bf16_long_kernel(AttnGeom g, const bf16* __restrict__ qkv, bf16* __restrict__ out,
+                                                                   float* __restrict__ lse, Drop drop) {
+    using L = Pad;
+    extern __shared__ __align__(16) uint8_t smem_l[];
+    bf16* Qs = reinterpret_cast<bf16*>(smem_l);            // [128][72]
+    bf16* KV = Qs + LQ * 72;                                // [2 buffers][K, V][64][72]
+    const int I = g.H * 64, h = blockIdx.y;
+    const int64_t ld = 3 * (int64_t)I;
+    const int qtiles = (g.N + LQ - 1) / LQ;
+    const int64_t seq = blockIdx.x / qtiles;
+    const int qt = blockIdx.x % qtiles;
+    const int64_t row_base = (seq / g.inner) * g.N * g.inner + (seq % g.inner);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+    const int r0 = warp * 16 + gq, r1 = r0 + 8;
+    const float sl2 = g.scale * 1.4426950408889634f;
+    const int c8 = (threadIdx.x & 7) * 8;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {                           // Q tile: 128 rows x 8 chunks
+        const int r = (threadIdx.x >> 3) + 32 * k, pos = qt * LQ + r;
+        const bool ok = pos < g.N;
+        cp_async16(Qs + L::at(r, c8), qkv + (row_base + (int64_t)(ok ? pos : 0) * g.inner) * ld + h * 64 + c8, ok);
+    }
+    auto prefetch_kv = [&](int kt, int b) {
+        bf16* Kb = KV + (size_t)b * 2 * L::TILE; bf16* Vb = Kb + L::TILE;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int r = (threadIdx.x >> 3) + 32 * k, pos = kt * TS + r;
+            const bool ok = pos < g.N;
+            const bf16* src = qkv + (row_base + (int64_t)(ok ? pos : 0) * g.inner) * ld + h * 64 + c8;
+            cp_async16(Kb + L::at(r, c8), src + I, ok);
+            cp_async16(Vb + L::at(r, c8), src + 2 * I, ok);
+        }
+        cp_async_commit();
+    };
+    prefetch_kv(0, 0);
+    float o[8][4] = {};
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    for (int kt = 0; kt < g.tiles; ++kt) {
+        const int b = kt & 1;
+        cp_async_wait_all();
+        __syncthreads();
+        if (kt + 1 < g.tiles) prefetch_kv(kt + 1, b ^ 1);
+        const bf16* Ks = KV + (size_t)b * 2 * L::TILE; const bf16* Vs = Ks + L::TILE;
+        float s[8][4] = {};
+        gemm_a_bnk<L>(s, Qs, warp * 16, Ks, lane);
+        const int kvalid = g.N - kt * TS;                  // keys of this tile with column index < kvalid exist
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int c = nt * 8 + 2 * tq;
+            s[nt][0] = c < kvalid ? s[nt][0] * sl2 : -INFINITY; s[nt][1] = c + 1 < kvalid ? s[nt][1] * sl2 : -INFINITY;
+            s[nt][2] = c < kvalid ? s[nt][2] * sl2 : -INFINITY; s[nt][3] = c + 1 < kvalid ? s[nt][3] * sl2 : -INFINITY;
+            mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1])); mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);     // every tile has >= 1 valid key: mn is finite
+        float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            s[nt][0] = exp2f(s[nt][0] - mn0); s[nt][1] = exp2f(s[nt][1] - mn0);
+            s[nt][2] = exp2f(s[nt][2] - mn1); s[nt][3] = exp2f(s[nt][3] - mn1);
+            rs0 += s[nt][0] + s[nt][1]; rs1 += s[nt][2] + s[nt][3];
+        }
+        rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1); rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
+        rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1); rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
+        l0 = l0 * c0 + rs0; l1 = l1 * c1 + rs1; m0 = mn0; m1 = mn1;
+        if (drop.on()) {   // same (64-row query tile, key tile, row, pair) indexing as the backward kernels
+            const uint64_t base = tile_pair_base(g, seq, h, 2 * qt + (warp >> 2), kt);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                float f0, f1;
+                pair_factors(drop, base + (uint64_t)((r0 & 63) * 32 + nt * 4 + tq), f0, f1); s[nt][0] *= f0; s[nt][1] *= f1;
+                pair_factors(drop, base + (uint64_t)((r1 & 63) * 32 + nt * 4 + tq), f0, f1); s[nt][2] *= f0; s[nt][3] *= f1;
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) { o[nt][0] *= c0; o[nt][1] *= c0; o[nt][2] *= c1; o[nt][3] *= c1; }
+        gemm_p_bkn<L>(o, s, Vs, lane);
+    }
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    __syncwarp();
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {                        // stage through this warp's own Q rows
+        *reinterpret_cast<uint32_t*>(Qs + L::at(r0, nt * 8 + 2 * tq)) = pack2(o[nt][0] * i0, o[nt][1] * i0);
+        *reinterpret_cast<uint32_t*>(Qs + L::at(r1, nt * 8 + 2 * tq)) = pack2(o[nt][2] * i1, o[nt][3] * i1);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = lane + 32 * k;
+        const int r = warp * 16 + (i >> 3), c = (i & 7) * 8, pos = qt * LQ + r;
+        if (pos < g.N)
+            *reinterpret_cast<uint4*>(out + (row_base + (int64_t)pos * g.inner) * I + h * 64 + c) = *reinterpret_cast<const uint4*>(Qs + L::at(r, c));
+    }
+    if (tq == 0) {
+        const int p0 = qt * LQ + r0, p1 = qt * LQ + r1;
+        if (p0 < g.N) lse[(row_base + (int64_t)p0 * g.inner) * g.H + h] = (m0 + log2f(l0)) * 0.6931471805599453f;
+        if (p1 < g.N) lse[(row_base + (int64_t)p1 * g.inner) * g.H + h] = (m1 + log2f(l1)) * 0.6931471805599453f;
+    }
+}
+
+
+// =========================================================================================================
+// Long sequences backward, two passes without atomics:
+//   MODE 1: CTA = one 64-row query tile, loops the key tiles (cp.async double buffer)  -> dQ
+//   MODE 2: CTA = one 64-key tile, loops the query tiles (cp.async double buffer)      -> dK, dV
+// D_i = dO_i . O_i is computed in-kernel per query tile (dO tile in smem, O rows from global / L2).
+// =========================================================================================================
+constexpr size_t kBwdLongSmem = sizeof(bf16) * 8 * Pad::TILE + sizeof(float) * 2 * TS;
+
+template <int MODE>
+__global__ void __launch_bounds__(BT, 2) attn_bwd_bf16_long_kernel(AttnGeom g, const bf16* __restrict__ qkv, const bf16* __restrict__ out,
+                                                                   const float* __restrict__ lse, const bf16* __restrict__ d_out,
+                                                                   bf16* __restrict__ d_qkv, Drop drop) {
+    using L = Pad;
+    extern __shared__ __align__(16) uint8_t smem_l[];
+    bf16* F0 = reinterpret_cast<bf16*>(smem_l);     // fixed tiles: MODE 1 -> Q, dO ; MODE 2 -> K, V
+    bf16* F1 = F0 + L::TILE;
+    bf16* LB = F1 + L::TILE;                         // looped tiles [2 buffers][2]: MODE 1 -> K, V ; MODE 2 -> Q, dO
+    bf16* Ps = LB + 4 * L::TILE;
+    bf16* dSs = Ps + L::TILE;
+    float* Drow = reinterpret_cast<float*>(dSs + L::TILE);
+    float* lse_s = Drow + TS;
+    const int I = g.H * 64, h = blockIdx.y;
+    const int64_t ld = 3 * (int64_t)I;
+    const int64_t seq = blockIdx.x / g.tiles;
+    const int own = blockIdx.x % g.tiles;
+    const int64_t row_base = (seq / g.inner) * g.N * g.inner + (seq % g.inner);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+    const int r0 = warp * 16 + gq, r1 = r0 + 8;
+    const float sl2 = g.scale * 1.4426950408889634f;
+    const int c8 = (threadIdx.x & 7) * 8;
+    // tile loaders: which = 0 (q), 1 (k), 2 (v) columns of qkv, 3 = d_out
+    auto load_tile = [&](bf16* dst, int which, int tile) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = (threadIdx.x >> 3) + 16 * k, pos = tile * TS + r;
+            const bool ok = pos < g.N;
+            const int64_t row = row_base + (int64_t)(ok ? pos : 0) * g.inner;
+            const bf16* src = which == 3 ? d_out + row * I + h * 64 + c8 : qkv + row * ld + which * I + h * 64 + c8;
+            cp_async16(dst + L::at(r, c8), src, ok);
+        }
+    };
+    auto compute_D = [&](const bf16* dOs, int qt) {   // Drow / lse_s of query tile qt (dO tile already in smem)
+        for (int k = 0; k < 8; ++k) {
+            const int r = warp * 16 + k * 2 + (lane >> 4), c = (lane & 15) * 4, pos = qt * TS + r;
+            float dsum = 0.f, l = 0.f;
+            if (pos < g.N) {
+                const int64_t row = row_base + (int64_t)pos * g.inner;
+                const uint2 ov = *reinterpret_cast<const uint2*>(out + row * I + h * 64 + c);
+                const __nv_bfloat162 o01 = *reinterpret_cast<const __nv_bfloat162*>(&ov.x), o23 = *reinterpret_cast<const __nv_bfloat162*>(&ov.y);
+                const bf16* dp = dOs + L::at(r, c);
+                dsum = __bfloat162float(dp[0]) * __low2float(o01) + __bfloat162float(dp[1]) * __high2float(o01) +
+                       __bfloat162float(dp[2]) * __low2float(o23) + __bfloat162float(dp[3]) * __high2float(o23);
+                l = lse[row * g.H + h];
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+            if ((lane & 15) == 0) { Drow[r] = dsum; lse_s[r] = l * 1.4426950408889634f; }
+        }
+    };
+    if (MODE == 1) { load_tile(F0, 0, own); load_tile(F1, 3, own); load_tile(LB, 1, 0); load_tile(LB + L::TILE, 2, 0); }
+    else           { load_tile(F0, 1, own); load_tile(F1, 2, own); load_tile(LB, 0, 0); load_tile(LB + L::TILE, 3, 0); }
+    cp_async_commit();
+    float acc0[8][4] = {}, acc1[8][4] = {};          // MODE 1: acc0 = dQ ; MODE 2: acc0 = dK, acc1 = dV
+    for (int it = 0; it < g.tiles; ++it) {
+        const int b = it & 1;
+        cp_async_wait_all();
+        __syncthreads();
+        if (it + 1 < g.tiles) {
+            bf16* nb = LB + (size_t)(b ^ 1) * 2 * L::TILE;
+            if (MODE == 1) { load_tile(nb, 1, it + 1); load_tile(nb + L::TILE, 2, it + 1); }
+            else           { load_tile(nb, 0, it + 1); load_tile(nb + L::TILE, 3, it + 1); }
+            cp_async_commit();
+        }
+        const bf16* L0 = LB + (size_t)b * 2 * L::TILE; const bf16* L1 = L0 + L::TILE;
+        const bf16* Qs = MODE == 1 ? F0 : L0; const bf16* dOs = MODE == 1 ? F1 : L1;
+        const bf16* Ks = MODE == 1 ? L0 : F0; const bf16* Vs = MODE == 1 ? L1 : F1;
+        const int qt = MODE == 1 ? own : it, kt = MODE == 1 ? it : own;
+        if (MODE == 2 || it == 0) { compute_D(dOs, qt); __syncthreads(); }
+        float s[8][4] = {}, dp[8][4] = {};
+        gemm_a_bnk<L>(s, Qs, warp * 16, Ks, lane);
+        gemm_a_bnk<L>(dp, dOs, warp * 16, Vs, lane);
+        const float Lr0 = lse_s[r0], Lr1 = lse_s[r1], D0 = Drow[r0], D1 = Drow[r1];
+        const bool q0 = qt * TS + r0 < g.N, q1 = qt * TS + r1 < g.N;
+        const int kvalid = g.N - kt * TS;
+        const uint64_t base = tile_pair_base(g, seq, h, qt, kt);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int c = nt * 8 + 2 * tq;
+            const bool k0 = c < kvalid, k1 = c + 1 < kvalid;
+            const float p0 = (q0 && k0) ? exp2f(s[nt][0] * sl2 - Lr0) : 0.f, p1 = (q0 && k1) ? exp2f(s[nt][1] * sl2 - Lr0) : 0.f;
+            const float p2 = (q1 && k0) ? exp2f(s[nt][2] * sl2 - Lr1) : 0.f, p3 = (q1 && k1) ? exp2f(s[nt][3] * sl2 - Lr1) : 0.f;
+            float f0 = 1.f, f1 = 1.f, f2 = 1.f, f3 = 1.f;
+            if (drop.on()) {
+                pair_factors(drop, base + (uint64_t)(r0 * 32 + nt * 4 + tq), f0, f1);
+                pair_factors(drop, base + (uint64_t)(r1 * 32 + nt * 4 + tq), f2, f3);
+            }
+            s[nt][0] = p0 * (f0 * dp[nt][0] - D0) * g.scale; s[nt][1] = p1 * (f1 * dp[nt][1] - D0) * g.scale;
+            s[nt][2] = p2 * (f2 * dp[nt][2] - D1) * g.scale; s[nt][3] = p3 * (f3 * dp[nt][3] - D1) * g.scale;
+            if (MODE == 2) {
+                *reinterpret_cast<uint32_t*>(Ps + L::at(r0, c)) = pack2(p0 * f0, p1 * f1);
+                *reinterpret_cast<uint32_t*>(Ps + L::at(r1, c)) = pack2(p2 * f2, p3 * f3);
+                *reinterpret_cast<uint32_t*>(dSs + L::at(r0, c)) = pack2(s[nt][0], s[nt][1]);
+                *reinterpret_cast<uint32_t*>(dSs + L::at(r1, c)) = pack2(s[nt][2], s[nt][3]);
+            }
+        }
+        if (MODE == 1) {
+            gemm_p_bkn<L>(acc0, s, Ks, lane);                    // dQ[16 rows] += dS . K
+        } else {
+            __syncthreads();
+            gemm_at_bkn<L>(acc1, Ps, warp * 16, dOs, lane);      // dV[16 keys] += (P f)^T . dO
+            gemm_at_bkn<L>(acc0, dSs, warp * 16, Qs, lane);      // dK[16 keys] += dS^T . Q
+        }
+    }
+    __syncthreads();
+    // stage through the (dead) P / dS tiles and store coalesced: this warp's 16 rows of the CTA's own tile
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const int c = nt * 8 + 2 * tq;
+        *reinterpret_cast<uint32_t*>(Ps + L::at(r0, c)) = pack2(acc0[nt][0], acc0[nt][1]);
+        *reinterpret_cast<uint32_t*>(Ps + L::at(r1, c)) = pack2(acc0[nt][2], acc0[nt][3]);
+        if (MODE == 2) {
+            *reinterpret_cast<uint32_t*>(dSs + L::at(r0, c)) = pack2(acc1[nt][0], acc1[nt][1]);
+            *reinterpret_cast<uint32_t*>(dSs + L::at(r1, c)) = pack2(acc1[nt][2], acc1[nt][3]);
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = lane + 32 * k;
+        const int r = warp * 16 + (i >> 3), c = (i & 7) * 8, pos = own * TS + r;
+        if (pos >= g.N) continue;
+        bf16* dst = d_qkv + (row_base + (int64_t)pos * g.inner) * ld + h * 64 + c;
+        if (MODE == 1) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(Ps + L::at(r, c));
+        else {
+            *reinterpret_cast<uint4*>(dst + I) = *reinterpret_cast<const uint4*>(Ps + L::at(r, c));
+            *reinterpret_cast<uint4*>(dst + 2 * I) = *reinterpret_cast<const uint4*>(dSs + L::at(r, c));
+        }
+    }
+}
 
 int attention_fwd_bf16(const msst_attn_dims* d, const bf16* qkv, bf16* out, float* lse, cudaStream_t st) {
     AttnGeom g;
@@ -617,8 +632,17 @@ int attention_fwd_bf16(const msst_attn_dims* d, const bf16* qkv, bf16* out, floa
         MSST_LAUNCH_CHECK();
         return MSST_OK;
     }
-    attn_fwd_bf16_kernel<<<dim3((unsigned)(g.groups * g.tiles), g.H), BT, 0, st>>>(g, qkv, out, lse, drop);
-    MSST_LAUNCH_CHECK();
+    {   // N > 64: 128-row query tiles, K/V streamed through a cp.async double buffer
+        static bool lattr = false;
+        if (!lattr) {
+            MSST_CUDA(cudaFuncSetAttribute(attn_fwd_bf16_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdLongSmem));
+            lattr = true;
+        }
+        const int64_t qtiles = (g.N + LQ - 1) / LQ;
+        MSST_REQUIRE(g.n_seq * qtiles < (int64_t)2147483647, "attention: grid too large");
+        attn_fwd_bf16_long_kernel<<<dim3((unsigned)(g.n_seq * qtiles), g.H), LT, kFwdLongSmem, st>>>(g, qkv, out, lse, drop);
+        MSST_LAUNCH_CHECK();
+    }
     return MSST_OK;
 }
 
@@ -629,13 +653,6 @@ int attention_bwd_bf16(const msst_attn_dims* d, const bf16* qkv, const bf16* out
     if (g.n_seq == 0) return MSST_OK;
     const Drop drop = make_drop(d->drop_p, d->seed, d->site, d->seed_dev);
     const dim3 grid((unsigned)(g.groups * g.tiles), g.H);
-    static bool attr_set = false;
-    if (!attr_set) {
-        MSST_CUDA(cudaFuncSetAttribute(attn_bwd_bf16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
-        MSST_CUDA(cudaFuncSetAttribute(attn_bwd_bf16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
-        MSST_CUDA(cudaFuncSetAttribute(attn_bwd_bf16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
-        attr_set = true;
-    }
     if (g.tiles == 1) {
         static bool hattr = false;
         if (!hattr) {
@@ -644,10 +661,16 @@ int attention_bwd_bf16(const msst_attn_dims* d, const bf16* qkv, const bf16* out
         }
         attn_bwd_bf16_heads_kernel<<<(unsigned)g.groups, BT, kBwdHeadsSmem, st>>>(g, qkv, lse, d_out, d_qkv, drop);
         MSST_LAUNCH_CHECK();
-    } else {   // long sequences: dQ pass over key tiles, dK/dV pass over query tiles (no atomics)
-        attn_bwd_bf16_kernel<1><<<grid, BT, kBwdSmem, st>>>(g, qkv, out, lse, d_out, d_qkv, drop);
+    } else {   // long sequences: dQ pass over key tiles, dK/dV pass over query tiles (no atomics), cp.async double-buffered
+        static bool lattr = false;
+        if (!lattr) {
+            MSST_CUDA(cudaFuncSetAttribute(attn_bwd_bf16_long_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdLongSmem));
+            MSST_CUDA(cudaFuncSetAttribute(attn_bwd_bf16_long_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdLongSmem));
+            lattr = true;
+        }
+        attn_bwd_bf16_long_kernel<1><<<grid, BT, kBwdLongSmem, st>>>(g, qkv, out, lse, d_out, d_qkv, drop);
         MSST_LAUNCH_CHECK();
-        attn_bwd_bf16_kernel<2><<<grid, BT, kBwdSmem, st>>>(g, qkv, out, lse, d_out, d_qkv, drop);
+        attn_bwd_bf16_long_kernel<2><<<grid, BT, kBwdLongSmem, st>>>(g, qkv, out, lse, d_out, d_qkv, drop);
         MSST_LAUNCH_CHECK();
     }
     return MSST_OK;
