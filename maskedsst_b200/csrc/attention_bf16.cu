@@ -623,20 +623,18 @@ int attention_fwd_bf16(const msst_attn_dims* d, const bf16* qkv, bf16* out, floa
     if (g.n_seq == 0) return MSST_OK;
     const Drop drop = make_drop(d->drop_p, d->seed, d->site, d->seed_dev);
     if (g.tiles == 1) {   // N <= 64: head-looping, cp.async double-buffered kernel
-        static bool attr_set = false;
-        if (!attr_set) {
+        static PerDeviceOnce attr_set;
+        if (attr_set.first()) {
             MSST_CUDA(cudaFuncSetAttribute(attn_fwd_bf16_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdHeadsSmem));
-            attr_set = true;
         }
         attn_fwd_bf16_heads_kernel<<<(unsigned)g.groups, BT, kFwdHeadsSmem, st>>>(g, qkv, out, lse, drop);
         MSST_LAUNCH_CHECK();
         return MSST_OK;
     }
     {   // N > 64: 128-row query tiles, K/V streamed through a cp.async double buffer
-        static bool lattr = false;
-        if (!lattr) {
+        static PerDeviceOnce lattr;
+        if (lattr.first()) {
             MSST_CUDA(cudaFuncSetAttribute(attn_fwd_bf16_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdLongSmem));
-            lattr = true;
         }
         const int64_t qtiles = (g.N + LQ - 1) / LQ;
         MSST_REQUIRE(g.n_seq * qtiles < (int64_t)2147483647, "attention: grid too large");
@@ -654,19 +652,17 @@ int attention_bwd_bf16(const msst_attn_dims* d, const bf16* qkv, const bf16* out
     const Drop drop = make_drop(d->drop_p, d->seed, d->site, d->seed_dev);
     const dim3 grid((unsigned)(g.groups * g.tiles), g.H);
     if (g.tiles == 1) {
-        static bool hattr = false;
-        if (!hattr) {
+        static PerDeviceOnce hattr;
+        if (hattr.first()) {
             MSST_CUDA(cudaFuncSetAttribute(attn_bwd_bf16_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdHeadsSmem));
-            hattr = true;
         }
         attn_bwd_bf16_heads_kernel<<<(unsigned)g.groups, BT, kBwdHeadsSmem, st>>>(g, qkv, lse, d_out, d_qkv, drop);
         MSST_LAUNCH_CHECK();
     } else {   // long sequences: dQ pass over key tiles, dK/dV pass over query tiles (no atomics), cp.async double-buffered
-        static bool lattr = false;
-        if (!lattr) {
+        static PerDeviceOnce lattr;
+        if (lattr.first()) {
             MSST_CUDA(cudaFuncSetAttribute(attn_bwd_bf16_long_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdLongSmem));
             MSST_CUDA(cudaFuncSetAttribute(attn_bwd_bf16_long_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdLongSmem));
-            lattr = true;
         }
         attn_bwd_bf16_long_kernel<1><<<grid, BT, kBwdLongSmem, st>>>(g, qkv, out, lse, d_out, d_qkv, drop);
         MSST_LAUNCH_CHECK();

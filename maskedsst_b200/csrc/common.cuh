@@ -30,6 +30,19 @@ void count_launch();
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+// cudaFuncSetAttribute is per device: one-time setup guards are kept per device ordinal (one process may drive several GPUs)
+struct PerDeviceOnce {
+    unsigned long long done = 0ull;
+    bool first() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const unsigned long long bit = 1ull << (dev & 63);
+        if (done & bit) return false;
+        done |= bit;
+        return true;
+    }
+};
+
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- warp helpers ----

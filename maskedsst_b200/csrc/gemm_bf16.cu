@@ -307,10 +307,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 // ---------------------------------------------------------------------------------------------------------
 // weight gradient: dW[N,K] += dY[M,N]^T X[M,K].  UMMA view: D[128 rows of N][BN cols of K] += A^T B with the
 // reduction dim = tokens; both operand tiles are [64 tokens][64-element chunks] in smem -> MN-major descriptors
-// (LBO = 8 KB between 64-element chunks, SBO = 1 KB between 8-token groups).  grid = (output tiles, splits).
+// (LBO = 16 KB between 64-element chunks, SBO = 1 KB between 8-token groups).  grid = (output tiles, splits).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int WG_TOK = 64;                         // tokens per stage
-constexpr uint32_t WG_CHUNK = WG_TOK * 128;        // bytes of one [64 tokens][64 elements] chunk = 8 KB
+constexpr int WG_TOK = 128;                        // tokens per stage
+constexpr int WG_STAGES = 3;
+constexpr uint32_t WG_CHUNK = WG_TOK * 128;        // bytes of one [128 tokens][64 elements] chunk = 16 KB
 
 struct WgradParams {
     int64_t M; int N, K;
@@ -327,7 +328,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tma_dy, const __grid_const
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t a_bytes = 2 * WG_CHUNK, b_bytes = (uint32_t)p.n_chunks_b * WG_CHUNK;
     const uint32_t stage_bytes = a_bytes + b_bytes;
-    GemmBars* bars = reinterpret_cast<GemmBars*>(smem + (size_t)GB_STAGES * stage_bytes);
+    GemmBars* bars = reinterpret_cast<GemmBars*>(smem + (size_t)WG_STAGES * stage_bytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile_n = blockIdx.x / p.tiles_k_out, tile_k = blockIdx.x % p.tiles_k_out;
     const int64_t total_tb = (p.M + WG_TOK - 1) / WG_TOK;
@@ -336,7 +337,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tma_dy, const __grid_const
 
     if (warp == 0 && elect_one()) { prefetch_tmap(&tma_dy); prefetch_tmap(&tma_x); }
     if (warp == 1 && elect_one()) {
-        for (int s = 0; s < GB_STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+        for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
         mbar_init(&bars->tmem_full[0], 1);
         fence_barrier_init();
     }
@@ -358,7 +359,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tma_dy, const __grid_const
                     tma_load_2d(s + WG_CHUNK, &tma_dy, &bars->full[stage], tile_n * GB_M + 64, tok);
                     for (int c = 0; c < p.n_chunks_b; ++c)
                         tma_load_2d(s + a_bytes + c * WG_CHUNK, &tma_x, &bars->full[stage], tile_k * p.block_n + c * 64, tok);
-                    if (++stage == GB_STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         } else if (warp == 1) {
@@ -372,7 +373,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tma_dy, const __grid_const
                     for (int k = 0; k < WG_TOK / 16; ++k)   // 16 tokens = 2 KB per UMMA_K step
                         umma_bf16(tmem_base, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), p.idesc, (tb > tb0) || k != 0);
                     umma_commit(&bars->empty[stage]);
-                    if (++stage == GB_STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&bars->tmem_full[0]);
             }
@@ -465,15 +466,14 @@ int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st) {
     const size_t smem = (size_t)GB_STAGES * (GB_A_BYTES + (size_t)p.block_n * GB_K * 2) + 256 + gb_epi_smem(mode) + 1024;
     const int64_t tiles = p.tiles_m * p.tiles_n;
     const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.first()) {
         MSST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         MSST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         MSST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         MSST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         MSST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         MSST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
     }
     switch (mode) {
         case 0: gemm_tn_kernel<0><<<grid, GB_THREADS, smem, st>>>(ta, tb, p); break;
@@ -493,7 +493,7 @@ int gemm_wgrad_bf16(const __nv_bfloat16* dy, const __nv_bfloat16* x, float* dW, 
     WgradParams p{};
     p.M = M; p.N = N; p.K = K; p.dW = dW;
     const int k32 = (K + 31) / 32 * 32;
-    p.block_n = k32 < 256 ? k32 : 256;
+    p.block_n = k32 < 128 ? k32 : 128;     // <= 2 chunks of B per stage: 3 stages x 64 KB of smem
     p.n_chunks_b = (p.block_n + 63) / 64;
     p.tiles_n_out = (N + GB_M - 1) / GB_M;
     p.tiles_k_out = (K + p.block_n - 1) / p.block_n;
@@ -509,11 +509,10 @@ int gemm_wgrad_bf16(const __nv_bfloat16* dy, const __nv_bfloat16* x, float* dW, 
     CUtensorMap ta, tb;
     if (int rc = make_tmap(&ta, dy, M, N, N, WG_TOK)) return rc;
     if (int rc = make_tmap(&tb, x, M, K, K, WG_TOK)) return rc;
-    const size_t smem = (size_t)GB_STAGES * (2 * WG_CHUNK + (size_t)p.n_chunks_b * WG_CHUNK) + sizeof(GemmBars) + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    const size_t smem = (size_t)WG_STAGES * (2 * WG_CHUNK + (size_t)p.n_chunks_b * WG_CHUNK) + sizeof(GemmBars) + 1024;
+    static PerDeviceOnce attr_set;
+    if (attr_set.first()) {
         MSST_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
     }
     gemm_wgrad_kernel<<<dim3(out_tiles, (unsigned)splits), WG_THREADS, smem, st>>>(ta, tb, p);
     MSST_LAUNCH_CHECK();

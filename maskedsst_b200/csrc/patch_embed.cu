@@ -325,7 +325,7 @@ static int launch_bwd(const EmbedGeom& g, int n_wb, size_t smem, cudaStream_t st
                       const uint8_t* mask, const float* d_tokens, const float* d_pln, float* d_pre_w, float* d_pre_b,
                       float* d_W, float* d_bias, float* d_post_w, float* d_post_b, float* d_pos, float* d_mt, Drop drop) {
     const int chunks = (g.S + kTok - 1) / kTok;
-    int nb = (int)ceil_div(2 * kNumSMs, (int64_t)g.C * chunks);
+    int nb = (int)((2 * kNumSMs) / ((int64_t)g.C * chunks));   // floor: at most two full waves of one CTA per SM (no tail wave)
     nb = nb < 1 ? 1 : (nb > g.B ? g.B : nb);
     MSST_CUDA(cudaFuncSetAttribute(patch_embed_bwd_kernel<NJ, PMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     patch_embed_bwd_kernel<NJ, PMAX><<<dim3(g.C * chunks, nb), kThreads, smem, st>>>(

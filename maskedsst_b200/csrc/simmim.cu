@@ -17,7 +17,9 @@ __device__ __forceinline__ float target_pixel(const DecGeom& g, const float* __r
     return img[((int64_t)(b * g.C + c) * g.p0 + p0i) * g.HW + (int64_t)(h * g.p1 + p1i) * g.Wimg + (w * g.p1 + p2i)];
 }
 
-template <int NJ>
+// lane p < P fetches target element p and bias p of the item up front (one load instruction each instead of P dependent
+// scalar loads inside the reduction loop); the P dot products are unrolled so their shuffles interleave.
+template <int NJ, int PMAX>
 __global__ void __launch_bounds__(DT) decode_fwd_kernel(DecGeom g, const float* __restrict__ enc, const int64_t* __restrict__ idx,
                                                         const float* __restrict__ img, const float* __restrict__ tgt_tok,
                                                         const float* __restrict__ W, const float* __restrict__ bias,
@@ -31,17 +33,23 @@ __global__ void __launch_bounds__(DT) decode_fwd_kernel(DecGeom g, const float* 
         float e[NJ];
 #pragma unroll
         for (int j = 0; j < NJ; ++j) e[j] = enc[((int64_t)b * g.T + t) * g.D + lane + 32 * j];
-        float l1 = 0.f;
-        for (int p = 0; p < g.P; ++p) {
-            const float* w = W + ((int64_t)blk * g.P + p) * g.D;
-            float a = 0.f;
+        float tgb = 0.f;   // target_p - bias_p held by lane p
+        if (lane < g.P)
+            tgb = (tgt_tok ? tgt_tok[((int64_t)b * g.T + t) * g.P + lane] : target_pixel(g, img, b, t, lane)) - bias[blk * g.P + lane];
+        float mine = 0.f;  // lane p keeps dot product p
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) a = fmaf(e[j], __ldg(w + lane + 32 * j), a);
-            a = warp_sum(a) + bias[blk * g.P + p];
-            const float tg = tgt_tok ? tgt_tok[((int64_t)b * g.T + t) * g.P + p] : target_pixel(g, img, b, t, p);
-            l1 += fabsf(a - tg);
-            if (pred && lane == 0) pred[it * g.P + p] = a;
+        for (int p = 0; p < PMAX; ++p) {
+            if (p < g.P) {
+                const float* w = W + ((int64_t)blk * g.P + p) * g.D;
+                float a = 0.f;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) a = fmaf(e[j], __ldg(w + lane + 32 * j), a);
+                a = warp_sum(a);
+                if (lane == p) mine = a;
+            }
         }
+        if (pred && lane < g.P) pred[it * g.P + lane] = mine + bias[blk * g.P + lane];
+        const float l1 = warp_sum(lane < g.P ? fabsf(mine - tgb) : 0.f);
         if (lane == 0) partial[it] = l1;
     }
 }
@@ -119,6 +127,9 @@ __global__ void __launch_bounds__(DT) decode_bwd_kernel(DecGeom g, const float* 
         float e[NJ], de[NJ];
 #pragma unroll
         for (int j = 0; j < NJ; ++j) { e[j] = enc[((int64_t)b * g.T + t) * g.D + lane + 32 * j]; de[j] = 0.f; }
+        float tgb = 0.f;   // lane p: target_p - bias_p (fetched before the reduction loop)
+        if (lane < g.P)
+            tgb = (tgt_tok ? tgt_tok[((int64_t)b * g.T + t) * g.P + lane] : target_pixel(g, img, b, t, lane)) - bias[blk * g.P + lane];
 #pragma unroll
         for (int p = 0; p < PMAX; ++p) {
             if (p < g.P) {
@@ -126,9 +137,7 @@ __global__ void __launch_bounds__(DT) decode_bwd_kernel(DecGeom g, const float* 
                 float wv[NJ], a = 0.f;
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) { wv[j] = __ldg(w + lane + 32 * j); a = fmaf(e[j], wv[j], a); }
-                a = warp_sum(a) + bias[blk * g.P + p];
-                const float tg = tgt_tok ? tgt_tok[((int64_t)b * g.T + t) * g.P + p] : target_pixel(g, img, b, t, p);
-                const float diff = a - tg;
+                const float diff = warp_sum(a) - __shfl_sync(0xffffffffu, tgb, p);
                 const float gp = diff > 0.f ? gscale : (diff < 0.f ? -gscale : 0.f);
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) { aW[p][j] = fmaf(gp, e[j], aW[p][j]); de[j] = fmaf(gp, wv[j], de[j]); }
@@ -169,8 +178,9 @@ extern "C" int msst_simmim_decode_l1_fwd(const msst_decode_dims* d, const float*
     const int64_t total = (int64_t)g.B * g.nm;
     int64_t grid = ceil_div(total, DT / 32);
     if (grid > 8 * kNumSMs) grid = 8 * kNumSMs;
-#define MSST_D(NJ) case NJ: decode_fwd_kernel<NJ><<<(int)grid, DT, 0, st>>>(g, enc, idx, img, target_tokens, W, bias, pred, partial); break;
-    switch (g.D / 32) { MSST_D(1) MSST_D(2) MSST_D(3) MSST_D(4) MSST_D(6) MSST_D(8) default: set_error("simmim_decode: D unsupported"); return MSST_ERR_ARG; }
+    MSST_REQUIRE(g.P <= 16, "simmim_decode: pixels per patch %d > 16 unsupported", g.P);
+#define MSST_D(NJ) case NJ: decode_fwd_kernel<NJ, 16><<<(int)grid, DT, 0, st>>>(g, enc, idx, img, target_tokens, W, bias, pred, partial); break;
+    switch (g.D / 32) { MSST_D(1) MSST_D(2) MSST_D(3) MSST_D(4) default: set_error("simmim_decode: D unsupported"); return MSST_ERR_ARG; }
 #undef MSST_D
     MSST_LAUNCH_CHECK();
     // loss = mean over B*nm*P elements, then / num_masked (reference double normalisation, :338)
