@@ -27,7 +27,7 @@ constexpr int GB_EPI_WARPS = 16;      // 4 per TMEM lane quarter: the epilogue m
 constexpr int GB_THREADS = 128 + 32 * GB_EPI_WARPS;   // TMA, MMA, TMEM-alloc, spare + epilogue warps
 // accumulator columns per epilogue step: 16 for the math-heavy epilogues (GELU / Philox / residual: more warps busy on the
 // N = 64 / 96 tiles), 32 for the store-only ones (whole 64/128-byte row segments per store instruction)
-__host__ __device__ constexpr int gb_chunk(int mode) { return (mode == 2 || mode == 3 || mode == 4) ? 16 : 32; }
+__host__ __device__ constexpr int gb_chunk(int mode) { return (mode == 2 || mode == 3 || mode == 4 || mode == 6) ? 16 : 32; }
 __host__ __device__ constexpr int gb_epi_smem(int mode) { return GB_EPI_WARPS * 32 * (gb_chunk(mode) + 4) * 4; }
 constexpr uint32_t GB_A_BYTES = GB_M * GB_K * 2;   // 16 KB
 
@@ -37,6 +37,7 @@ struct GemmTnParams {
     uint32_t idesc, tmem_cols;
     const float* bias; const float* residual; void* out; int out_fp32;
     __nv_bfloat16* pre_act; const __nv_bfloat16* aux; int act; Drop drop;
+    const float* ln_w; const float* ln_b; __nv_bfloat16* ln_out; float* ln_stats;   // MODE 6: fused LayerNorm of the output rows
     int debug;   // MSST_GEMM_DEBUG bits (profiling experiments only): 1 skip global stores, 2 skip epilogue body, 4 skip MMA issue
 };
 
@@ -59,12 +60,14 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 //   2: fp32 out = acc + bias [dropout] + residual      (out-projection, MLP second linear)
 //   3: bf16 out = [dropout] gelu(acc + bias), pre_act = acc + bias   (MLP first linear)
 //   4: bf16 out = acc * gelu'(aux) [dropout]            (data-gradient through the MLP hidden layer)
+//   6: MODE 2 + LayerNorm of the finished rows (bf16) + its statistics: the pre-norm of the NEXT sub-block is produced by
+//      the GEMM that finishes the residual stream row (needs the whole row in one tile: N == block_n <= 128)
 // residual (MODE 2) / GELU' argument (MODE 4) of this lane's 8 row segments, fetched BEFORE the accumulator is waited for:
 // the loads must not sit between the stores of the main loop (possible aliasing would serialise them on DRAM latency).
 template <int MODE>
 __device__ __forceinline__ void epilogue_prefetch(const GemmTnParams& p, int64_t row_base, int col0, int sub_r, int c4,
                                                   float4 (&pre)[gb_chunk(MODE) / 4]) {
-    if (MODE != 2 && MODE != 4) return;
+    if (MODE != 2 && MODE != 4 && MODE != 6) return;
     constexpr int ITER = gb_chunk(MODE) / 4, RPI = 128 / gb_chunk(MODE);   // row iterations, rows per iteration
     const int col = col0 + c4;
     const int64_t rows_left = p.M - row_base;
@@ -74,7 +77,7 @@ __device__ __forceinline__ void epilogue_prefetch(const GemmTnParams& p, int64_t
         pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (rr < rows_left && col < p.N) {
             const int64_t off = (row_base + rr) * p.N + col;
-            if (MODE == 2) pre[i] = *reinterpret_cast<const float4*>(p.residual + off);
+            if (MODE == 2 || MODE == 6) pre[i] = *reinterpret_cast<const float4*>(p.residual + off);
             else { const uint2 u = *reinterpret_cast<const uint2*>(p.aux + off); pre[i].x = __uint_as_float(u.x); pre[i].y = __uint_as_float(u.y); }
         }
     }
@@ -82,7 +85,7 @@ __device__ __forceinline__ void epilogue_prefetch(const GemmTnParams& p, int64_t
 
 template <int MODE>
 __device__ __forceinline__ void epilogue_rows(const GemmTnParams& p, const float* stg, int64_t row_base, int col0, int sub_r, int c4,
-                                              const float4 (&pre)[gb_chunk(MODE) / 4]) {
+                                              const float4 (&pre)[gb_chunk(MODE) / 4], float* rowbuf, int rowbuf_pitch) {
     constexpr int ITER = gb_chunk(MODE) / 4, RPI = 128 / gb_chunk(MODE), PITCH = gb_chunk(MODE) + 4;
     if (MODE == 0 && (p.N & 7) == 0) {
         // store-only bf16 epilogue: lane -> 8 consecutive columns (one 16-byte store), 4 lanes per row, 8 rows per instruction
@@ -106,7 +109,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmTnParams& p, const float
     if (MODE != 5) {
         if (col >= p.N) return;            // N % 4 == 0 in the specialised modes: a float4 is all-in or all-out
         float b4[4] = {0.f, 0.f, 0.f, 0.f};
-        if (MODE == 2 || MODE == 3) {
+        if (MODE == 2 || MODE == 3 || MODE == 6) {
             const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + col));
             b4[0] = t.x; b4[1] = t.y; b4[2] = t.z; b4[3] = t.w;
         }
@@ -136,9 +139,10 @@ __device__ __forceinline__ void epilogue_rows(const GemmTnParams& p, const float
 #pragma unroll
                 for (int t = 0; t < 4; ++t) f[t] *= d4[t];
             }
-            if (MODE == 2) { f[0] += pre[i].x; f[1] += pre[i].y; f[2] += pre[i].z; f[3] += pre[i].w; }
+            if (MODE == 2 || MODE == 6) { f[0] += pre[i].x; f[1] += pre[i].y; f[2] += pre[i].z; f[3] += pre[i].w; }
+            if (MODE == 6) *reinterpret_cast<float4*>(rowbuf + rr * rowbuf_pitch + col) = make_float4(f[0], f[1], f[2], f[3]);
             if (p.debug & 1) continue;
-            if (MODE == 1 || MODE == 2) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = make_float4(f[0], f[1], f[2], f[3]);
+            if (MODE == 1 || MODE == 2 || MODE == 6) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = make_float4(f[0], f[1], f[2], f[3]);
             else *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
         }
         return;
@@ -268,6 +272,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int q = (warp - 4) & 3, sub = (warp - 4) >> 2;
         float* stg = reinterpret_cast<float*>(smem + (size_t)GB_STAGES * stage_bytes + 256) + (size_t)(warp - 4) * (32 * PITCH);
         const int sub_r = lane / LPR, c4 = (lane % LPR) * 4;
+        // MODE 6: finished fp32 rows of this TMEM lane quarter, [32 rows][block_n + 4]
+        const int rb_pitch = p.block_n + 4;
+        float* rowbuf = reinterpret_cast<float*>(smem + (size_t)GB_STAGES * stage_bytes + 256 + gb_epi_smem(MODE)) + (size_t)q * 32 * rb_pitch;
+        float4 lnw4 = make_float4(0.f, 0.f, 0.f, 0.f), lnb4 = lnw4;
+        if (MODE == 6 && lane * 4 < p.N) { lnw4 = *reinterpret_cast<const float4*>(p.ln_w + lane * 4); lnb4 = *reinterpret_cast<const float4*>(p.ln_b + lane * 4); }
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
@@ -291,12 +300,35 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     *reinterpret_cast<float4*>(stg + lane * PITCH + g8 * 4) =
                         make_float4(__uint_as_float(v[g8 * 4]), __uint_as_float(v[g8 * 4 + 1]), __uint_as_float(v[g8 * 4 + 2]), __uint_as_float(v[g8 * 4 + 3]));
                 __syncwarp();
-                epilogue_rows<MODE>(p, stg, row_base, col0, sub_r, c4, pre);
+                epilogue_rows<MODE>(p, stg, row_base, col0, sub_r, c4, pre, rowbuf, rb_pitch);
             }
             if (first_chunk) { mbar_wait(&bars->tmem_full[acc], acc_phase); tc_fence_after(); }   // warp had no chunk in this tile
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+            if (MODE == 6) {
+                // the 4 warps of this quarter have written its 32 finished rows: warp `sub` normalises rows 8*sub .. 8*sub+7
+                // (lane -> 4 columns, two-pass variance like nn.LayerNorm), bf16 output + (mean, rstd) for the backward
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+                const int c = lane * 4;
+                const bool act = c < p.N;
+#pragma unroll 4
+                for (int k = 0; k < 8; ++k) {
+                    const int rr = sub * 8 + k;
+                    const int64_t row = row_base + rr;
+                    if (row >= p.M) break;
+                    const float4 v = act ? *reinterpret_cast<const float4*>(rowbuf + rr * rb_pitch + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float mean = warp_sum(v.x + v.y + v.z + v.w) / p.N;
+                    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+                    const float rstd = rsqrtf(warp_sum(act ? d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3 : 0.f) / p.N + 1e-5f);
+                    if (lane == 0) { p.ln_stats[2 * row] = mean; p.ln_stats[2 * row + 1] = rstd; }
+                    if (act)
+                        *reinterpret_cast<uint2*>(p.ln_out + row * p.N + c) =
+                            make_uint2(pack_bf16(d0 * rstd * lnw4.x + lnb4.x, d1 * rstd * lnw4.y + lnb4.y),
+                                       pack_bf16(d2 * rstd * lnw4.z + lnb4.z, d3 * rstd * lnw4.w + lnb4.w));
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");   // rowbuf is free for the next tile
+            }
         }
     }
     tc_fence_before();
@@ -452,6 +484,7 @@ int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st) {
     p.tmem_cols = pow2_cols(2 * p.block_n);
     p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.out_fp32 = a.out_fp32; p.pre_act = a.pre_act; p.aux = a.aux;
     p.act = a.act; p.drop = a.drop;
+    p.ln_w = a.ln_w; p.ln_b = a.ln_b; p.ln_out = a.ln_out; p.ln_stats = a.ln_stats;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MSST_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
     CUtensorMap ta, tb;
     if (int rc = make_tmap(&ta, a.A, a.M, a.K, a.K, GB_M)) return rc;
@@ -461,9 +494,15 @@ int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st) {
     const bool vec = (a.N % 4 == 0);
     if (vec && !a.pre_act && !a.bias && !a.residual && a.act == 0 && !a.drop.on()) mode = a.out_fp32 ? 1 : 0;
     else if (vec && a.out_fp32 && a.bias && a.residual && a.act == 0 && !a.pre_act) mode = 2;
+    if (a.ln_out) {
+        MSST_REQUIRE(mode == 2 && p.tiles_n == 1 && a.N <= 128 && a.ln_w && a.ln_b && a.ln_stats,
+                     "bf16 GEMM: the fused LayerNorm epilogue needs fp32 out + bias + residual and N <= 128 (N=%d)", a.N);
+        mode = 6;
+    }
     else if (vec && !a.out_fp32 && a.bias && a.act == 1 && a.pre_act && !a.residual) mode = 3;
     else if (vec && !a.out_fp32 && !a.bias && a.act == 2 && a.aux && !a.residual && !a.pre_act) mode = 4;
-    const size_t smem = (size_t)GB_STAGES * (GB_A_BYTES + (size_t)p.block_n * GB_K * 2) + 256 + gb_epi_smem(mode) + 1024;
+    const size_t smem = (size_t)GB_STAGES * (GB_A_BYTES + (size_t)p.block_n * GB_K * 2) + 256 + gb_epi_smem(mode) + 1024 +
+                        (mode == 6 ? (size_t)4 * 32 * (p.block_n + 4) * 4 : 0);
     const int64_t tiles = p.tiles_m * p.tiles_n;
     const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
     static PerDeviceOnce attr_set;
@@ -474,6 +513,7 @@ int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st) {
         MSST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         MSST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         MSST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MSST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     }
     switch (mode) {
         case 0: gemm_tn_kernel<0><<<grid, GB_THREADS, smem, st>>>(ta, tb, p); break;
@@ -481,6 +521,7 @@ int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st) {
         case 2: gemm_tn_kernel<2><<<grid, GB_THREADS, smem, st>>>(ta, tb, p); break;
         case 3: gemm_tn_kernel<3><<<grid, GB_THREADS, smem, st>>>(ta, tb, p); break;
         case 4: gemm_tn_kernel<4><<<grid, GB_THREADS, smem, st>>>(ta, tb, p); break;
+        case 6: gemm_tn_kernel<6><<<grid, GB_THREADS, smem, st>>>(ta, tb, p); break;
         default: gemm_tn_kernel<5><<<grid, GB_THREADS, smem, st>>>(ta, tb, p); break;
     }
     MSST_LAUNCH_CHECK();

@@ -30,6 +30,8 @@ struct GemmBf16Args {
     __nv_bfloat16* pre_act; const __nv_bfloat16* aux;  // optional bf16 [M,N] out (pre-activation) / in (GELU' argument)
     int act;                                           // 0 none, 1 GELU(erf), 2 multiply by GELU'(aux)
     Drop drop;
+    // optional fused LayerNorm of the finished output rows (fp32 out + bias + residual GEMMs with N <= 128):
+    const float* ln_w; const float* ln_b; __nv_bfloat16* ln_out; float* ln_stats;
 };
 int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st);
 int gemm_wgrad_bf16(const __nv_bfloat16* dy, const __nv_bfloat16* x, float* dW, int64_t M, int N, int K, cudaStream_t st);

@@ -114,19 +114,28 @@ static int tf_fwd_bf16(const msst_tf_dims* d, const msst_layer_params* layers, c
         const uint32_t site = d->site_base + 8u * l;
         bf16* h1 = d->save_for_backward ? (bf16*)(lw + L.o_h1) : h;
         bf16* h2 = d->save_for_backward ? (bf16*)(lw + L.o_h2) : h;
-        if (int rc = layernorm_fwd(x, p.ln1_w, p.ln1_b, h1, 1, stats1, R, D, 1e-5f, st)) return rc;
+        // pre-norms are produced by the epilogue of the GEMM that finishes the residual-stream row (fused LayerNorm);
+        // only the first layer's LN1 is a stand-alone kernel
+        const bool fuse_ln = (D % 4 == 0 && D <= 128);
+        if (l == 0 || !fuse_ln) { if (int rc = layernorm_fwd(x, p.ln1_w, p.ln1_b, h1, 1, stats1, R, D, 1e-5f, st)) return rc; }
         if (int rc = gemm_tn_bf16(gemm_args(h1, w.wq, R, 3 * I, D, qkv, 0), st)) return rc;
         msst_attn_dims ad{d->n_seq, d->N, d->inner, d->H, d->dh, d->drop_p, d->seed, site + kSiteAttnProb, d->prec, d->seed_dev};
         if (int rc = attention_fwd_bf16(&ad, qkv, o, lse, st)) return rc;
         GemmBf16Args a = gemm_args(o, w.wo, R, D, I, xmid, 1);
         a.bias = p.b_out; a.residual = x; a.drop = make_drop(d->drop_p, d->seed, site + kSiteAttnOut, d->seed_dev);
+        if (fuse_ln) { a.ln_w = p.ln2_w; a.ln_b = p.ln2_b; a.ln_out = h2; a.ln_stats = stats2; }
         if (int rc = gemm_tn_bf16(a, st)) return rc;
-        if (int rc = layernorm_fwd(xmid, p.ln2_w, p.ln2_b, h2, 1, stats2, R, D, 1e-5f, st)) return rc;
+        if (!fuse_ln) { if (int rc = layernorm_fwd(xmid, p.ln2_w, p.ln2_b, h2, 1, stats2, R, D, 1e-5f, st)) return rc; }
         a = gemm_args(h2, w.w1, R, M, D, g, 0);
         a.bias = p.b1; a.pre_act = u; a.act = 1; a.drop = make_drop(d->drop_p, d->seed, site + kSiteMlpHidden, d->seed_dev);
         if (int rc = gemm_tn_bf16(a, st)) return rc;
         a = gemm_args(g, w.w2, R, D, M, y, 1);
         a.bias = p.b2; a.residual = xmid; a.drop = make_drop(d->drop_p, d->seed, site + kSiteMlpOut, d->seed_dev);
+        if (fuse_ln && l + 1 < d->L) {   // LN1 of the next layer
+            char* nlw = ws + L.layer_bytes * (d->save_for_backward ? l + 1 : 0);
+            a.ln_w = layers[l + 1].ln1_w; a.ln_b = layers[l + 1].ln1_b;
+            a.ln_out = d->save_for_backward ? (bf16*)(nlw + L.o_h1) : h; a.ln_stats = (float*)(nlw + L.o_stats1);
+        }
         if (int rc = gemm_tn_bf16(a, st)) return rc;
         x = y;
     }
