@@ -306,52 +306,76 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def _time_launch(fn, reps=10):
+    import torch
+    for _ in range(3):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / 1e3 / reps
+
+
 def roofline(args, B, dev, model, peaks):
-    """Dominant kernel timed alone with CUDA events on the launching stream: the QKV projection GEMM of one
-    transformer stack at the step's shape (largest single FLOP consumer: 294,912 of 417,792 linear FLOP/token/layer)."""
+    """Roofline of the DOMINANT kernel of the step (largest share of the ncu launch list, profiles/): the attention backward
+    kernel, timed alone with CUDA events on the launching stream at the step's spatial-stack shape (B*C sequences of 64 tokens,
+    8 heads, dh 64).  HBM-bound: algorithmic bytes per launch = R*(3*I + I)*e [q,k,v,dO in] + R*3*I*e [dq,dk,dv out] + R*H*4 [lse].
+    `other_kernels` adds the largest GEMM (QKV projection, tcgen05) measured the same way."""
     import ctypes as C
     import torch
     from maskedsst_b200 import _lib
-    T = 320 if args.dataset == "houston" else 1280
-    R, D, N = B * T, 96, 1536
-    prec = _lib.PREC_BF16 if args.precision == "bf16" else _lib.PREC_FP32
-    dt = torch.bfloat16 if args.precision == "bf16" else torch.float32
-    x = torch.randn(R, D, device=dev).to(dt)
-    W = (torch.randn(N, D, device=dev) / 10).to(dt)
-    y = torch.empty(R, N, device=dev, dtype=dt)
-    dims = _lib.LinearDims(R, N, D, 0, 0.0, 0, 0, prec, None, 0)
-    st = torch.cuda.current_stream().cuda_stream
     lib = _lib.lib()
-    try:
-        for _ in range(3):
-            _lib.check(lib.msst_linear_fwd(C.byref(dims), x.data_ptr(), W.data_ptr(), None, None, y.data_ptr(), None, st))
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 10
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(reps):
-            _lib.check(lib.msst_linear_fwd(C.byref(dims), x.data_ptr(), W.data_ptr(), None, None, y.data_ptr(), None, st))
-        e1.record()
-        torch.cuda.synchronize()
-        sec = e0.elapsed_time(e1) / 1e3 / reps
-    except Exception as e:   # noqa
-        return {"error": str(e)}
-    flops = 2.0 * R * N * D
-    bytes_ = R * D * x.element_size() + R * N * y.element_size() + N * D * W.element_size()
-    # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed `ncu --set full` capture
-    # (profiles/r01_ncu_full_final_kernels.txt, gemm_tn_kernel<0>, B = 1024 Houston shape): 63.2 MB + 951.5 MB
-    traffic = 1014752768 if (args.precision == "bf16" and R == 327680) else None
+    st = torch.cuda.current_stream().cuda_stream
+    bf16 = args.precision == "bf16"
+    prec = _lib.PREC_BF16 if bf16 else _lib.PREC_FP32
+    dt = torch.bfloat16 if bf16 else torch.float32
+    es = 2 if bf16 else 4
+    Cb, T = (5, 320) if args.dataset == "houston" else (20, 1280)
+    R, H, dh, I = B * T, 8, 64, 512
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    tf_peak = peaks.get("bf16_tflops", 1590.0)
     src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback"
-    # K = 96: arithmetic intensity = flops/bytes; the bound is whichever roof is lower at this intensity
-    t_tensor, t_hbm = flops / (tf_peak * 1e12), bytes_ / (hbm_peak * 1e9)
-    if t_hbm >= t_tensor:
-        return {"kernel": "qkv projection GEMM [R,96]x[96,1536]", "bound": "hbm", "achieved": bytes_ / sec / 1e9, "peak": hbm_peak,
-                "unit": "GB/s", "frac": bytes_ / sec / 1e9 / hbm_peak, "traffic": traffic, "algorithmic_bytes": bytes_, "peak_source": src,
-                "tflops": flops / sec / 1e12, "us_per_launch": sec * 1e6}
-    return {"kernel": "qkv projection GEMM [R,96]x[96,1536]", "bound": "tensor", "achieved": flops / sec / 1e12, "peak": tf_peak,
-            "unit": "TFLOP/s", "frac": flops / sec / 1e12 / tf_peak, "traffic": traffic, "peak_source": src, "us_per_launch": sec * 1e6}
+    out = {}
+    try:
+        qkv = torch.randn(R, 3 * I, device=dev).to(dt)
+        o = torch.empty(R, I, device=dev, dtype=dt)
+        lse = torch.empty(R, H, device=dev)
+        do = torch.randn(R, I, device=dev).to(dt)
+        dqkv = torch.empty_like(qkv)
+        ad = _lib.AttnDims(B * Cb, 64, 1, H, dh, float(args.dropout), 1234, 16, prec, None)
+        _lib.check(lib.msst_attention_fwd(C.byref(ad), qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), st))
+        sec = _time_launch(lambda: _lib.check(lib.msst_attention_bwd(C.byref(ad), qkv.data_ptr(), o.data_ptr(), lse.data_ptr(),
+                                                                     do.data_ptr(), dqkv.data_ptr(), st)))
+        bytes_ = R * 4 * I * es + R * 3 * I * es + R * H * 4
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this kernel
+        # at this shape (profiles/r01_ncu_full_final_kernels.txt): 1.355 GB + 0.966 GB
+        traffic = 2321000000 if (bf16 and R == 327680) else None
+        out = {"kernel": "attention backward (attn_bwd_bf16_heads_kernel), spatial stack shape" if bf16 else "attention backward (fp32 kernel)",
+               "bound": "hbm", "achieved": bytes_ / sec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": bytes_ / sec / 1e9 / hbm_peak,
+               "traffic": traffic, "algorithmic_bytes": bytes_, "us_per_launch": sec * 1e6, "peak_source": src,
+               "tflops": 2.0 * 5 * 64 * 64 * 64 * (R // 64) * H / sec / 1e12}
+        del qkv, o, lse, do, dqkv
+    except Exception as e:   # noqa
+        out = {"error": str(e)}
+    try:
+        D, N = 96, 1536
+        x = torch.randn(R, D, device=dev).to(dt)
+        W = (torch.randn(N, D, device=dev) / 10).to(dt)
+        y = torch.empty(R, N, device=dev, dtype=dt)
+        dims = _lib.LinearDims(R, N, D, 0, 0.0, 0, 0, prec, None, 0)
+        sec = _time_launch(lambda: _lib.check(lib.msst_linear_fwd(C.byref(dims), x.data_ptr(), W.data_ptr(), None, None, y.data_ptr(), None, st)))
+        gb = R * D * es + R * N * es + N * D * es
+        out["other_kernels"] = [{
+            "kernel": "qkv projection GEMM [R,96]x[96,1536] (gemm_tn_kernel<0>, tcgen05/TMA)" if bf16 else "qkv projection GEMM (fp32 FFMA)",
+            "bound": "hbm", "achieved": gb / sec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": gb / sec / 1e9 / hbm_peak,
+            "traffic": 1014752768 if (bf16 and R == 327680) else None, "algorithmic_bytes": gb, "us_per_launch": sec * 1e6,
+            "tflops": 2.0 * R * N * D / sec / 1e12}]
+    except Exception as e:   # noqa
+        out["other_kernels"] = [{"error": str(e)}]
+    return out
 
 
 if __name__ == "__main__":
