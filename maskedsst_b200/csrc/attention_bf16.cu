@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "attn_geom.cuh"
+#include <stdlib.h>
 
 namespace msst {
 
@@ -622,6 +623,11 @@ int attention_fwd_bf16(const msst_attn_dims* d, const bf16* qkv, bf16* out, floa
     if (int rc = make_attn_geom(d, g, false)) return rc;
     if (g.n_seq == 0) return MSST_OK;
     const Drop drop = make_drop(d->drop_p, d->seed, d->site, d->seed_dev);
+    if (g.tiles == 1) {
+        static int use_tc = -1;
+        if (use_tc < 0) { const char* e = getenv("MSST_ATTN_TC"); use_tc = e ? atoi(e) : 0; }
+        if (use_tc) return attention_fwd_tc(g, qkv, out, lse, drop, st);   // tcgen05 / TMEM forward (attention_tc.cu)
+    }
     if (g.tiles == 1) {   // N <= 64: head-looping, cp.async double-buffered kernel
         static PerDeviceOnce attr_set;
         if (attr_set.first()) {

@@ -48,6 +48,10 @@ int attention_fwd_bf16(const msst_attn_dims* d, const __nv_bfloat16* qkv, __nv_b
 int attention_bwd_bf16(const msst_attn_dims* d, const __nv_bfloat16* qkv, const __nv_bfloat16* out, const float* lse,
                        const __nv_bfloat16* d_out, __nv_bfloat16* d_qkv, cudaStream_t st);
 
+// attention_tc.cu (tcgen05 forward, N <= 64)
+struct AttnGeom;
+int attention_fwd_tc(const AttnGeom& g, const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, Drop drop, cudaStream_t st);
+
 // attention_f32.cu
 int attention_fwd_f32(const msst_attn_dims* d, const float* qkv, float* out, float* lse, cudaStream_t st);
 int attention_bwd_f32(const msst_attn_dims* d, const float* qkv, const float* out, const float* lse, const float* d_out,
