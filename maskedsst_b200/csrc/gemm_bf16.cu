@@ -466,6 +466,10 @@ static int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t col
     return MSST_OK;
 }
 
+int make_tmap_bf16(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    return make_tmap(m, base, rows, cols, ld, box_rows);
+}
+
 static uint32_t pow2_cols(int c) { uint32_t v = 32; while ((int)v < c) v <<= 1; return v; }
 
 int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st) {
