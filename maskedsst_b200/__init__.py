@@ -6,11 +6,11 @@ Public surface mirrors the reference modules:
 All arithmetic runs in libmsst.so (include/msst.h); importing this package without a CUDA device works
 (module construction, state_dict handling), calling a kernel without one raises.
 """
-from .vit_spatial_spectral import (ViTSpatialSpectral, Transformer, Attention, FeedForward, PreNorm,
+from .vit_spatial_spectral import (ViTSpatialSpectral, ViTSpatialSpectral_V1, Transformer, Attention, FeedForward, PreNorm,
                                    BlockwisePatchEmbedding, PatchEmbed, MoveAxis, get_pos_for_spectral_embedding)
 from .vit_simmim_original import SimMIMSpatialSpectral, BlockwiseToPixels, MaskGenerator
 from .ops import cross_entropy
 
-__all__ = ["ViTSpatialSpectral", "SimMIMSpatialSpectral", "BlockwiseToPixels", "MaskGenerator", "Transformer", "Attention",
+__all__ = ["ViTSpatialSpectral", "ViTSpatialSpectral_V1", "SimMIMSpatialSpectral", "BlockwiseToPixels", "MaskGenerator", "Transformer", "Attention",
            "FeedForward", "PreNorm", "BlockwisePatchEmbedding", "PatchEmbed", "MoveAxis", "get_pos_for_spectral_embedding",
            "cross_entropy"]

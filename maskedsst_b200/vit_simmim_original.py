@@ -7,7 +7,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .vit_spatial_spectral import ViTSpatialSpectral, KLinear
+from .vit_spatial_spectral import ViTSpatialSpectral, ViTSpatialSpectral_V1
 
 
 class BlockwiseToPixels(nn.Module):
@@ -85,10 +85,18 @@ class SimMIMSpatialSpectral(nn.Module):
                  to_pixels_per_spectral_block=False, precision="32-true"):
         super().__init__()
         assert masking_ratio > 0 and masking_ratio < 1, "masking ratio must be kept between 0 and 1"
-        if not isinstance(encoder, ViTSpatialSpectral):
-            raise NotImplementedError("maskedsst_b200: SimMIMSpatialSpectral supports ViTSpatialSpectral encoders")
-        if intermediate_losses:
-            raise NotImplementedError("intermediate_losses needs the legacy ViTSpatialSpectral_V1 encoder (not built)")
+        self.v1 = isinstance(encoder, ViTSpatialSpectral_V1)
+        if not (self.v1 or isinstance(encoder, ViTSpatialSpectral)):
+            raise NotImplementedError("maskedsst_b200: SimMIMSpatialSpectral supports ViTSpatialSpectral(_V1) encoders")
+        if intermediate_losses and not self.v1:
+            # the reference reads `encoded_spatial` / `encoded_spectral`, which only the V1 branch assigns (:297-313)
+            raise NotImplementedError("intermediate_losses needs a ViTSpatialSpectral_V1 encoder (the reference raises "
+                                      "UnboundLocalError in forward for any other encoder)")
+        if to_pixels_per_spectral_block and self.v1:
+            # :319-327 builds the block-id table with V1's num_spatial_patches (= grid side, not its square), so the
+            # reference's gather runs out of bounds for every index >= C * side
+            raise NotImplementedError("to_pixels_per_spectral_block is not usable with ViTSpatialSpectral_V1 (the reference "
+                                      "raises IndexError in forward)")
         self.masking_ratio = masking_ratio
         self.mask_patch_size = mask_patch_size
         self.intermediate_losses = intermediate_losses
@@ -102,11 +110,16 @@ class SimMIMSpatialSpectral(nn.Module):
         # no host work and no synchronisation per step.
         self.mask_backend = "host"
         self.encoder = encoder
-        encoder_dim = encoder.dim
-        # reference :181-182 -- with PatchEmbed these are sub-modules and add alias keys to the state_dict
-        self.to_patch = encoder.to_patch_embedding.to_patch
-        self.patch_to_emb = encoder.to_patch_embedding.embed
-        self.pixel_values_per_patch = encoder.pixels_per_patch
+        if self.v1:   # reference :172-178 -- the slice is a new Sequential sharing the LN/Linear/LN modules (alias keys)
+            encoder_dim = encoder.pos_embedding.shape[-1]
+            self.to_patch, self.patch_to_emb = encoder.to_patch_embedding[0], encoder.to_patch_embedding[1:]
+            self.pixel_values_per_patch = self.patch_to_emb[1].weight.shape[-1]
+        else:
+            encoder_dim = encoder.dim
+            # reference :181-182 -- with PatchEmbed these are sub-modules and add alias keys to the state_dict
+            self.to_patch = encoder.to_patch_embedding.to_patch
+            self.patch_to_emb = encoder.to_patch_embedding.embed
+            self.pixel_values_per_patch = encoder.pixels_per_patch
         self.mask_token = nn.Parameter(torch.randn(encoder_dim))
         if self.to_pixels_per_spectral_block:
             self.to_pixels = BlockwiseToPixels(encoder_dim, encoder.num_spectral_patches, self.pixel_values_per_patch,
@@ -157,6 +170,8 @@ class SimMIMSpatialSpectral(nn.Module):
         enc = self.encoder
         B = img.shape[0]
         mask, idx = masks if masks is not None else self.draw_masks(B, img.device)
+        if self.v1:
+            return self._forward_v1(img, mask, idx)
         blockwise = enc.blockwise_patch_embed
         # tokens = where(mask, mask_token + pos, embed(patches) + pos); no emb-dropout on this path (C5)
         out = enc.to_patch_embedding._embed_img(img, pos=enc._pos_rows(), mask_token=self.mask_token, mask=mask,
@@ -171,3 +186,16 @@ class SimMIMSpatialSpectral(nn.Module):
                 idx.shape[1])
         # target: raw pixels (blockwise embedding) or the LayerNormed patches (PatchEmbed), C6
         return ops.simmim_decode_l1(encoded, idx, img if blockwise else None, None if blockwise else pln, W, b, geom=geom)
+
+    def _forward_v1(self, img, mask, idx):
+        """ViTSpatialSpectral_V1 branch (:172-178, :232-234, :297-338): positional rows [1, T], raw-pixel target, shared
+        decoder; with intermediate_losses the (identical) term is accumulated three times."""
+        enc = self.encoder
+        B, T = img.shape[0], enc.num_patches
+        tokens = enc._embed_img(img, enc.pos_embedding[0, 1: T + 1], mask_token=self.mask_token, mask=mask)
+        encoded, _, _ = enc.transformer_forward(tokens)
+        geom = (B, enc.num_spectral_patches, enc.num_spatial_patches, enc.patch_depth, enc.patch_height, enc.dim, idx.shape[1])
+        loss = ops.simmim_decode_l1(encoded, idx, img, None, self.to_pixels.weight[None], self.to_pixels.bias[None], geom=geom)
+        if self.intermediate_losses:
+            loss = (loss + loss) + loss
+        return loss

@@ -7,6 +7,7 @@ Reference map (file:line in the upstream repo):
       the arithmetic of a whole Transformer stack is one msst_transformer_fwd/bwd call
   BlockwisePatchEmbedding :178-229, PatchEmbed :232-253                       -> msst_patch_embed_fwd/bwd
   ViTSpatialSpectral :256-564                                                  -> ViTSpatialSpectral below
+  ViTSpatialSpectral_V1 :600-764 (legacy; the only encoder `intermediate_losses` works with) -> ViTSpatialSpectral_V1
 The spatial->spectral re-tiling copies of the reference (:409-431) do not exist here: the residual stream stays in
 (b, c, s) row order and the spectral stack addresses its sequences with a stride (msst.h, attention section).
 """
@@ -438,6 +439,107 @@ class ViTSpatialSpectral(nn.Module):
         ln, lin = self.mlp_head[0], self.mlp_head[1]
         return ops.head(x, ln.weight, ln.bias, lin.weight, lin.bias,
                         geom=(B, c, g, self.patch_height, self.dim, self.num_classes))
+
+
+# ---------------------------------------------------------------------------------------------------
+# legacy encoder (reference :600-764) -- kept so V1 checkpoints / `intermediate_losses` runs have a drop-in
+# ---------------------------------------------------------------------------------------------------
+class AvgPoolMerge(nn.Module):
+    """(x1 + x2) / 2 (:567-576).  Constructed by V1 but never called by its forward (:735-744)."""
+
+    def forward(self, x1, x2):
+        return torch.stack((x1, x2), dim=1).mean(axis=1)
+
+
+class LinearMerge(nn.Module):
+    """Linear(2 dim -> dim) over cat(x1, x2) (:579-588); parameter container for checkpoint compatibility."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.fc = KLinear(2 * dim, dim)
+
+    def forward(self, x1, x2):
+        return self.fc(torch.concat((x1, x2), dim=2))
+
+
+class ViTSpatialSpectral_V1(nn.Module):
+    """ViTSpatialSpectral_V1 (:600-764): one shared Linear patch embedding held in an nn.Sequential
+    (keys to_patch_embedding.{1,2,3}.*), learned positional table, the same spatial -> spectral stacks, default head.
+    NB `num_spatial_patches` is the grid SIDE here (:629), not its square as in ViTSpatialSpectral."""
+
+    def __init__(self, *, image_size, spatial_patch_size, spectral_patch_size, num_classes, dim, depth, heads, mlp_dim,
+                 pool="mean", channels=3, dim_head=64, dropout=0.0, emb_dropout=0.0, merge="avgpool", precision="fp32"):
+        super().__init__()
+        image_height, image_width = pair(image_size)
+        self.patch_height, self.patch_width = pair(spatial_patch_size)
+        self.patch_depth = spectral_patch_size
+        self.image_size = image_size
+        assert (image_height % self.patch_height == 0 and image_width % self.patch_width == 0
+                and channels % self.patch_depth == 0), "Image dimensions must be divisible by the patch size."
+        assert image_height == image_width and self.patch_height == self.patch_width, \
+            "maskedsst_b200: square images / patches only"
+        self.num_spatial_patches = image_height // self.patch_height
+        self.num_spectral_patches = channels // self.patch_depth
+        self.num_patches = self.num_spatial_patches ** 2 * self.num_spectral_patches
+        patch_dim = self.patch_depth * self.patch_height * self.patch_width
+        self.pixels_per_patch = patch_dim
+        assert pool in {"mean"}, "pool type must be either cls (cls token) or mean (mean pooling)"
+        self.to_patch_embedding = nn.Sequential(ToPatch(self.patch_depth, self.patch_height, flat=True),
+                                                KLayerNorm(patch_dim), KLinear(patch_dim, dim), KLayerNorm(dim))
+        self.pos_embedding = nn.Parameter(torch.randn(1, self.num_patches + 1, dim))
+        self.dropout = nn.Dropout(emb_dropout)
+        c, s = self.num_spectral_patches, self.num_spatial_patches ** 2
+        self.spatial_spectral_transformer = nn.Sequential(
+            Retile("to_spatial", c, s), Transformer(dim, depth, heads, dim_head, mlp_dim, dropout),
+            Retile("spatial_to_spectral", c, s), Transformer(dim, depth, heads, dim_head, mlp_dim, dropout),
+            Retile("from_spectral", c, s))
+        self.spatial_spectral_transformer[3].site_base = ops.SITE_LAYER_BASE + 8 * depth
+        if merge == "avgpool":
+            self.merge = AvgPoolMerge()
+        elif merge == "linear":
+            self.merge = LinearMerge(dim)
+        self.pool = pool
+        self.to_latent = nn.Identity()
+        self.dim = dim
+        self.num_classes = num_classes
+        self.mlp_head = nn.Sequential(
+            nn.LayerNorm(dim), nn.Linear(dim, num_classes * self.patch_width * self.patch_height),
+            HeadRearrange(self.patch_height, num_classes), MoveAxis((-1, 1)))
+        self.precision = precision
+
+    precision = ViTSpatialSpectral.precision
+
+    def _embed_img(self, img, pos, mask_token=None, mask=None, drop_p=0.0):
+        """to_patch_embedding (+ pos, + mask-token select, + emb-dropout) as one msst_patch_embed launch."""
+        seq = self.to_patch_embedding
+        G, C_ = self.num_spatial_patches, self.num_spectral_patches
+        geom = (C_, G, self.patch_depth, self.patch_height, self.dim)
+        return ops.patch_embed(img, seq[1].weight, seq[1].bias, seq[2].weight[None], seq[2].bias[None], seq[3].weight,
+                               seq[3].bias, pos, mask_token, mask, geom=geom, drop_p=drop_p,
+                               seed=ops.next_seed() if drop_p > 0 else 0, want_ln=False)
+
+    def transformer_forward(self, x):
+        """-> (x, x, x): the reference returns the final representation three times (:735-744)."""
+        B, T, D = x.shape
+        c, s = self.num_spectral_patches, self.num_spatial_patches ** 2
+        assert T == c * s
+        rows = (x if x.is_contiguous() else x.contiguous()).reshape(B * T, D)
+        seq = self.spatial_spectral_transformer
+        rows = seq[3].run(seq[1].run(rows, B * c, s, 1), B * s, c, s)
+        x = rows.reshape(B, T, D)
+        return x, x, x
+
+    def forward_features(self, img):
+        p = self.dropout.p if self.training else 0.0
+        x = self._embed_img(img, self.pos_embedding[0, : self.num_patches], drop_p=p)
+        return self.transformer_forward(x)
+
+    def forward(self, img):
+        x, _, _ = self.forward_features(img)
+        ln, lin = self.mlp_head[0], self.mlp_head[1]
+        return ops.head(x, ln.weight, ln.bias, lin.weight, lin.bias,
+                        geom=(x.shape[0], self.num_spectral_patches, self.num_spatial_patches, self.patch_height, self.dim,
+                              self.num_classes))
 
 
 class _PixelwiseRearrange(nn.Module):

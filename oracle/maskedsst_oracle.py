@@ -47,6 +47,8 @@ class Spec:
     blockwise_patch_embed: bool = True
     spectral_only: bool = False
     spectral_pos: Optional[Sequence[int]] = None
+    v1: bool = False           # legacy ViTSpatialSpectral_V1 (vit_spatial_spectral.py:600-764)
+    v1_merge: str = "avgpool"  # V1 ctor argument `merge`; "linear" only adds the (unused) merge.fc parameters
 
     @property
     def C(self) -> int:  # spectral blocks, :326
@@ -109,13 +111,21 @@ def state_dict_layout(spec: Spec, simmim: bool, blockwise_decoder: bool = True) 
     out: List[Tuple[str, Tuple[int, ...]]] = []
     if simmim:
         out.append(("mask_token", (D,)))
-    if spec.spectral_pos_embed:
+    if spec.v1:
+        # ViTSpatialSpectral_V1 (:640-650, :652): Sequential(Rearrange, LN(P), Linear(P,D), LN(D)), learned table
+        out.append((pre + "pos_embedding", (1, spec.T + 1, D)))
+        pe = pre + "to_patch_embedding."
+        out += [(pe + "1.weight", (P,)), (pe + "1.bias", (P,)), (pe + "2.weight", (D, P)), (pe + "2.bias", (D,)),
+                (pe + "3.weight", (D,)), (pe + "3.bias", (D,))]
+    elif spec.spectral_pos_embed:
         out.append((pre + "pos_embed", (1, spec.S, D - D // 3)))
         out.append((pre + "channel_embed", (1, C, D // 3)))
     else:
         out.append((pre + "pos_embedding", (1, spec.T + 1, D)))
     pe = pre + "to_patch_embedding."
-    if spec.blockwise_patch_embed:
+    if spec.v1:
+        pass
+    elif spec.blockwise_patch_embed:
         out += [(pe + "pre_norm.weight", (P,)), (pe + "pre_norm.bias", (P,)),
                 (pe + "post_norm.weight", (D,)), (pe + "post_norm.bias", (D,))]
         for i in range(C):
@@ -133,6 +143,8 @@ def state_dict_layout(spec: Spec, simmim: bool, blockwise_decoder: bool = True) 
                     (b + "1.norm.weight", (D,)), (b + "1.norm.bias", (D,)),
                     (b + "1.fn.net.0.weight", (M, D)), (b + "1.fn.net.0.bias", (M,)),
                     (b + "1.fn.net.3.weight", (D, M)), (b + "1.fn.net.3.bias", (D,))]
+    if spec.v1 and spec.v1_merge == "linear":   # LinearMerge.fc (:579-588); never called by V1.forward
+        out += [(pre + "merge.fc.weight", (D, 2 * D)), (pre + "merge.fc.bias", (D,))]
     out += [(pre + "mlp_head.0.weight", (D,)), (pre + "mlp_head.0.bias", (D,)),
             (pre + "mlp_head.1.weight", (spec.num_classes * spec.spatial_patch_size ** 2, D)),
             (pre + "mlp_head.1.bias", (spec.num_classes * spec.spatial_patch_size ** 2,))]
@@ -159,7 +171,9 @@ def synthetic_state_dict(spec: Spec, seed: int = 5, simmim: bool = False,
             arr = sincos_2d(shape[-1], spec.S_sqrt)[None] + 0.02 * rng.standard_normal(shape)
         elif key.endswith("channel_embed"):
             arr = sincos_1d(shape[-1], spec.pos())[None] + 0.02 * rng.standard_normal(shape)
-        elif "norm" in key or "mlp_head.0" in key or "to_patch.1" in key or "embed.1" in key:
+        elif ("norm" in key or "mlp_head.0" in key or "to_patch.1" in key or "embed.1" in key
+              or key.endswith(("to_patch_embedding.1.weight", "to_patch_embedding.1.bias",
+                               "to_patch_embedding.3.weight", "to_patch_embedding.3.bias"))):
             arr = (1.0 if leaf == "weight" else 0.0) + 0.1 * rng.standard_normal(shape)
         elif leaf == "weight" and len(shape) == 2:
             bound = 1.0 / math.sqrt(shape[1])
@@ -207,6 +221,10 @@ def embed(patches: torch.Tensor, sd, spec: Spec, pre: str = "") -> torch.Tensor:
     patches [B,C,S,P] raw -> tokens [B,T,D]."""
     pe = pre + "to_patch_embedding."
     B = patches.shape[0]
+    if spec.v1:   # ViTSpatialSpectral_V1.to_patch_embedding[1:] (:646-649)
+        h = _ln(patches.reshape(B, spec.T, spec.P), sd[pe + "1.weight"], sd[pe + "1.bias"])
+        y = h @ sd[pe + "2.weight"].T + sd[pe + "2.bias"]
+        return _ln(y, sd[pe + "3.weight"], sd[pe + "3.bias"])
     if spec.blockwise_patch_embed:
         h = _ln(patches, sd[pe + "pre_norm.weight"], sd[pe + "pre_norm.bias"])
         W = torch.stack([sd[pe + f"blockwise_embed.{i}.weight"] for i in range(spec.C)])  # [C,D,P]
@@ -300,7 +318,8 @@ def encoder_forward(img, sd, spec: Spec, pre: str = ""):
 
 
 def simmim_forward(img, sd, spec: Spec, bool_mask: torch.Tensor, idx: torch.Tensor,
-                   blockwise_decoder: bool = True, return_parts: bool = False, drop: float = 0.0):
+                   blockwise_decoder: bool = True, return_parts: bool = False, drop: float = 0.0,
+                   intermediate_losses: bool = False):
     """SimMIMSpatialSpectral.forward (vit_simmim_original.py:203-340) with the mask pair supplied
     from outside (the pair may be mutually inconsistent).  Dropout off; the SimMIM
     path never applies emb-dropout (C5).  loss = mean|pred-target| / num_masked (C4)."""
@@ -308,12 +327,15 @@ def simmim_forward(img, sd, spec: Spec, bool_mask: torch.Tensor, idx: torch.Tens
     B = img.shape[0]
     patches = to_patch(img, spec)
     tokens = embed(patches, sd, spec, pre)
-    if spec.blockwise_patch_embed:
-        target = patches.reshape(B, spec.T, spec.P)                 # raw pixels (C6)
+    if spec.blockwise_patch_embed or spec.v1:
+        target = patches.reshape(B, spec.T, spec.P)                 # raw pixels (C6); V1: to_patch = Rearrange only (:174-178)
     else:
         pe = pre + "to_patch_embedding."
         target = _ln(patches.reshape(B, spec.T, spec.P), sd[pe + "to_patch.1.weight"], sd[pe + "to_patch.1.bias"])
-    pos = pos_table(sd, spec, pre)
+    if spec.v1:
+        pos = sd[pre + "pos_embedding"][:, 1: spec.T + 1]            # V1 + SimMIM reads rows [1, T] (:233, C11)
+    else:
+        pos = pos_table(sd, spec, pre)
     tokens = tokens + pos
     mask_tokens = sd["mask_token"][None, None, :] + pos
     tokens = torch.where(bool_mask[..., None], mask_tokens, tokens)
@@ -330,6 +352,10 @@ def simmim_forward(img, sd, spec: Spec, bool_mask: torch.Tensor, idx: torch.Tens
         pred = sel @ sd["to_pixels.weight"].T + sd["to_pixels.bias"]
     tgt = target[br, idx]
     loss = (pred - tgt).abs().mean() / nm
+    if intermediate_losses:
+        # :311-338 with a V1 encoder: the "spatial" and "spectral" representations V1.transformer_forward returns are the
+        # final one (:735-744 `return x, x, x`), so the same term is accumulated three times: 0.0 + a + a + a
+        loss = (loss + loss) + loss
     if return_parts:
         return loss, tokens, enc, pred
     return loss

@@ -48,3 +48,33 @@ def load_checkpoint(config, model, classifier_name, device):
     weights[f"{classifier_name}.{linear_idx}.weight"] = head.weight
     print(model.load_state_dict(weights))
     return model
+
+
+def save_pretrain_checkpoint(path, model, config, losses, lr_current, img):
+    """Writes a SimMIM pre-training checkpoint in the reference's pickle layout (pretrain.py:135-148): a dict with
+    `losses` (1-D tensor), `config` (the Dotdict instance itself), `model_state_dict` (the SimMIM wrapper's state_dict,
+    'encoder.'-prefixed keys + mask_token + to_pixels.*), `lr_current`, and the last batch under both `input` and
+    `transformer_input` -- so the reference's load_checkpoint (src/utils.py:276-313) and ours read it unchanged."""
+    stats = {
+        "losses": torch.as_tensor(losses),
+        "config": config,
+        "model_state_dict": model.state_dict(),
+        "lr_current": lr_current,
+        "input": img.detach(),
+        "transformer_input": img,
+    }
+    torch.save(stats, path)
+    return stats
+
+
+def save_finetune_checkpoint(path, model, config, lr_current, epoch):
+    """Fine-tuning checkpoint in the reference layout (src/utils.py:584-601): `config` as a plain dict, the encoder's
+    state_dict (no prefix), `lr_current`, `epoch`."""
+    stats = {
+        "config": dict(config.__dict__) if not isinstance(config, dict) else config,
+        "model_state_dict": model.state_dict(),
+        "lr_current": lr_current,
+        "epoch": epoch,
+    }
+    torch.save(stats, path)
+    return stats

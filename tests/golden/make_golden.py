@@ -14,12 +14,14 @@ import numpy as np
 np.float = float  # src/pos_embed.py:52 uses the alias removed in numpy>=1.24; shim, no edit
 REF = os.environ.get("MSST_REFERENCE", "/root/reference")
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, REF)          # 'src' resolves to the reference here
-sys.path.insert(1, ROOT)
+# the reference's `src` is a namespace package (no __init__.py), so a regular `src` package anywhere on sys.path (this
+# repo's drop-in alias!) would win: keep the repo root and the script directory off the path until the reference is imported
+sys.path[:] = [REF] + [p for p in sys.path if os.path.abspath(p or os.getcwd()) not in (ROOT, os.path.dirname(os.path.abspath(__file__)))]
 import torch
-from src.vit_spatial_spectral import ViTSpatialSpectral           # reference
+from src.vit_spatial_spectral import ViTSpatialSpectral, ViTSpatialSpectral_V1   # reference
 from src.vit_simmim_original import SimMIMSpatialSpectral         # reference
-assert os.path.abspath(sys.modules["src"].__path__[0]).startswith(REF)
+assert os.path.abspath(list(sys.modules["src"].__path__)[0]).startswith(REF)
+sys.path.append(ROOT)
 from oracle import maskedsst_oracle as O
 
 OUT = os.path.dirname(os.path.abspath(__file__))
@@ -146,6 +148,53 @@ def case_simmim(name, spec, B, seed, tube, blockwise_decoder=True, mask_patch=4,
                               mask_patch=mask_patch, ratio=ratio, zero_pad=zero_pad)), **full)
 
 
+def ref_encoder_v1(spec, merge="avgpool"):
+    return ViTSpatialSpectral_V1(
+        image_size=spec.image_size, spatial_patch_size=spec.spatial_patch_size, spectral_patch_size=spec.spectral_patch_size,
+        num_classes=spec.num_classes, dim=spec.dim, depth=spec.depth, heads=spec.heads, mlp_dim=spec.mlp_dim,
+        channels=spec.channels, merge=merge)
+
+
+def case_v1(name, spec, B, seed, zero_pad, intermediate):
+    """Legacy ViTSpatialSpectral_V1: encoder logits, then a SimMIM step (shared decoder; `intermediate_losses`)."""
+    sd = O.synthetic_state_dict(spec, seed=seed, simmim=False)
+    enc = ref_encoder_v1(spec, spec.v1_merge).eval()
+    assert dict((k, tuple(v.shape)) for k, v in enc.state_dict().items()) == dict(O.state_dict_layout(spec, False))
+    enc.load_state_dict(sd, strict=True)
+    x = O.synthetic_cube(spec, B, seed=seed, zero_pad_bands=zero_pad)
+    with torch.no_grad():
+        logits = enc(x)
+    ssd = O.synthetic_state_dict(spec, seed=seed + 100, simmim=True, blockwise_decoder=False)
+    m = SimMIMSpatialSpectral(encoder=ref_encoder_v1(spec, spec.v1_merge), masking_ratio=0.7, mask_patch_size=4, tube_masking=True,
+                              intermediate_losses=intermediate, to_pixels_per_spectral_block=False).train()
+    ref_keys = dict((k, tuple(v.shape)) for k, v in m.state_dict().items())
+    lay = dict(O.state_dict_layout(spec, True, False))
+    assert all(k in ref_keys and ref_keys[k] == s for k, s in lay.items()), "layout mismatch"
+    extra = sorted(set(ref_keys) - set(lay))
+    m.load_state_dict(ssd, strict=False)
+    np.random.seed(seed)
+    captured = {}
+    orig = m.mask_generator.get_batch_tube_masked
+    def wrap(*a, **k):
+        bm, ix = orig(*a, **k)
+        captured["mask"], captured["idx"] = bm.clone(), ix.clone()
+        return bm, ix
+    m.mask_generator.get_batch_tube_masked = wrap
+    loss = m(x)
+    loss.backward()
+    seen, named = set(), []
+    for k, p in m.named_parameters():
+        if id(p) in seen or p.grad is None:
+            continue
+        seen.add(id(p)); named.append((k, p.grad))
+    names, rows = grad_summary(named)
+    save(name, logits=logits.numpy(), loss=np.float64(loss.item()), mask=captured["mask"].numpy(), idx=captured["idx"].numpy(),
+         grad_names=np.array(names), grad_rows=rows, extra_keys=np.array(extra),
+         grad__mask_token=m.mask_token.grad.numpy(), grad__to_pixels_weight=m.to_pixels.weight.grad.numpy(),
+         grad__pos_embedding_rows=m.encoder.pos_embedding.grad.numpy()[0, [0, 1, 2, spec.T]],
+         meta=json.dumps(dict(B=B, seed=seed, zero_pad=zero_pad, intermediate=intermediate, merge=spec.v1_merge)))
+
+
 def case_maskgen():
     """MaskGenerator draws for several seeds/shapes (host numpy RNG)."""
     from src.vit_simmim_original import MaskGenerator
@@ -172,6 +221,11 @@ def case_sincos():
 if __name__ == "__main__":
     H = O.Spec(**O.HOUSTON)
     E = O.Spec(**O.ENMAP)
+    if sys.argv[1:] == ["v1"]:    # only the cases added after the first fixture set (keeps the older .npz files byte-identical)
+        case_v1("houston_v1_intermediate", O.Spec(**O.HOUSTON, v1=True), B=2, seed=14, zero_pad=2, intermediate=True)
+        case_v1("houston_v1_linearmerge", O.Spec(**O.HOUSTON, v1=True, v1_merge="linear", depth=2), B=2, seed=15, zero_pad=0,
+                intermediate=False)
+        sys.exit(0)
     m = case_encoder("houston_encoder", H, B=2, zero_pad=2, seed=5)
     case_encoder("enmap_encoder", E, B=1, zero_pad=0, seed=6)
     case_encoder("enmap_encoder_spectralpos", O.Spec(**O.ENMAP, spectral_pos_embed=True), B=1, zero_pad=0, seed=7)

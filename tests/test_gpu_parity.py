@@ -235,3 +235,49 @@ def test_whole_tile_inference_equals_window_loop():
     labels[0, :4] = -1
     acc, n = tile_accuracy(full, labels)
     assert float(acc) == 1.0 and int(n) == 2 * 24 * 16 - 4 * 16
+
+
+@pytest.mark.parametrize("name,kw", [("houston_v1_intermediate", dict(**O.HOUSTON, v1=True)),
+                                     ("houston_v1_linearmerge", dict(**O.HOUSTON, v1=True, v1_merge="linear", depth=2))])
+def test_v1_encoder_and_simmim_vs_reference_golden(name, kw):
+    """Legacy ViTSpatialSpectral_V1 (reference :600-764): logits, then a SimMIM step with the shared decoder and
+    `intermediate_losses`, against vectors from the unmodified reference."""
+    g = gold(name)
+    meta = json.loads(str(g["meta"]))
+    spec = O.Spec(**kw)
+
+    def make():
+        return M.ViTSpatialSpectral_V1(image_size=8, spatial_patch_size=1, spectral_patch_size=10, num_classes=spec.num_classes,
+                                       dim=spec.dim, depth=spec.depth, heads=spec.heads, mlp_dim=spec.mlp_dim, channels=spec.channels,
+                                       merge=meta["merge"])
+    enc = make().eval()
+    enc.load_state_dict(O.synthetic_state_dict(spec, seed=meta["seed"]), strict=True)
+    enc.to(DEV)
+    x = O.synthetic_cube(spec, meta["B"], seed=meta["seed"], zero_pad_bands=meta["zero_pad"]).to(DEV)
+    with torch.no_grad():
+        assert rel_l2(enc(x), g["logits"]) < TOL
+    m = M.SimMIMSpatialSpectral(encoder=make(), masking_ratio=0.7, mask_patch_size=4, tube_masking=True,
+                                intermediate_losses=meta["intermediate"]).train()
+    assert sorted(set(m.state_dict()) - set(dict(O.state_dict_layout(spec, True, False)))) == [str(k) for k in g["extra_keys"]]
+    missing, unexpected = m.load_state_dict(O.synthetic_state_dict(spec, seed=meta["seed"] + 100, simmim=True, blockwise_decoder=False),
+                                            strict=False)
+    assert not unexpected and all(k.startswith("patch_to_emb.") for k in missing)
+    m.to(DEV)
+    np.random.seed(meta["seed"])
+    loss = m(x)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < TOL * abs(float(g["loss"]))
+    seen, named = set(), []
+    for k, p in m.named_parameters():
+        if id(p) in seen or p.grad is None:
+            continue
+        seen.add(id(p)); named.append((k, p.grad))
+    check_grad_rows(grad_rows(named), g["grad_names"], g["grad_rows"], tol=GTOL)
+    assert rel_l2(m.mask_token.grad, g["grad__mask_token"]) < GTOL
+    assert rel_l2(m.to_pixels.weight.grad, g["grad__to_pixels_weight"]) < GTOL
+    pg = m.encoder.pos_embedding.grad[0, [0, 1, 2, spec.T]]
+    assert float(pg[0].abs().max()) == 0.0 and rel_l2(pg, g["grad__pos_embedding_rows"]) < GTOL
+    with pytest.raises(NotImplementedError):
+        M.SimMIMSpatialSpectral(encoder=make(), to_pixels_per_spectral_block=True)
+    with pytest.raises(NotImplementedError):
+        M.SimMIMSpatialSpectral(encoder=make_encoder(O.Spec(**O.HOUSTON)), intermediate_losses=True)

@@ -104,6 +104,34 @@ def test_simmim_matches_reference(name, kw):
             assert rel_l2(p[k[6:]].grad, g[k]) < 2e-5, k
 
 
+V1_CASES = [("houston_v1_intermediate", dict(**O.HOUSTON, v1=True)),
+            ("houston_v1_linearmerge", dict(**O.HOUSTON, v1=True, v1_merge="linear", depth=2))]
+
+
+@pytest.mark.parametrize("name,kw", V1_CASES)
+def test_v1_matches_reference(name, kw):
+    """Legacy ViTSpatialSpectral_V1 (+ SimMIM with the shared decoder, `intermediate_losses`)."""
+    g = gold(name)
+    meta = json.loads(str(g["meta"]))
+    spec = O.Spec(**kw)
+    x = O.synthetic_cube(spec, meta["B"], seed=meta["seed"], zero_pad_bands=meta["zero_pad"])
+    assert rel_l2(O.encoder_forward(x, O.synthetic_state_dict(spec, seed=meta["seed"]), spec), g["logits"]) < 5 * TOL
+    p = _params(O.synthetic_state_dict(spec, seed=meta["seed"] + 100, simmim=True, blockwise_decoder=False))
+    np.random.seed(meta["seed"])
+    mask, idx = O.MaskGen(spec.image_size, 4, 1, 0.7).batch(meta["B"], spec.C, int(0.7 * spec.T), True)
+    assert np.array_equal(mask.numpy(), g["mask"]) and np.array_equal(idx.numpy(), g["idx"])
+    loss = O.simmim_forward(x, p, spec, mask, idx, blockwise_decoder=False, intermediate_losses=meta["intermediate"])
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < 5 * TOL * abs(float(g["loss"]))
+    rows = grad_rows([(k, v.grad) for k, v in p.items() if v.grad is not None])
+    check_grad_rows(rows, [str(n) for n in g["grad_names"]], g["grad_rows"], tol=2e-5)
+    assert rel_l2(p["mask_token"].grad, g["grad__mask_token"]) < 2e-5
+    assert rel_l2(p["to_pixels.weight"].grad, g["grad__to_pixels_weight"]) < 2e-5
+    pg = p["encoder.pos_embedding"].grad[0, [0, 1, 2, spec.T]]
+    assert float(pg[0].abs().max()) == 0.0          # row 0 is dead on the SimMIM path (C11)
+    assert rel_l2(pg, g["grad__pos_embedding_rows"]) < 2e-5
+
+
 def test_maskgen_matches_reference():
     g = gold("maskgen")
     for k in g.files:
