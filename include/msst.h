@@ -54,11 +54,32 @@ MSST_API long long msst_launch_count(void);
  *       tokens   [B, T, D] out
  *       patches_ln [B,T,P] optional out: pre-norm'ed patches (PatchEmbed SimMIM target, C6), or NULL
  * ------------------------------------------------------------------------------------------- */
+/* Optional RAW input: the cube is read from sensor tiles with the reference's input pipeline applied on the fly inside
+ * the patch-embedding and decoder kernels (no fp32 cube in HBM; the host ships int16).  Replaces, per pixel:
+ *   (raw - means[band]) / stds[band] in float64 -> fp32   StandardizeEnMAP.__call__ / StandardizeHouston2018.__call__ + ToTensor
+ *                                                         (src/data_enmap.py:454-457,517-522; src/data_houston2018.py:442-445)
+ *   torch.clip(img, clip_lo, clip_hi) of the standardised value (src/data_enmap.py:303-304), when clip != 0
+ *   zero bands raw_bands .. C*p0-1                        (Houston 48 -> 50: F.pad, src/data_houston2018.py:268-269)
+ *   img[:, :, y0:y0+H, x0:x0+W], one window for the batch (pretrain.py:99-107)
+ * When `raw` is set in the dims struct the `img` argument of the entry point is ignored (may be NULL). */
+enum { MSST_RAW_I16 = 0, MSST_RAW_U16 = 1, MSST_RAW_F32 = 2 };
+typedef struct {
+    const void* tiles;           /* device [B, raw_bands, tile_h, tile_w], element type `dtype` */
+    int dtype;                   /* MSST_RAW_* */
+    int raw_bands;               /* <= C*p0; model bands beyond it are zero */
+    int tile_h, tile_w;
+    int y0, x0;                  /* crop window origin inside the tile */
+    const double* mean;          /* device [raw_bands] float64 */
+    const double* std;           /* device [raw_bands] float64 */
+    int clip; float clip_lo, clip_hi;
+} msst_raw_input;
+
 typedef struct {
     int B, C, G, p0, p1, D;      /* G = spatial patches per side, P = p0*p1*p1, S = G*G, T = C*S */
     int n_weight_blocks;         /* C for blockwise embedding, 1 for PatchEmbed */
     float drop_p; uint64_t seed; /* emb-dropout (encoder.forward path only) */
     const uint64_t* seed_dev;    /* optional device u64 added to seed (fresh masks per CUDA-graph replay); may be NULL */
+    const msst_raw_input* raw;   /* optional (host pointer): read pixels from raw tiles instead of `img`; may be NULL */
 } msst_embed_dims;
 
 MSST_API int msst_patch_embed_fwd(const msst_embed_dims* d, const float* img, const float* pre_w, const float* pre_b,
@@ -184,7 +205,9 @@ MSST_API int msst_cross_entropy_fwd_bwd(const float* logits, const int64_t* labe
  *   loss        = mean |pred - target| / num_masked          (double normalisation)
  * idx [B,nm] int64 may disagree with the bool mask and may repeat (C3): backward accumulates.
  * ------------------------------------------------------------------------------------------- */
-typedef struct { int B, C, G, p0, p1, D, nm, n_weight_blocks; } msst_decode_dims;
+typedef struct { int B, C, G, p0, p1, D, nm, n_weight_blocks;
+                 const msst_raw_input* raw;   /* optional: gather the target pixels from raw tiles (see msst_raw_input); may be NULL */
+} msst_decode_dims;
 MSST_API int msst_simmim_decode_l1_fwd(const msst_decode_dims* d, const float* enc, const int64_t* idx, const float* img,
                               const float* target_tokens, const float* W, const float* bias, float* pred /*or NULL*/,
                               float* partial /*[B*nm] scratch*/, float* loss, msst_stream_t stream);

@@ -10,7 +10,8 @@ from .vit_spatial_spectral import (ViTSpatialSpectral, ViTSpatialSpectral_V1, Tr
                                    BlockwisePatchEmbedding, PatchEmbed, MoveAxis, get_pos_for_spectral_embedding)
 from .vit_simmim_original import SimMIMSpatialSpectral, BlockwiseToPixels, MaskGenerator
 from .ops import cross_entropy
+from .input import RawTiles
 
 __all__ = ["ViTSpatialSpectral", "ViTSpatialSpectral_V1", "SimMIMSpatialSpectral", "BlockwiseToPixels", "MaskGenerator", "Transformer", "Attention",
            "FeedForward", "PreNorm", "BlockwisePatchEmbedding", "PatchEmbed", "MoveAxis", "get_pos_for_spectral_embedding",
-           "cross_entropy"]
+           "cross_entropy", "RawTiles"]

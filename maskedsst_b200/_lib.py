@@ -12,9 +12,19 @@ u64p = C.POINTER(C.c_uint64)
 vp = C.c_void_p
 
 
+RAW_I16, RAW_U16, RAW_F32 = 0, 1, 2
+
+
+class RawInput(C.Structure):   # msst_raw_input
+    _fields_ = [("tiles", vp), ("dtype", C.c_int), ("raw_bands", C.c_int), ("tile_h", C.c_int), ("tile_w", C.c_int),
+                ("y0", C.c_int), ("x0", C.c_int), ("mean", vp), ("std", vp), ("clip", C.c_int), ("clip_lo", C.c_float),
+                ("clip_hi", C.c_float)]
+
+
 class EmbedDims(C.Structure):
     _fields_ = [("B", C.c_int), ("C", C.c_int), ("G", C.c_int), ("p0", C.c_int), ("p1", C.c_int), ("D", C.c_int),
-                ("n_weight_blocks", C.c_int), ("drop_p", C.c_float), ("seed", C.c_uint64), ("seed_dev", vp)]
+                ("n_weight_blocks", C.c_int), ("drop_p", C.c_float), ("seed", C.c_uint64), ("seed_dev", vp),
+                ("raw", C.POINTER(RawInput))]
 
 
 class LinearDims(C.Structure):
@@ -43,7 +53,7 @@ class HeadDims(C.Structure):
 
 class DecodeDims(C.Structure):
     _fields_ = [("B", C.c_int), ("C", C.c_int), ("G", C.c_int), ("p0", C.c_int), ("p1", C.c_int), ("D", C.c_int),
-                ("nm", C.c_int), ("n_weight_blocks", C.c_int)]
+                ("nm", C.c_int), ("n_weight_blocks", C.c_int), ("raw", C.POINTER(RawInput))]
 
 
 class AdamArgs(C.Structure):

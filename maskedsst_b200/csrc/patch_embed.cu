@@ -6,6 +6,7 @@
 // Work decomposition: one CTA per (sample b, spectral block c, chunk of 64 spatial positions).  With
 // spatial patch size 1 the chunk's pixels are P runs of 64 contiguous floats (256 B each) -> coalesced.
 #include "common.cuh"
+#include "pixel_source.cuh"
 
 namespace msst {
 
@@ -14,26 +15,27 @@ constexpr int kThreads = 256;  // 8 warps, 8 tokens each
 
 struct EmbedGeom {
     int B, C, G, p0, p1, D, P, S, T, HW, Wimg, nb;
+    PixelSource src;
 };
 
-__device__ __forceinline__ int64_t pixel_index(const EmbedGeom& g, int b, int c, int s, int p) {
+__device__ __forceinline__ float load_pixel(const EmbedGeom& g, int b, int c, int s, int p) {
     // element p = (p0i, p1i, p2i) of the patch at spatial position s = (h, w) of spectral block c
-    if (g.p1 == 1) return ((int64_t)(b * g.C + c) * g.p0 + p) * g.HW + s;
+    if (g.p1 == 1) return g.src.load(b, c * g.p0 + p, s / g.Wimg, s % g.Wimg);
     const int pp = g.p1 * g.p1;
     const int p0i = p / pp, r = p % pp, p1i = r / g.p1, p2i = r % g.p1;
     const int h = s / g.G, w = s % g.G;
-    return ((int64_t)(b * g.C + c) * g.p0 + p0i) * g.HW + (int64_t)(h * g.p1 + p1i) * g.Wimg + (w * g.p1 + p2i);
+    return g.src.load(b, c * g.p0 + p0i, h * g.p1 + p1i, w * g.p1 + p2i);
 }
 
 // loads the chunk's raw patches into xs[tok][P+1] and pre-normalises: xs <- xhat, hs <- xhat*w+b
-__device__ __forceinline__ void load_and_prenorm(const EmbedGeom& g, const float* __restrict__ img, int b, int c, int s0,
+__device__ __forceinline__ void load_and_prenorm(const EmbedGeom& g, int b, int c, int s0,
                                                  const float* __restrict__ pre_w, const float* __restrict__ pre_b,
                                                  float* xs, float* hs, float* rstd_s) {
     const int P = g.P, ld = P + 1;
     for (int i = threadIdx.x; i < kTok * P; i += kThreads) {
         const int tok = i % kTok, p = i / kTok;
         const int s = s0 + tok;
-        xs[tok * ld + p] = s < g.S ? __ldg(img + pixel_index(g, b, c, s, p)) : 0.f;
+        xs[tok * ld + p] = s < g.S ? load_pixel(g, b, c, s, p) : 0.f;
     }
     __syncthreads();
     if (threadIdx.x < kTok) {
@@ -72,7 +74,7 @@ patch_embed_fwd_kernel(EmbedGeom g, int n_wb, const float* __restrict__ img, con
     const int s0 = chunk * kTok;
     const int wb = n_wb == 1 ? 0 : c;
     for (int i = threadIdx.x; i < D * P; i += kThreads) Ws[(i / P) * ld + (i % P)] = __ldg(W + (int64_t)wb * D * P + i);
-    load_and_prenorm(g, img, b, c, s0, pre_w, pre_b, xs, hs, rstd_s);
+    load_and_prenorm(g, b, c, s0, pre_w, pre_b, xs, hs, rstd_s);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float bj[NJ], pw[NJ], pb[NJ], mt[NJ];
@@ -170,7 +172,7 @@ patch_embed_bwd_kernel(EmbedGeom g, int n_wb, const float* __restrict__ img, con
             for (int j = 0; j < NJ; ++j) dt_all[k][j] = s < g.S ? d_tokens[row * D + lane + 32 * j] : 0.f;
         }
         __syncthreads();
-        load_and_prenorm(g, img, b, c, s0, pre_w, pre_b, xs, hs, rstd_s);
+        load_and_prenorm(g, b, c, s0, pre_w, pre_b, xs, hs, rstd_s);
 #pragma unroll
         for (int k = 0; k < TPW; ++k) {
             const int tok = warp * TPW + k, s = s0 + tok;
@@ -296,7 +298,7 @@ patch_embed_bwd_kernel(EmbedGeom g, int n_wb, const float* __restrict__ img, con
     }
 }
 
-static int make_geom(const msst_embed_dims* d, EmbedGeom& g) {
+static int make_geom(const msst_embed_dims* d, const float* img, EmbedGeom& g) {
     MSST_REQUIRE(d && d->B > 0 && d->C > 0 && d->G > 0 && d->p0 > 0 && d->p1 > 0, "patch_embed: bad dims");
     MSST_REQUIRE(d->D % 32 == 0 && d->D >= 32 && d->D <= 256, "patch_embed: D=%d must be a multiple of 32 in [32,256]", d->D);
     MSST_REQUIRE(d->n_weight_blocks == 1 || d->n_weight_blocks == d->C, "patch_embed: n_weight_blocks must be 1 or C");
@@ -304,6 +306,7 @@ static int make_geom(const msst_embed_dims* d, EmbedGeom& g) {
     g.P = d->p0 * d->p1 * d->p1; g.S = d->G * d->G; g.T = g.C * g.S;
     g.Wimg = d->G * d->p1; g.HW = g.Wimg * g.Wimg; g.nb = 1;
     MSST_REQUIRE(g.P <= 64, "patch_embed: pixels per patch %d > 64 unsupported", g.P);
+    if (const char* e = make_pixel_source(g.src, img, d->raw, g.C * g.p0, g.Wimg, g.Wimg)) { set_error("patch_embed: %s", e); return MSST_ERR_ARG; }
     return MSST_OK;
 }
 
@@ -344,7 +347,7 @@ extern "C" int msst_patch_embed_fwd(const msst_embed_dims* d, const float* img, 
                                     const float* pos, const uint8_t* mask, const float* mask_token, float* tokens,
                                     float* patches_ln, msst_stream_t stream) {
     EmbedGeom g;
-    if (int rc = make_geom(d, g)) return rc;
+    if (int rc = make_geom(d, img, g)) return rc;
     MSST_REQUIRE(!mask || mask_token, "patch_embed: mask given without mask_token");
     const size_t smem = sizeof(float) * ((size_t)2 * kTok * (g.P + 1) + (size_t)g.D * (g.P + 1) + kTok);
     const Drop drop = make_drop(d->drop_p, d->seed, kSiteEmb, d->seed_dev);
@@ -364,7 +367,7 @@ extern "C" int msst_patch_embed_bwd(const msst_embed_dims* d, const float* img, 
                                     float* d_pre_b, float* d_W, float* d_bias, float* d_post_w, float* d_post_b,
                                     float* d_pos, float* d_mask_token, msst_stream_t stream) {
     EmbedGeom g;
-    if (int rc = make_geom(d, g)) return rc;
+    if (int rc = make_geom(d, img, g)) return rc;
     MSST_REQUIRE(g.P <= 16, "patch_embed_bwd: pixels per patch %d > 16 unsupported in backward", g.P);
     const int pmax = 16;
     size_t red = (size_t)8 * g.D;

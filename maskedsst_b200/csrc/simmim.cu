@@ -4,17 +4,18 @@
 // The gathers are fused: masked rows are read straight from the encoder output and target pixels straight
 // from the input cube.  HBM-bound: per masked token D + P floats in, nothing out (the loss is a scalar).
 #include "common.cuh"
+#include "pixel_source.cuh"
 
 namespace msst {
 
 constexpr int DT = 256;
-struct DecGeom { int B, C, G, p0, p1, D, nm, n_wb, P, S, T, HW, Wimg; };
+struct DecGeom { int B, C, G, p0, p1, D, nm, n_wb, P, S, T, HW, Wimg; PixelSource src; };
 
-__device__ __forceinline__ float target_pixel(const DecGeom& g, const float* __restrict__ img, int b, int t, int p) {
+__device__ __forceinline__ float target_pixel(const DecGeom& g, int b, int t, int p) {
     const int c = t / g.S, s = t % g.S;
-    if (g.p1 == 1) return img[((int64_t)(b * g.C + c) * g.p0 + p) * g.HW + s];
+    if (g.p1 == 1) return g.src.load(b, c * g.p0 + p, s / g.Wimg, s % g.Wimg);
     const int pp = g.p1 * g.p1, p0i = p / pp, r = p % pp, p1i = r / g.p1, p2i = r % g.p1, h = s / g.G, w = s % g.G;
-    return img[((int64_t)(b * g.C + c) * g.p0 + p0i) * g.HW + (int64_t)(h * g.p1 + p1i) * g.Wimg + (w * g.p1 + p2i)];
+    return g.src.load(b, c * g.p0 + p0i, h * g.p1 + p1i, w * g.p1 + p2i);
 }
 
 // lane p < P fetches target element p and bias p of the item up front (one load instruction each instead of P dependent
@@ -35,7 +36,7 @@ __global__ void __launch_bounds__(DT) decode_fwd_kernel(DecGeom g, const float* 
         for (int j = 0; j < NJ; ++j) e[j] = enc[((int64_t)b * g.T + t) * g.D + lane + 32 * j];
         float tgb = 0.f;   // target_p - bias_p held by lane p
         if (lane < g.P)
-            tgb = (tgt_tok ? tgt_tok[((int64_t)b * g.T + t) * g.P + lane] : target_pixel(g, img, b, t, lane)) - bias[blk * g.P + lane];
+            tgb = (tgt_tok ? tgt_tok[((int64_t)b * g.T + t) * g.P + lane] : target_pixel(g, b, t, lane)) - bias[blk * g.P + lane];
         float mine = 0.f;  // lane p keeps dot product p
 #pragma unroll
         for (int p = 0; p < PMAX; ++p) {
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(DT) decode_bwd_kernel(DecGeom g, const float* 
         for (int j = 0; j < NJ; ++j) { e[j] = enc[((int64_t)b * g.T + t) * g.D + lane + 32 * j]; de[j] = 0.f; }
         float tgb = 0.f;   // lane p: target_p - bias_p (fetched before the reduction loop)
         if (lane < g.P)
-            tgb = (tgt_tok ? tgt_tok[((int64_t)b * g.T + t) * g.P + lane] : target_pixel(g, img, b, t, lane)) - bias[blk * g.P + lane];
+            tgb = (tgt_tok ? tgt_tok[((int64_t)b * g.T + t) * g.P + lane] : target_pixel(g, b, t, lane)) - bias[blk * g.P + lane];
 #pragma unroll
         for (int p = 0; p < PMAX; ++p) {
             if (p < g.P) {
@@ -156,12 +157,16 @@ __global__ void __launch_bounds__(DT) decode_bwd_kernel(DecGeom g, const float* 
     }
 }
 
-static int make_geom(const msst_decode_dims* d, DecGeom& g) {
+static int make_geom(const msst_decode_dims* d, const float* img, const float* target_tokens, DecGeom& g) {
     MSST_REQUIRE(d && d->B > 0 && d->C > 0 && d->G > 0 && d->p0 > 0 && d->p1 > 0 && d->nm > 0, "simmim_decode: bad dims");
     MSST_REQUIRE(d->D % 32 == 0 && d->D >= 32 && d->D <= 256, "simmim_decode: D=%d must be a multiple of 32 in [32,256]", d->D);
     MSST_REQUIRE(d->n_weight_blocks == 1 || d->n_weight_blocks == d->C, "simmim_decode: n_weight_blocks must be 1 or C");
     g.B = d->B; g.C = d->C; g.G = d->G; g.p0 = d->p0; g.p1 = d->p1; g.D = d->D; g.nm = d->nm; g.n_wb = d->n_weight_blocks;
     g.P = d->p0 * d->p1 * d->p1; g.S = d->G * d->G; g.T = g.C * g.S; g.Wimg = d->G * d->p1; g.HW = g.Wimg * g.Wimg;
+    g.src = PixelSource{};
+    if (!target_tokens) {   // targets are gathered from the cube (fp32 or raw tiles)
+        if (const char* e = make_pixel_source(g.src, img, d->raw, g.C * g.p0, g.Wimg, g.Wimg)) { set_error("simmim_decode: %s", e); return MSST_ERR_ARG; }
+    }
     return MSST_OK;
 }
 
@@ -172,8 +177,7 @@ extern "C" int msst_simmim_decode_l1_fwd(const msst_decode_dims* d, const float*
                                          const float* target_tokens, const float* W, const float* bias, float* pred,
                                          float* partial, float* loss, msst_stream_t stream) {
     DecGeom g;
-    if (int rc = make_geom(d, g)) return rc;
-    MSST_REQUIRE(img || target_tokens, "simmim_decode: need img or target_tokens");
+    if (int rc = make_geom(d, img, target_tokens, g)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t total = (int64_t)g.B * g.nm;
     int64_t grid = ceil_div(total, DT / 32);
@@ -194,7 +198,7 @@ extern "C" int msst_simmim_decode_l1_bwd(const msst_decode_dims* d, const float*
                                          const float* target_tokens, const float* W, const float* bias, const float* d_loss,
                                          float* d_enc, float* d_W, float* d_bias, float* d_target_tokens, msst_stream_t stream) {
     DecGeom g;
-    if (int rc = make_geom(d, g)) return rc;
+    if (int rc = make_geom(d, img, target_tokens, g)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t total = (int64_t)g.B * g.nm;
     MSST_REQUIRE(g.P <= 16, "simmim_decode_bwd: pixels per patch %d > 16 unsupported", g.P);

@@ -7,6 +7,7 @@ import torch
 
 from . import _lib
 from ._lib import check, PREC_FP32, PREC_BF16
+from .input import RawTiles
 
 _SITE_EMB = 1
 SITE_LAYER_BASE = 16
@@ -66,19 +67,29 @@ class PatchEmbedFn(torch.autograd.Function):
         C_, G, p0, p1, D = geom
         B = img.shape[0]
         T = C_ * G * G
-        img = _c(img)
-        for n, t in (("img", img), ("pre_w", pre_w), ("W", W), ("pos", pos)):
+        raw = img if isinstance(img, RawTiles) else None     # pixels come from raw tiles through the fused input pipeline
+        if raw is not None:
+            if tuple(raw.shape[1:]) != (C_ * p0, G * p1, G * p1):
+                raise RuntimeError(f"maskedsst_b200: RawTiles cube shape {tuple(raw.shape)} does not match the model ({C_ * p0} bands, {G * p1} px)")
+            ctx.raw_struct = raw.c_struct()
+            img = None
+        else:
+            img = _c(img)
+            _chk(img, "img")
+        for n, t in (("pre_w", pre_w), ("W", W), ("pos", pos)):
             _chk(t, n)
         mask_u8 = None
         if mask is not None:
             mask_u8 = _c(mask.to(torch.uint8))
-        dims = _lib.EmbedDims(B, C_, G, p0, p1, D, W.shape[0], float(drop_p), seed, _seed_dev())
-        tokens = torch.empty(B, T, D, device=img.device, dtype=torch.float32)
-        pln = torch.empty(B, T, p0 * p1 * p1, device=img.device, dtype=torch.float32) if want_ln else None
+        dims = _lib.EmbedDims(B, C_, G, p0, p1, D, W.shape[0], float(drop_p), seed, _seed_dev(),
+                              C.pointer(ctx.raw_struct) if raw is not None else None)
+        tokens = torch.empty(B, T, D, device=pos.device, dtype=torch.float32)
+        pln = torch.empty(B, T, p0 * p1 * p1, device=pos.device, dtype=torch.float32) if want_ln else None
         pos_c = _c(pos)
         check(_lib.lib().msst_patch_embed_fwd(C.byref(dims), _p(img), _p(pre_w), _p(pre_b), _p(W), _p(bias), _p(post_w),
                                               _p(post_b), _p(pos_c), _p(mask_u8), _p(mask_token), _p(tokens), _p(pln), _stream()))
         ctx.save_for_backward(img, pre_w, pre_b, W, bias, post_w, post_b, mask_u8)
+        ctx.raw = raw            # keeps the tiles / statistics alive until backward
         ctx.dims = dims
         ctx.has_mt = mask_token is not None
         ctx.pos_shape = pos.shape
@@ -90,7 +101,7 @@ class PatchEmbedFn(torch.autograd.Function):
         dims = ctx.dims
         T, D = ctx.pos_shape
         sizes = [pre_w.numel(), pre_b.numel(), W.numel(), bias.numel(), post_w.numel(), post_b.numel(), T * D, D]
-        flat = torch.zeros(sum(sizes), device=img.device, dtype=torch.float32)
+        flat = torch.zeros(sum(sizes), device=pre_w.device, dtype=torch.float32)
         g = list(torch.split(flat, sizes))
         d_tokens = _c(d_tokens)
         d_pln = _c(d_pln) if d_pln is not None else None
@@ -265,11 +276,17 @@ class DecodeL1Fn(torch.autograd.Function):
         _chk(enc, "enc")
         idx = _c(idx)
         _chk(idx, "idx", torch.int64)
+        raw = img if isinstance(img, RawTiles) else None
         if target_tokens is not None:
             target_tokens = _c(target_tokens)
+            raw = img = None
+        elif raw is not None:
+            ctx.raw_struct = raw.c_struct()
+            img = None
         else:
             img = _c(img)
-        dims = _lib.DecodeDims(B, C_, G, p0, p1, D, nm, W.shape[0])
+        ctx.raw = raw
+        dims = _lib.DecodeDims(B, C_, G, p0, p1, D, nm, W.shape[0], C.pointer(ctx.raw_struct) if raw is not None else None)
         partial = torch.empty(B * nm, device=enc.device, dtype=torch.float32)
         loss = torch.empty((), device=enc.device, dtype=torch.float32)
         check(_lib.lib().msst_simmim_decode_l1_fwd(C.byref(dims), _p(enc), _p(idx), _p(img), _p(target_tokens), _p(W), _p(bias),

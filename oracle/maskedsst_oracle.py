@@ -196,6 +196,32 @@ def synthetic_cube(spec: Spec, batch: int, seed: int = 5, zero_pad_bands: int = 
     return torch.from_numpy(x)
 
 
+def synthetic_raw_tiles(batch: int, bands: int, size: int = 64, seed: int = 21) -> np.ndarray:
+    """Stand-in for raw sensor tiles [B, bands, size, size] int16 (reflectance * 10000 range, with some negatives and
+    saturated values so a clip has something to do)."""
+    rng = np.random.Generator(np.random.PCG64(seed + 2000))
+    return rng.integers(-400, 12000, (batch, bands, size, size)).astype(np.int16)
+
+
+def input_pipeline(raw: np.ndarray, means, stds, image_size: int, crop=(0, 0), pad_bands: int = 0, clip=None) -> torch.Tensor:
+    """The reference's path from a raw tile to the model's cube:
+      StandardizeEnMAP / StandardizeHouston2018.__call__: (x - means[:,None,None]) / stds[:,None,None] on the numpy array
+        -> float64 (src/data_enmap.py:454-457, src/data_houston2018.py:442-445);
+      ToTensor: torch.Tensor(x).to(float32) -> one rounding to fp32 (src/data_enmap.py:517-522);
+      EnMAP: torch.clip(img, clip[0], clip[1]) on the standardised values (src/data_enmap.py:303-304);
+      Houston: F.pad 48 -> 50 zero bands after standardisation (src/data_houston2018.py:268-269);
+      one crop window img[:, :, x:x+s, y:y+s] for the whole batch (pretrain.py:99-107)."""
+    m = np.asarray(means, dtype=np.float64)[None, :, None, None]
+    sd = np.asarray(stds, dtype=np.float64)[None, :, None, None]
+    x = torch.from_numpy(((raw - m) / sd)).to(torch.float32)
+    if clip is not None:
+        x = torch.clip(x, min=clip[0], max=clip[1])
+    if pad_bands:
+        x = F.pad(x, (0, 0, 0, 0, 0, pad_bands), "constant", 0)
+    a, b = crop
+    return x[:, :, a: a + image_size, b: b + image_size].contiguous()
+
+
 # --------------------------------------------------------------------------------------
 # forward pieces
 # --------------------------------------------------------------------------------------

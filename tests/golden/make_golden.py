@@ -195,6 +195,59 @@ def case_v1(name, spec, B, seed, zero_pad, intermediate):
          meta=json.dumps(dict(B=B, seed=seed, zero_pad=zero_pad, intermediate=intermediate, merge=spec.v1_merge)))
 
 
+def _stub_missing(roots=("rasterio", "spectral", "torchmetrics", "wandb")):
+    """The reference's data modules import I/O libraries that are not installed here; only their Standardize* / ToTensor
+    classes (pure numpy / torch) are exercised, so absent libraries are replaced by empty stub modules."""
+    import importlib.abc, importlib.machinery, types
+    class _Stub(types.ModuleType):
+        __path__ = []
+        def __getattr__(self, k):
+            if k.startswith("__"):
+                raise AttributeError(k)
+            return type(k, (), {})
+    class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+        def find_spec(self, name, path=None, target=None):
+            if name.split(".")[0] in roots:
+                return importlib.machinery.ModuleSpec(name, self, is_package=True)
+        def create_module(self, spec):
+            return _Stub(spec.name)
+        def exec_module(self, module):
+            pass
+    sys.meta_path.append(_Finder())
+
+
+def case_input_pipeline():
+    """The reference's input pipeline on synthetic raw int16 tiles: Standardize* (numpy float64) -> ToTensor (fp32) ->
+    [EnMAP: torch.clip] / [Houston: F.pad 48 -> 50] -> one crop window per batch (pretrain.py:99-107)."""
+    _stub_missing()
+    import torch.nn.functional as F
+    from src.data_enmap import StandardizeEnMAP, ToTensor
+    from src.data_houston2018 import StandardizeHouston2018
+    out = {}
+    for tag, std, nb, pad, clip, crop, seed in [("houston", StandardizeHouston2018(), 48, 2, None, (3, 41), 21),
+                                                ("enmap", StandardizeEnMAP(use_clipped=True), None, 0, (-200, 10000), (56, 0), 22),
+                                                ("enmap_tightclip", StandardizeEnMAP(use_clipped=False), None, 0, (-1.5, 2.0), (17, 30), 23)]:
+        means = std.means_clipped if getattr(std, "use_clipped", False) else std.means
+        stds = std.stds_clipped if getattr(std, "use_clipped", False) else std.stds
+        nb = nb or len(means)
+        raw = O.synthetic_raw_tiles(2, nb, 64, seed)
+        imgs = []
+        for i in range(raw.shape[0]):                     # per-sample transform chain, as the datasets apply it
+            img = ToTensor()(std(raw[i]))
+            if clip is not None:
+                img = torch.clip(img, min=clip[0], max=clip[1])
+            if pad:
+                img = F.pad(img, (0, 0, 0, 0, 0, pad), "constant", 0)
+            imgs.append(img)
+        batch = torch.stack(imgs)
+        x, y = crop
+        cube = batch[:, :, x: x + 8, y: y + 8]
+        out[f"{tag}__means"], out[f"{tag}__stds"] = np.asarray(means, dtype=np.float64), np.asarray(stds, dtype=np.float64)
+        out[f"{tag}__cube"] = cube.numpy()
+        out[f"{tag}__meta"] = json.dumps(dict(raw_bands=nb, pad=pad, clip=clip, crop=crop, seed=seed, B=2))
+    save("input_pipeline", **out)
+
+
 def case_maskgen():
     """MaskGenerator draws for several seeds/shapes (host numpy RNG)."""
     from src.vit_simmim_original import MaskGenerator
@@ -225,6 +278,9 @@ if __name__ == "__main__":
         case_v1("houston_v1_intermediate", O.Spec(**O.HOUSTON, v1=True), B=2, seed=14, zero_pad=2, intermediate=True)
         case_v1("houston_v1_linearmerge", O.Spec(**O.HOUSTON, v1=True, v1_merge="linear", depth=2), B=2, seed=15, zero_pad=0,
                 intermediate=False)
+        sys.exit(0)
+    if sys.argv[1:] == ["input"]:
+        case_input_pipeline()
         sys.exit(0)
     m = case_encoder("houston_encoder", H, B=2, zero_pad=2, seed=5)
     case_encoder("enmap_encoder", E, B=1, zero_pad=0, seed=6)

@@ -132,6 +132,19 @@ def test_v1_matches_reference(name, kw):
     assert rel_l2(pg, g["grad__pos_embedding_rows"]) < 2e-5
 
 
+@pytest.mark.parametrize("tag", ["houston", "enmap", "enmap_tightclip"])
+def test_input_pipeline_matches_reference_bit_exact(tag):
+    """Standardize* (float64) -> ToTensor (fp32) -> clip / zero-pad -> batch crop: the oracle restatement reproduces the
+    reference's cube bit for bit."""
+    g = gold("input_pipeline")
+    meta = json.loads(str(g[f"{tag}__meta"]))
+    raw = O.synthetic_raw_tiles(meta["B"], meta["raw_bands"], 64, meta["seed"])
+    cube = O.input_pipeline(raw, g[f"{tag}__means"], g[f"{tag}__stds"], 8, crop=tuple(meta["crop"]), pad_bands=meta["pad"],
+                            clip=tuple(meta["clip"]) if meta["clip"] else None)
+    assert cube.shape == g[f"{tag}__cube"].shape
+    assert np.array_equal(cube.numpy().view(np.uint32), g[f"{tag}__cube"].view(np.uint32))
+
+
 def test_maskgen_matches_reference():
     g = gold("maskgen")
     for k in g.files:
