@@ -657,6 +657,11 @@ int attention_bwd_bf16(const msst_attn_dims* d, const bf16* qkv, const bf16* out
     if (g.n_seq == 0) return MSST_OK;
     const Drop drop = make_drop(d->drop_p, d->seed, d->site, d->seed_dev);
     const dim3 grid((unsigned)(g.groups * g.tiles), g.H);
+    if (attention_tc_contiguous(g)) {   // default: tcgen05 / TMEM backward (attention_tc.cu, 1.5x the mma.sync kernel); MSST_ATTN_BWD_TC=0 selects mma.sync
+        static int use_tc = -1;
+        if (use_tc < 0) { const char* e = getenv("MSST_ATTN_BWD_TC"); use_tc = e ? atoi(e) : 1; }
+        if (use_tc) return attention_bwd_tc(g, qkv, lse, d_out, d_qkv, drop, st);
+    }
     if (g.tiles == 1) {
         static PerDeviceOnce hattr;
         if (hattr.first()) {

@@ -17,6 +17,8 @@
 #include "attn_geom.cuh"
 #include "ptx.cuh"
 #include <string.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace msst {
 using namespace ptx;
@@ -290,6 +292,342 @@ int attention_fwd_tc(const AttnGeom& g, const bf16* qkv, bf16* out, float* lse, 
     const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
     attn_fwd_tc_kernel<<<grid, TC_THREADS, kTcSmem, st>>>(tm, g, qkv, out, lse, drop, n_tiles, use_tma);
     MSST_LAUNCH_CHECK();
+    return MSST_OK;
+}
+
+// =========================================================================================================
+// Backward on tcgen05 / TMEM (N <= 64, tiles whose 128 slots are 128 consecutive rows: the spatial stack).
+//
+// Per (128-slot tile, head) item, all five contractions run on the tensor cores from one elected thread:
+//   S  = Q K^T, dP = dO V^T            -> TMEM [128 x 128] fp32 each (K-major operands straight from the TMA tiles)
+//   softmax warps (thread = query row): P = exp2(S*scale*log2e - lse), dropout mask regenerated from the pair hash,
+//       D_i = sum_j P~_ij dP_ij in registers (no O re-read), P~ and dS = P (f dP - D) scale -> smem (bf16, K-major rows)
+//   dV = P~^T dO, dK = dS^T Q          -> P~ / dS consumed as MN-major A operands, dO / Q as MN-major B (no transposes)
+//   dQ = dS K                          -> dS K-major A, K as MN-major B
+// dV | dK | dQ accumulate into the TMEM columns S / dP occupied (dead once the softmax warps hold them in registers), so an
+// item needs 256 columns and two items are in flight: the S/dP MMAs of item i+1 overlap the softmax of item i (two
+// ping-pong warpgroups).  Results leave through the dead Q/K/V tiles of the stage: bf16 rows -> smem -> TMA store.
+// Only the diagonal 64x64 blocks of S / dP are read; the off-diagonal halves of the P~ / dS tiles stay zero.
+// HBM-bound: (4 + 3) * 128 B per (slot, head).
+// =========================================================================================================
+struct alignas(8) TcbBars {
+    uint64_t full[2], kv_empty[2], s_full[2], o_full[2], tmem_free[2], p_full, pds_free, stg_free, stg_full;
+    uint32_t tmem_base;
+};
+constexpr int TCB_THREADS = 608;           // warps 0-7 softmax group A, 8-15 group B, 16 TMA producer (+ TMEM alloc), 17 MMA issuer, 18 TMA store
+// P~ / dS tiles [128 q][128 k] are block diagonal.  Each is kept as two OVERLAPPING virtual [128 rows][64 keys] chunks
+//   V0 = [C0: rows 0-63, keys 0-63][Z: 8 KB of zeros]      V1 = V0 + 8 KB = [Z][C1: rows 64-127, keys 64-127]
+// (24 KB instead of 32 KB: both chunks share the zero block), so the chunk stride of the UMMA descriptors is 8 KB.
+constexpr uint32_t TCB_CHUNK = 8192, TCB_PD = 3 * 8192;
+constexpr int TCB_PREFETCH = 2;            // items ahead whose operand boxes are prefetched into L2
+// smem: [2 stages][Q, K, V, dO][16 KB] | P~ (24 KB) | dS (24 KB) | output staging dQ, dK, dV [16 KB] | partial row sums | barriers
+// = 226.1 KB: no slack for re-aligning the base, the kernel checks that the dynamic window starts 1 KB aligned
+constexpr size_t kTcbSmem = 2 * 4 * TC_TILE + 2 * TCB_PD + 3 * TC_TILE + 2 * 2 * 128 * sizeof(float) + sizeof(TcbBars);
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// One thread's share of an item: 32 of the 64 diagonal-block columns of row r.  p[] holds S, q[] holds dP on entry.
+// Packs P~ (bf16 pairs) into pfp[], returns the partial row sum D; leaves p = P * scale and q = f * dP for the second pass.
+template <bool FULL, bool DROP>
+__device__ __forceinline__ float tcb_softmax_pass1(float (&p)[32], float (&q)[32], uint32_t (&pfp)[16], float sl2, float L, float scale, int c0,
+                                                   int klo, int khi, uint32_t hash_lo, uint32_t hash_hi, uint32_t t16, float dscale) {
+    float D = 0.f;
+#pragma unroll
+    for (int pc = 0; pc < 4; ++pc) {
+        float pf[8];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+            const int j = pc * 8 + e;
+            float f0 = 1.f, f1 = 1.f;
+            if (DROP) {   // lowbias32 over (pair index, seed, site): identical to tc_pair_hash (the pair index never carries into the high word)
+                uint32_t x = (hash_lo + (uint32_t)(j >> 1)) * 0x9E3779B1u ^ hash_hi;
+                x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+                f0 = (x & 0xFFFFu) >= t16 ? dscale : 0.f;
+                f1 = (x >> 16) >= t16 ? dscale : 0.f;
+            }
+            float p0 = ex2_approx(fmaf(p[j], sl2, -L)), p1 = ex2_approx(fmaf(p[j + 1], sl2, -L));
+            if (!FULL) {
+                p0 = (c0 + j >= klo && c0 + j < khi) ? p0 : 0.f;
+                p1 = (c0 + j + 1 >= klo && c0 + j + 1 < khi) ? p1 : 0.f;
+            }
+            pf[e] = DROP ? p0 * f0 : p0; pf[e + 1] = DROP ? p1 * f1 : p1;
+            D = fmaf(pf[e], q[j], D); D = fmaf(pf[e + 1], q[j + 1], D);
+            p[j] = p0 * scale; p[j + 1] = p1 * scale;
+            if (DROP) { q[j] *= f0; q[j + 1] *= f1; }
+        }
+        pfp[pc * 4] = pack_bf(pf[0], pf[1]); pfp[pc * 4 + 1] = pack_bf(pf[2], pf[3]);
+        pfp[pc * 4 + 2] = pack_bf(pf[4], pf[5]); pfp[pc * 4 + 3] = pack_bf(pf[6], pf[7]);
+    }
+    return D;
+}
+
+__global__ void __launch_bounds__(TCB_THREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
+                   const __grid_constant__ CUtensorMap tma_dqkv, AttnGeom g, const float* __restrict__ lse, Drop drop, int64_t n_tiles, long long* dbg) {
+#define TCB_T(it, slot) do { if (dbg && blockIdx.x == 0 && (it) < 32) dbg[(it) * 16 + (slot)] = clock64(); } while (0)
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if (smem_u32(smem) & 1023u) __trap();                   // SWIZZLE_128B tiles need 1 KB alignment (see kTcbSmem)
+    uint8_t* op_s = smem;                                   // [2][4][16 KB]
+    uint8_t* p_s = smem + 2 * 4 * TC_TILE;                  // P~ (24 KB), dS (24 KB)
+    uint8_t* stg_s = p_s + 2 * TCB_PD;                      // dQ, dK, dV staging for the TMA stores
+    float* dpart = reinterpret_cast<float*>(stg_s + 3 * TC_TILE);   // [group][half][128] partial row sums
+    TcbBars* bars = reinterpret_cast<TcbBars*>(dpart + 2 * 2 * 128);
+    const int warp = threadIdx.x >> 5;
+    const int I = g.H * 64;
+
+    if (warp == 17 && elect_one()) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bars->full[s], 1); mbar_init(&bars->kv_empty[s], 1); mbar_init(&bars->s_full[s], 1);
+            mbar_init(&bars->o_full[s], 1); mbar_init(&bars->tmem_free[s], 256);
+        }
+        mbar_init(&bars->p_full, 256); mbar_init(&bars->pds_free, 1); mbar_init(&bars->stg_free, 1); mbar_init(&bars->stg_full, 256);
+        fence_barrier_init();
+    }
+    if (warp == 16) {
+        tmem_alloc(&bars->tmem_base, 512);
+        if (elect_one()) { prefetch_tmap(&tma_qkv); prefetch_tmap(&tma_do); prefetch_tmap(&tma_dqkv); }
+    }
+    // the off-diagonal halves of the P~ / dS tiles are never written afterwards
+    for (uint32_t i = threadIdx.x; i < 2 * TCB_PD / 16; i += TCB_THREADS) reinterpret_cast<uint4*>(p_s)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+    const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0), idesc_mn = make_idesc_bf16(128, 64, 1, 1), idesc_q = make_idesc_bf16(128, 64, 0, 1);
+
+    const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const int64_t n_items = my_tiles * g.H;
+
+    if (warp == 16) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            for (int64_t it = 0; it < n_items; ++it) {
+                const int st = (int)(it & 1); const uint32_t ph = (uint32_t)(it >> 1) & 1;
+                const int64_t tile = blockIdx.x + (it / g.H) * gridDim.x; const int h = (int)(it % g.H);
+                mbar_wait(&bars->kv_empty[st], ph ^ 1);
+                TCB_T(it, 0);
+                uint8_t* base = op_s + (size_t)st * 4 * TC_TILE;
+                const int row0 = (int)(tile * TC_ROWS);
+                mbar_arrive_expect_tx(&bars->full[st], 4 * TC_TILE);
+                tma_load_2d(base, &tma_qkv, &bars->full[st], h * 64, row0);
+                tma_load_2d(base + TC_TILE, &tma_qkv, &bars->full[st], I + h * 64, row0);
+                tma_load_2d(base + 2 * TC_TILE, &tma_qkv, &bars->full[st], 2 * I + h * 64, row0);
+                tma_load_2d(base + 3 * TC_TILE, &tma_do, &bars->full[st], h * 64, row0);
+                if (it + TCB_PREFETCH < n_items) {   // pull a later item's operand boxes into L2 now (its smem stage is still busy)
+                    const int64_t it2 = it + TCB_PREFETCH;
+                    const int row2 = (int)((blockIdx.x + (it2 / g.H) * gridDim.x) * TC_ROWS); const int h2 = (int)(it2 % g.H);
+                    tma_prefetch_l2_2d(&tma_qkv, h2 * 64, row2);
+                    tma_prefetch_l2_2d(&tma_qkv, I + h2 * 64, row2);
+                    tma_prefetch_l2_2d(&tma_qkv, 2 * I + h2 * 64, row2);
+                    tma_prefetch_l2_2d(&tma_do, h2 * 64, row2);
+                }
+            }
+        }
+    } else if (warp == 17) {
+        // ===== MMA issuer =====
+        if (elect_one()) {
+            // Two kinds of work, issued in whatever order their inputs become ready (never block on one while the other
+            // could run): phase 1 of item next_s (S, dP; needs its operands + a drained TMEM stage) and phase 2 of item
+            // next_p (dV, dK, dQ; needs P~ / dS from the softmax warps).  Phase 1 runs at most one item ahead.
+            const uint32_t pb = smem_u32(p_s), dsb = pb + TCB_PD;
+            int64_t next_s = 0, next_p = 0;
+            while (next_p < n_items) {
+                if (next_s < n_items && next_s <= next_p + 1) {
+                    const int st = (int)(next_s & 1); const uint32_t ph = (uint32_t)(next_s >> 1) & 1;
+                    if (mbar_try_wait(&bars->tmem_free[st], ph ^ 1) && mbar_try_wait(&bars->full[st], ph)) {
+                        TCB_T(next_s, 1);
+                        tc_fence_after();
+                        const uint32_t qb = smem_u32(op_s + (size_t)st * 4 * TC_TILE);
+                        const uint64_t dq = make_smem_desc(qb, 16, 1024), dk = make_smem_desc(qb + TC_TILE, 16, 1024);
+                        const uint64_t dv = make_smem_desc(qb + 2 * TC_TILE, 16, 1024), dd = make_smem_desc(qb + 3 * TC_TILE, 16, 1024);
+                        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + st * 256, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k != 0);          // S = Q K^T
+                        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + st * 256 + 128, dd + (uint64_t)(k * 2), dv + (uint64_t)(k * 2), idesc_s, k != 0);    // dP = dO V^T
+                        umma_commit(&bars->s_full[st]);
+                        ++next_s;
+                    }
+                }
+                if (next_p < next_s && mbar_try_wait(&bars->p_full, (uint32_t)next_p & 1)) {   // P~ and dS written (generic proxy + the writers' fence)
+                    const int st = (int)(next_p & 1);
+                    TCB_T(next_p, 5);
+                    const uint32_t qb = smem_u32(op_s + (size_t)st * 4 * TC_TILE);
+                    fence_proxy_async();
+                    tc_fence_after();
+                    const uint64_t a_pf = make_smem_desc(pb, TCB_CHUNK, 1024), a_ds = make_smem_desc(dsb, TCB_CHUNK, 1024);
+                    const uint64_t b_q = make_smem_desc(qb, TC_TILE, 1024), b_k = make_smem_desc(qb + TC_TILE, TC_TILE, 1024);
+                    const uint64_t b_do = make_smem_desc(qb + 3 * TC_TILE, TC_TILE, 1024);
+                    const uint32_t d0 = tmem_base + st * 256;
+                    for (int k = 0; k < 8; ++k)   // dV[keys] = P~^T dO : reduction over the 128 queries, 16 rows (2 KB) per step
+                        umma_bf16(d0, a_pf + (uint64_t)(k * 128), b_do + (uint64_t)(k * 128), idesc_mn, k != 0);
+                    for (int k = 0; k < 8; ++k)   // dK[keys] = dS^T Q
+                        umma_bf16(d0 + 64, a_ds + (uint64_t)(k * 128), b_q + (uint64_t)(k * 128), idesc_mn, k != 0);
+                    for (int k = 0; k < 8; ++k) { // dQ[queries] = dS K : reduction over the 128 keys (2 chunks x 4 steps)
+                        const uint64_t a = make_smem_desc(dsb + (k >> 2) * TCB_CHUNK, 16, 1024) + (uint64_t)((k & 3) * 2);
+                        umma_bf16(d0 + 128, a, b_k + (uint64_t)(k * 128), idesc_q, k != 0);
+                    }
+                    umma_commit(&bars->o_full[st]);
+                    umma_commit(&bars->pds_free);
+                    umma_commit(&bars->kv_empty[st]);          // Q, K, V, dO of this stage are dead: the next loads may start
+                    ++next_p;
+                }
+            }
+        }
+    } else if (warp == 18) {
+        // ===== TMA store of the staged dQ / dK / dV tiles (its own warp: nobody else ever waits for a store to drain) =====
+        if (elect_one()) {
+            for (int64_t it = 0; it < n_items; ++it) {
+                const int64_t tile = blockIdx.x + (it / g.H) * gridDim.x; const int h = (int)(it % g.H);
+                const int row0 = (int)(tile * TC_ROWS);
+                mbar_wait(&bars->stg_full, (uint32_t)it & 1);
+                TCB_T(it, 7);
+                tma_store_2d(&tma_dqkv, stg_s, h * 64, row0);
+                tma_store_2d(&tma_dqkv, stg_s + TC_TILE, I + h * 64, row0);
+                tma_store_2d(&tma_dqkv, stg_s + 2 * TC_TILE, 2 * I + h * 64, row0);
+                tma_store_commit();
+                tma_store_wait_read();
+                TCB_T(it, 8);
+                mbar_arrive(&bars->stg_free);
+            }
+        }
+    } else if (warp < 16) {
+        // ===== two softmax + epilogue groups of 8 warps (ping-pong over items).  Within a group, thread (r, half) owns
+        // row r of the tile (query row in the softmax, key / query row in the epilogue) and 32 of its 64 columns. =====
+        const int grp = warp >> 3, wl = warp & 7, half = wl >> 2;
+        const int r = (wl & 3) * 32 + (threadIdx.x & 31);
+        const int blk = r >> 6;
+        const int st = grp;
+        const int c0 = half * 32;
+        const float sl2 = g.scale * 1.4426950408889634f;
+        const uint32_t lane_base = (uint32_t)((wl & 3) * 32) << 16;
+        const uint32_t swz = (uint32_t)(r & 7);
+        const bool full_blocks = g.N == 64;               // every row attends to its whole 64-key block (the spatial stack)
+        const uint64_t seed = drop.seed + (drop.seed_dev ? __ldg(drop.seed_dev) : 0ull);
+        const uint32_t t16 = drop.thresh >> 16;
+        float* my_part = dpart + (grp * 2 + half) * 128 + r;
+        const float* other_part = dpart + (grp * 2 + (half ^ 1)) * 128 + r;
+        int64_t cur_tile = -1, grow = -1; int klo = 0, khi = 0;
+        for (int64_t it = grp; it < n_items; it += 2) {
+            const uint32_t ph = (uint32_t)(it >> 1) & 1;
+            const int64_t tile = blockIdx.x + (it / g.H) * gridDim.x; const int h = (int)(it % g.H);
+            if (tile != cur_tile) {
+                cur_tile = tile;
+                grow = tc_row(g, tile, r, klo);
+                khi = grow >= 0 ? klo + g.N : 0;
+            }
+            const float L = grow >= 0 ? __ldg(lse + grow * g.H + h) * 1.4426950408889634f : 0.f;
+            // dropout pair index of (row, column pair jj): tile_pair_base_tc + (r & 63) * 32 + jj  -- split into the hash's 32-bit halves
+            const uint64_t hidx = tile_pair_base_tc(g, tile * 2 + blk, h) + (uint64_t)((r & 63) * 32 + (c0 >> 1));
+            const uint32_t hash_lo = (uint32_t)hidx + (uint32_t)(seed >> 32);
+            const uint32_t hash_hi = ((uint32_t)(hidx >> 32) * 0x85EBCA77u) ^ (uint32_t)seed ^ (drop.site * 0xC2B2AE3Du);
+            mbar_wait(&bars->s_full[st], ph);
+            if (r == 0 && half == 0) TCB_T(it, 2);
+            tc_fence_after();
+            float p[32], q[32];
+            {
+                uint32_t a[32], b[32];
+                const uint32_t scol = tmem_base + lane_base + st * 256 + blk * 64 + c0;
+                tmem_ld_32x32(scol, a);
+                tmem_ld_32x32(scol + 128, b);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { p[j] = __uint_as_float(a[j]); q[j] = __uint_as_float(b[j]); }
+            }
+            if (r == 0 && half == 0) TCB_T(it, 3);
+            uint32_t pfp[16], dsp[16];
+            float D;
+            if (drop.on()) {
+                if (full_blocks) D = tcb_softmax_pass1<true, true>(p, q, pfp, sl2, L, g.scale, c0, klo, khi, hash_lo, hash_hi, t16, drop.scale);
+                else D = tcb_softmax_pass1<false, true>(p, q, pfp, sl2, L, g.scale, c0, klo, khi, hash_lo, hash_hi, t16, drop.scale);
+            } else {
+                if (full_blocks) D = tcb_softmax_pass1<true, false>(p, q, pfp, sl2, L, g.scale, c0, klo, khi, hash_lo, hash_hi, t16, drop.scale);
+                else D = tcb_softmax_pass1<false, false>(p, q, pfp, sl2, L, g.scale, c0, klo, khi, hash_lo, hash_hi, t16, drop.scale);
+            }
+            *my_part = D;
+            asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory");
+            D += *other_part;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dsp[j] = pack_bf(p[2 * j] * (q[2 * j] - D), p[2 * j + 1] * (q[2 * j + 1] - D));
+            // everything above overlaps the previous item's dV / dK / dQ MMAs; the single P~ / dS buffer is free once they completed
+            if (it > 0) mbar_wait(&bars->pds_free, (uint32_t)(it - 1) & 1);
+            uint8_t* prow = p_s + (size_t)blk * TCB_CHUNK + r * 128;
+#pragma unroll
+            for (int pc = 0; pc < 4; ++pc) {
+                const uint32_t off = ((uint32_t)(half * 4 + pc) ^ swz) << 4;
+                *reinterpret_cast<uint4*>(prow + off) = make_uint4(pfp[pc * 4], pfp[pc * 4 + 1], pfp[pc * 4 + 2], pfp[pc * 4 + 3]);
+                *reinterpret_cast<uint4*>(prow + TCB_PD + off) = make_uint4(dsp[pc * 4], dsp[pc * 4 + 1], dsp[pc * 4 + 2], dsp[pc * 4 + 3]);
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(&bars->p_full);
+            if (r == 0 && half == 0) TCB_T(it, 4);
+            // ---- epilogue: dQ / dK / dV rows (fp32, TMEM) -> bf16 -> staging tiles -> TMA store ----
+            mbar_wait(&bars->o_full[st], ph);
+            if (it > 0) mbar_wait(&bars->stg_free, (uint32_t)(it - 1) & 1);   // the previous item's stores have read the staging tiles
+            if (r == 0 && half == 0) TCB_T(it, 6);
+            tc_fence_after();
+            uint8_t* stage = stg_s;
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {                       // TMEM columns: dV at +0, dK at +64, dQ at +128 -> tiles V, K, Q
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + lane_base + st * 256 + m * 64 + c0, v);
+                tmem_ld_wait();
+                uint8_t* trow = stage + (size_t)(2 - m) * TC_TILE + r * 128;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    *reinterpret_cast<uint4*>(trow + (((uint32_t)(half * 4 + c) ^ swz) << 4)) =
+                        make_uint4(pack_bf(__uint_as_float(v[c * 8]), __uint_as_float(v[c * 8 + 1])), pack_bf(__uint_as_float(v[c * 8 + 2]), __uint_as_float(v[c * 8 + 3])),
+                                   pack_bf(__uint_as_float(v[c * 8 + 4]), __uint_as_float(v[c * 8 + 5])), pack_bf(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7])));
+            }
+            tc_fence_before();
+            mbar_arrive(&bars->tmem_free[st]);
+            fence_proxy_async();
+            mbar_arrive(&bars->stg_full);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 16) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+#undef TCB_T
+}
+
+bool attention_tc_contiguous(const AttnGeom& g) {
+    return g.tiles == 1 && g.inner == 1 && 64 % g.N == 0 && ((g.groups + 1) / 2) * TC_ROWS < (int64_t)2147483647;
+}
+
+int attention_bwd_tc(const AttnGeom& g, const bf16* qkv, const float* lse, const bf16* d_out, bf16* d_qkv, Drop drop, cudaStream_t st) {
+    MSST_REQUIRE(attention_tc_contiguous(g), "attention_bwd_tc: needs tiles of 128 consecutive rows (inner == 1, N | 64)");
+    const int64_t n_tiles = (g.groups + 1) / 2;
+    static PerDeviceOnce once;
+    if (once.first()) MSST_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcbSmem));
+    const int64_t R = g.n_seq * g.N, I = (int64_t)g.H * 64;
+    CUtensorMap t_qkv, t_do, t_dqkv;
+    if (int rc = make_tmap_bf16(&t_qkv, qkv, R, 3 * I, 3 * I, TC_ROWS)) return rc;
+    if (int rc = make_tmap_bf16(&t_do, d_out, R, I, I, TC_ROWS)) return rc;
+    if (int rc = make_tmap_bf16(&t_dqkv, d_qkv, R, 3 * I, 3 * I, TC_ROWS)) return rc;
+    const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
+    static long long* dbg = nullptr;
+    static int dbg_on = -1;
+    if (dbg_on < 0) { const char* e = getenv("MSST_ATTN_DBG"); dbg_on = e ? atoi(e) : 0; if (dbg_on) { cudaMalloc(&dbg, 32 * 16 * 8); } }
+    if (dbg_on) cudaMemsetAsync(dbg, 0, 32 * 16 * 8, st);
+    attn_bwd_tc_kernel<<<grid, TCB_THREADS, kTcbSmem, st>>>(t_qkv, t_do, t_dqkv, g, lse, drop, n_tiles, dbg);
+    MSST_LAUNCH_CHECK();
+    if (dbg_on) {
+        static int printed = 0;
+        if (++printed == dbg_on) {
+            long long h[32 * 16];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+            long long t0 = h[0];
+            printf("item: load_issue p1_issue sfull_seen ld_done pfull_arr p2_issue ofull_seen epi_done store_read (clks rel. to first load)\n");
+            for (int i = 0; i < 24; ++i) { printf("%2d:", i); for (int k = 0; k < 9; ++k) printf(" %7lld", h[i * 16 + k] ? h[i * 16 + k] - t0 : -1); printf("\n"); }
+            fflush(stdout);
+        }
+    }
     return MSST_OK;
 }
 

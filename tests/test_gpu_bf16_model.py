@@ -155,3 +155,39 @@ print("TC_OK")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "TC_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_tcgen05_attention_backward_matches_mma_sync_kernel():
+    """The default backward for contiguous tiles (spatial stack) is the tcgen05 / TMEM kernel (attention_tc.cu); the mma.sync
+    kernel (MSST_ATTN_BWD_TC=0, also the spectral-stack kernel) must give the same gradients -- with dropout on, which only
+    holds if both regenerate exactly the forward's mask."""
+    import os, subprocess, sys, tempfile
+    code = r'''
+import sys, torch
+sys.path.insert(0, ".")
+from maskedsst_b200 import ops
+torch.manual_seed(3)
+out = {}
+for k, (n_seq, N, H, p) in enumerate([(40, 64, 8, 0.3), (33, 64, 3, 0.0), (9, 32, 2, 0.2), (7, 16, 8, 0.1), (300, 64, 8, 0.1)]):
+    R, I = n_seq * N, H * 64
+    qkv = torch.randn(R, 3 * I).bfloat16().cuda().requires_grad_(True)
+    w = torch.randn(R, I).bfloat16().cuda()
+    o = ops.attention(qkv, n_seq=n_seq, N=N, heads=H, dim_head=64, drop_p=p, seed=11, site=3)
+    (o.float() * w.float()).sum().backward()
+    out[k] = qkv.grad.float().cpu()
+torch.save(out, sys.argv[1])
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    with tempfile.TemporaryDirectory() as td:
+        for flag in ("1", "0"):
+            path = os.path.join(td, f"g{flag}.pt")
+            r = subprocess.run([sys.executable, "-c", code, path], cwd=root, env=dict(os.environ, MSST_ATTN_BWD_TC=flag),
+                               capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stdout + r.stderr
+            res[flag] = torch.load(path)
+    for k in res["1"]:
+        a, b = res["1"][k], res["0"][k]
+        assert torch.isfinite(a).all()
+        # same mask + same bf16 roundings of P~ / dS: only the fp32 accumulation order differs
+        assert rel_l2(a, b) < 2e-3, (k, rel_l2(a, b))
