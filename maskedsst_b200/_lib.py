@@ -96,10 +96,12 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    from . import build as _build
-    _build.build()   # no-op when the in-tree library is up to date (source digest) or nvcc is absent
+    path = os.environ.get("MSST_LIB", LIB_PATH)   # A/B runs of two builds of the library (profiling only)
+    if path == LIB_PATH:
+        from . import build as _build
+        _build.build()   # no-op when the in-tree library is up to date (source digest) or nvcc is absent
     try:
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(path)
     except OSError as e:   # fail loudly: there is no CPU / eager fallback
         raise RuntimeError(f"maskedsst_b200: cannot load {LIB_PATH}: {e}. Run `python -m maskedsst_b200.build`.") from e
     for name, (res, args) in SIGNATURES.items():

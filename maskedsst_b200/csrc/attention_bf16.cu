@@ -135,7 +135,7 @@ __device__ __forceinline__ void heads_setup(const AttnGeom& g, int64_t group, He
     if (threadIdx.x < TS) {
         int64_t seq; int pos;
         const bool ok = slot_to(g, group, 0, threadIdx.x, seq, pos);
-        hs.seq[threadIdx.x] = ok ? (int)(seq - group * g.G) : -1;
+        hs.seq[threadIdx.x] = ok ? (int)(seq - group_seq0(g, group)) : -1;
         hs.pos[threadIdx.x] = pos;
         hs.row[threadIdx.x] = ok ? row_of(g, seq, pos) : -1;
     }
@@ -626,7 +626,7 @@ int attention_fwd_bf16(const msst_attn_dims* d, const bf16* qkv, bf16* out, floa
     if (g.tiles == 1) {
         static int use_tc = -1;
         if (use_tc < 0) { const char* e = getenv("MSST_ATTN_TC"); use_tc = e ? atoi(e) : 0; }
-        if (use_tc) return attention_fwd_tc(g, qkv, out, lse, drop, st);   // tcgen05 / TMEM forward (attention_tc.cu)
+        if (use_tc && g.gpb == 0) return attention_fwd_tc(g, qkv, out, lse, drop, st);   // tcgen05 / TMEM forward (attention_tc.cu; sequence-major packing only)
     }
     if (g.tiles == 1) {   // N <= 64: head-looping, cp.async double-buffered kernel
         static PerDeviceOnce attr_set;
@@ -657,7 +657,7 @@ int attention_bwd_bf16(const msst_attn_dims* d, const bf16* qkv, const bf16* out
     if (g.n_seq == 0) return MSST_OK;
     const Drop drop = make_drop(d->drop_p, d->seed, d->site, d->seed_dev);
     const dim3 grid((unsigned)(g.groups * g.tiles), g.H);
-    if (attention_tc_contiguous(g)) {   // default: tcgen05 / TMEM backward (attention_tc.cu, 1.5x the mma.sync kernel); MSST_ATTN_BWD_TC=0 selects mma.sync
+    if (attention_bwd_tc_supported(g)) {   // default: tcgen05 / TMEM backward (attention_tc.cu, 1.5x the mma.sync kernel); MSST_ATTN_BWD_TC=0 selects mma.sync
         static int use_tc = -1;
         if (use_tc < 0) { const char* e = getenv("MSST_ATTN_BWD_TC"); use_tc = e ? atoi(e) : 1; }
         if (use_tc) return attention_bwd_tc(g, qkv, lse, d_out, d_qkv, drop, st);

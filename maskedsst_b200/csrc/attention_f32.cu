@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(AT) attn_fwd_kernel(AttnGeom g, const float* _
     if (threadIdx.x < TS) {
         int64_t seq; int pos;
         const bool ok = slot_to(g, group, qtile, threadIdx.x, seq, pos);
-        qseq[threadIdx.x] = ok ? (int)(seq - group * g.G) : -1;
+        qseq[threadIdx.x] = ok ? (int)(seq - group_seq0(g, group)) : -1;
         qpos[threadIdx.x] = pos;
         m_run[threadIdx.x] = -INFINITY; l_run[threadIdx.x] = 0.f;
     }
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(AT) attn_fwd_kernel(AttnGeom g, const float* _
         if (threadIdx.x < TS) {
             int64_t seq; int pos;
             const bool ok = slot_to(g, group, kt, threadIdx.x, seq, pos);
-            kseq[threadIdx.x] = ok ? (int)(seq - group * g.G) : -2;
+            kseq[threadIdx.x] = ok ? (int)(seq - group_seq0(g, group)) : -2;
             kpos[threadIdx.x] = pos;
         }
         __syncthreads();
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(AT) attn_fwd_kernel(AttnGeom g, const float* _
             }
             const float rs = warp_sum(p0 + p1);
             if (drop.on() && qseq[r] >= 0) {
-                const int64_t seq = group * g.G + qseq[r];
+                const int64_t seq = group_seq0(g, group) + qseq[r];
                 const uint64_t e0 = (((uint64_t)seq * g.H + h) * g.N + qpos[r]) * g.N;
                 if (kseq[lane] == qseq[r]) p0 *= drop_factor(drop, e0 + kpos[lane]);
                 if (kseq[lane + 32] == qseq[r]) p1 *= drop_factor(drop, e0 + kpos[lane + 32]);
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(AT) attn_fwd_kernel(AttnGeom g, const float* _
     for (int i = 0; i < 4; ++i) {
         const int r = ty * 4 + i;
         if (qseq[r] < 0) continue;
-        const int64_t row = row_of(g, group * g.G + qseq[r], qpos[r]);
+        const int64_t row = row_of(g, group_seq0(g, group) + qseq[r], qpos[r]);
         const float inv = 1.f / l_run[r];
 #pragma unroll
         for (int cc = 0; cc < CW; ++cc) out[row * I + h * DH + tx * CW + cc] = acc[i][cc] * inv;
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(AT) attn_bwd_kernel(AttnGeom g, const float* _
     if (threadIdx.x < TS) {
         int64_t seq; int pos;
         const bool ok = slot_to(g, group, ktile, threadIdx.x, seq, pos);
-        kseq[threadIdx.x] = ok ? (int)(seq - group * g.G) : -2;
+        kseq[threadIdx.x] = ok ? (int)(seq - group_seq0(g, group)) : -2;
         kpos[threadIdx.x] = pos;
     }
     float dK[4][CW] = {}, dV[4][CW] = {};
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(AT) attn_bwd_kernel(AttnGeom g, const float* _
         if (threadIdx.x < TS) {
             int64_t seq; int pos;
             const bool ok = slot_to(g, group, qt, threadIdx.x, seq, pos);
-            qseq[threadIdx.x] = ok ? (int)(seq - group * g.G) : -1;
+            qseq[threadIdx.x] = ok ? (int)(seq - group_seq0(g, group)) : -1;
             qpos[threadIdx.x] = pos;
         }
         __syncthreads();
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(AT) attn_bwd_kernel(AttnGeom g, const float* _
             const int r = warp * 8 + k;
             float dsum = 0.f, l = 0.f;
             if (qseq[r] >= 0) {
-                const int64_t row = row_of(g, group * g.G + qseq[r], qpos[r]);
+                const int64_t row = row_of(g, group_seq0(g, group) + qseq[r], qpos[r]);
                 for (int d = lane; d < DH; d += 32) dsum += dOs[r][d] * out[row * I + h * DH + d];
                 l = lse[row * g.H + h];
             }
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(AT) attn_bwd_kernel(AttnGeom g, const float* _
                 float p = ok ? expf(s[i][j] * g.scale - lse_s[r]) : 0.f;
                 float f = 1.f;
                 if (drop.on() && ok) {
-                    const int64_t seq = group * g.G + qseq[r];
+                    const int64_t seq = group_seq0(g, group) + qseq[r];
                     f = drop_factor(drop, (((uint64_t)seq * g.H + h) * g.N + qpos[r]) * g.N + kpos[cidx]);
                 }
                 Ss[r][cidx] = p * f;
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(AT) attn_bwd_kernel(AttnGeom g, const float* _
         for (int i = 0; i < 4; ++i) {
             const int r = ty * 4 + i;
             if (qseq[r] < 0) continue;
-            const int64_t row = row_of(g, group * g.G + qseq[r], qpos[r]);
+            const int64_t row = row_of(g, group_seq0(g, group) + qseq[r], qpos[r]);
 #pragma unroll
             for (int cc = 0; cc < CW; ++cc) {
                 float* dst = d_qkv + row * ld + h * DH + tx * CW + cc;
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(AT) attn_bwd_kernel(AttnGeom g, const float* _
     for (int j = 0; j < 4; ++j) {
         const int r = ty * 4 + j;
         if (kseq[r] < 0) continue;
-        const int64_t row = row_of(g, group * g.G + kseq[r], kpos[r]);
+        const int64_t row = row_of(g, group_seq0(g, group) + kseq[r], kpos[r]);
 #pragma unroll
         for (int cc = 0; cc < CW; ++cc) {
             d_qkv[row * ld + I + h * DH + tx * CW + cc] = dK[j][cc];

@@ -24,6 +24,7 @@ namespace msst {
 using namespace ptx;
 typedef __nv_bfloat16 bf16;
 int make_tmap_bf16(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);   // gemm_bf16.cu
+int make_tmap_bf16_4d(CUtensorMap* m, const void* base, const int64_t dims[4], const int64_t strides[3], int box1, int box2);
 
 constexpr int TC_ROWS = 128;
 constexpr int TC_THREADS = 384;            // warps 0-3 softmax group A (even items), 4-5 producers, 6 MMA, 7 TMEM alloc, 8-11 softmax group B
@@ -296,7 +297,9 @@ int attention_fwd_tc(const AttnGeom& g, const bf16* qkv, bf16* out, float* lse, 
 }
 
 // =========================================================================================================
-// Backward on tcgen05 / TMEM (N <= 64, tiles whose 128 slots are 128 consecutive rows: the spatial stack).
+// Backward on tcgen05 / TMEM for all packed short-sequence shapes (N <= 64): both the spatial and the spectral stack.
+// A tile = two 64-slot groups; each group's rows arrive as ONE 4-D TMA box per operand (attn_geom.cuh: the group's slots are
+// runs of consecutive rows in the (col, s, pos, blk) view of the activation matrix), so strided sequences cost nothing extra.
 //
 // Per (128-slot tile, head) item, all five contractions run on the tensor cores from one elected thread:
 //   S  = Q K^T, dP = dO V^T            -> TMEM [128 x 128] fp32 each (K-major operands straight from the TMA tiles)
@@ -311,7 +314,10 @@ int attention_fwd_tc(const AttnGeom& g, const bf16* qkv, bf16* out, float* lse, 
 // HBM-bound: (4 + 3) * 128 B per (slot, head).
 // =========================================================================================================
 struct alignas(8) TcbBars {
-    uint64_t full[2], kv_empty[2], s_full[2], o_full[2], tmem_free[2], p_full, pds_free, stg_free, stg_full;
+    uint64_t full[2], kv_empty[2], s_full[2], o_full[2], tmem_free[2];
+    // events of the single P~/dS buffer and the single staging buffer, one barrier per item parity: with ONE barrier a waiter
+    // that runs two items ahead would take the completion of item i - 2 for that of item i (same phase parity)
+    uint64_t p_full[2], pds_free[2], stg_free[2], stg_full[2];
     uint32_t tmem_base;
 };
 constexpr int TCB_THREADS = 608;           // warps 0-7 softmax group A, 8-15 group B, 16 TMA producer (+ TMEM alloc), 17 MMA issuer, 18 TMA store
@@ -319,7 +325,7 @@ constexpr int TCB_THREADS = 608;           // warps 0-7 softmax group A, 8-15 gr
 //   V0 = [C0: rows 0-63, keys 0-63][Z: 8 KB of zeros]      V1 = V0 + 8 KB = [Z][C1: rows 64-127, keys 64-127]
 // (24 KB instead of 32 KB: both chunks share the zero block), so the chunk stride of the UMMA descriptors is 8 KB.
 constexpr uint32_t TCB_CHUNK = 8192, TCB_PD = 3 * 8192;
-constexpr int TCB_PREFETCH = 2;            // items ahead whose operand boxes are prefetched into L2
+constexpr int TCB_PREFETCH = 1;            // items ahead whose operand boxes are prefetched into L2 (MSST_ATTN_PF overrides; >= 3 thrashes)
 // smem: [2 stages][Q, K, V, dO][16 KB] | P~ (24 KB) | dS (24 KB) | output staging dQ, dK, dV [16 KB] | partial row sums | barriers
 // = 226.1 KB: no slack for re-aligning the base, the kernel checks that the dynamic window starts 1 KB aligned
 constexpr size_t kTcbSmem = 2 * 4 * TC_TILE + 2 * TCB_PD + 3 * TC_TILE + 2 * 2 * 128 * sizeof(float) + sizeof(TcbBars);
@@ -333,8 +339,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // One thread's share of an item: 32 of the 64 diagonal-block columns of row r.  p[] holds S, q[] holds dP on entry.
 // Packs P~ (bf16 pairs) into pfp[], returns the partial row sum D; leaves p = P * scale and q = f * dP for the second pass.
 template <bool FULL, bool DROP>
-__device__ __forceinline__ float tcb_softmax_pass1(float (&p)[32], float (&q)[32], uint32_t (&pfp)[16], float sl2, float L, float scale, int c0,
-                                                   int klo, int khi, uint32_t hash_lo, uint32_t hash_hi, uint32_t t16, float dscale) {
+__device__ __forceinline__ float tcb_softmax_pass1(float (&p)[32], float (&q)[32], uint32_t (&pfp)[16], float sl2, float L, float scale,
+                                                   uint32_t vmask, uint32_t hash_lo, uint32_t hash_hi, uint32_t t16, float dscale) {
     float D = 0.f;
 #pragma unroll
     for (int pc = 0; pc < 4; ++pc) {
@@ -350,9 +356,9 @@ __device__ __forceinline__ float tcb_softmax_pass1(float (&p)[32], float (&q)[32
                 f1 = (x >> 16) >= t16 ? dscale : 0.f;
             }
             float p0 = ex2_approx(fmaf(p[j], sl2, -L)), p1 = ex2_approx(fmaf(p[j + 1], sl2, -L));
-            if (!FULL) {
-                p0 = (c0 + j >= klo && c0 + j < khi) ? p0 : 0.f;
-                p1 = (c0 + j + 1 >= klo && c0 + j + 1 < khi) ? p1 : 0.f;
+            if (!FULL) {   // vmask bit j: column j of this thread is a key of the row's own sequence
+                p0 = (vmask >> j) & 1u ? p0 : 0.f;
+                p1 = (vmask >> (j + 1)) & 1u ? p1 : 0.f;
             }
             pf[e] = DROP ? p0 * f0 : p0; pf[e + 1] = DROP ? p1 * f1 : p1;
             D = fmaf(pf[e], q[j], D); D = fmaf(pf[e + 1], q[j + 1], D);
@@ -365,9 +371,16 @@ __device__ __forceinline__ float tcb_softmax_pass1(float (&p)[32], float (&q)[32
     return D;
 }
 
+// TMA coordinates (c1, c2, c3) of a slot group's box (see attention_bwd_tc for the two tensor views); a group past the end maps
+// to an out-of-range coordinate: zero-filled on load, clipped on store
+__device__ __forceinline__ void tcb_group_coords(const AttnGeom& g, int64_t group, int& c1, int& c2, int& c3) {
+    if (g.gpb == 0) { c1 = 0; c2 = (int)(group * g.G); c3 = 0; }
+    else { c1 = (int)(group % g.gpb) * g.G; c2 = 0; c3 = (int)(group / g.gpb); }
+}
+
 __global__ void __launch_bounds__(TCB_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
-                   const __grid_constant__ CUtensorMap tma_dqkv, AttnGeom g, const float* __restrict__ lse, Drop drop, int64_t n_tiles, long long* dbg) {
+                   const __grid_constant__ CUtensorMap tma_dqkv, AttnGeom g, const float* __restrict__ lse, Drop drop, int64_t n_tiles, int nbox, int pf_dist, long long* dbg) {
 #define TCB_T(it, slot) do { if (dbg && blockIdx.x == 0 && (it) < 32) dbg[(it) * 16 + (slot)] = clock64(); } while (0)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
@@ -385,15 +398,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
             mbar_init(&bars->full[s], 1); mbar_init(&bars->kv_empty[s], 1); mbar_init(&bars->s_full[s], 1);
             mbar_init(&bars->o_full[s], 1); mbar_init(&bars->tmem_free[s], 256);
         }
-        mbar_init(&bars->p_full, 256); mbar_init(&bars->pds_free, 1); mbar_init(&bars->stg_free, 1); mbar_init(&bars->stg_full, 256);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bars->p_full[s], 256); mbar_init(&bars->pds_free[s], 1); mbar_init(&bars->stg_free[s], 1); mbar_init(&bars->stg_full[s], 256);
+        }
         fence_barrier_init();
     }
     if (warp == 16) {
         tmem_alloc(&bars->tmem_base, 512);
         if (elect_one()) { prefetch_tmap(&tma_qkv); prefetch_tmap(&tma_do); prefetch_tmap(&tma_dqkv); }
     }
-    // the off-diagonal halves of the P~ / dS tiles are never written afterwards
-    for (uint32_t i = threadIdx.x; i < 2 * TCB_PD / 16; i += TCB_THREADS) reinterpret_cast<uint4*>(p_s)[i] = make_uint4(0, 0, 0, 0);
+    // zero once: the operand rows a group's box does not cover (slots G*N .. 63) and the shared zero blocks of the P~ / dS tiles
+    for (uint32_t i = threadIdx.x; i < (2 * 4 * TC_TILE + 2 * TCB_PD) / 16; i += TCB_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -403,6 +418,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
 
     const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
     const int64_t n_items = my_tiles * g.H;
+    // nbox == 2: one box per slot group; nbox == 1: the tile's 128 slots are 128 consecutive rows (inner == 1, N | 64) -> one box
+    const uint32_t box_bytes = (uint32_t)(g.G * g.N) * 128u * (nbox == 1 ? 2u : 1u);
 
     if (warp == 16) {
         // ===== TMA producer =====
@@ -413,19 +430,41 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
                 mbar_wait(&bars->kv_empty[st], ph ^ 1);
                 TCB_T(it, 0);
                 uint8_t* base = op_s + (size_t)st * 4 * TC_TILE;
-                const int row0 = (int)(tile * TC_ROWS);
-                mbar_arrive_expect_tx(&bars->full[st], 4 * TC_TILE);
-                tma_load_2d(base, &tma_qkv, &bars->full[st], h * 64, row0);
-                tma_load_2d(base + TC_TILE, &tma_qkv, &bars->full[st], I + h * 64, row0);
-                tma_load_2d(base + 2 * TC_TILE, &tma_qkv, &bars->full[st], 2 * I + h * 64, row0);
-                tma_load_2d(base + 3 * TC_TILE, &tma_do, &bars->full[st], h * 64, row0);
-                if (it + TCB_PREFETCH < n_items) {   // pull a later item's operand boxes into L2 now (its smem stage is still busy)
-                    const int64_t it2 = it + TCB_PREFETCH;
-                    const int row2 = (int)((blockIdx.x + (it2 / g.H) * gridDim.x) * TC_ROWS); const int h2 = (int)(it2 % g.H);
-                    tma_prefetch_l2_2d(&tma_qkv, h2 * 64, row2);
-                    tma_prefetch_l2_2d(&tma_qkv, I + h2 * 64, row2);
-                    tma_prefetch_l2_2d(&tma_qkv, 2 * I + h2 * 64, row2);
-                    tma_prefetch_l2_2d(&tma_do, h2 * 64, row2);
+                mbar_arrive_expect_tx(&bars->full[st], 4 * nbox * box_bytes);
+                if (nbox == 1) {                                 // 128 consecutive rows: plain 2-D boxes
+                    const int row0 = (int)(tile * TC_ROWS);
+                    tma_load_2d(base, &tma_qkv, &bars->full[st], h * 64, row0);
+                    tma_load_2d(base + TC_TILE, &tma_qkv, &bars->full[st], I + h * 64, row0);
+                    tma_load_2d(base + 2 * TC_TILE, &tma_qkv, &bars->full[st], 2 * I + h * 64, row0);
+                    tma_load_2d(base + 3 * TC_TILE, &tma_do, &bars->full[st], h * 64, row0);
+                } else
+                for (int gi = 0; gi < nbox; ++gi) {              // the tile's two slot groups -> rows 0.. and 64.. of every operand tile
+                    int c1, c2, c3;
+                    tcb_group_coords(g, tile * 2 + gi, c1, c2, c3);
+                    uint8_t* dst = base + gi * 64 * 128;
+                    tma_load_4d(dst, &tma_qkv, &bars->full[st], h * 64, c1, c2, c3);
+                    tma_load_4d(dst + TC_TILE, &tma_qkv, &bars->full[st], I + h * 64, c1, c2, c3);
+                    tma_load_4d(dst + 2 * TC_TILE, &tma_qkv, &bars->full[st], 2 * I + h * 64, c1, c2, c3);
+                    tma_load_4d(dst + 3 * TC_TILE, &tma_do, &bars->full[st], h * 64, c1, c2, c3);
+                }
+                if (pf_dist > 0 && it + pf_dist < n_items) {   // pull a later item's operand boxes into L2 now (its smem stage is still busy)
+                    const int64_t it2 = it + pf_dist;
+                    const int64_t tile2 = blockIdx.x + (it2 / g.H) * gridDim.x; const int h2 = (int)(it2 % g.H);
+                    if (nbox == 1) {
+                        const int row2 = (int)(tile2 * TC_ROWS);
+                        tma_prefetch_l2_2d(&tma_qkv, h2 * 64, row2);
+                        tma_prefetch_l2_2d(&tma_qkv, I + h2 * 64, row2);
+                        tma_prefetch_l2_2d(&tma_qkv, 2 * I + h2 * 64, row2);
+                        tma_prefetch_l2_2d(&tma_do, h2 * 64, row2);
+                    } else
+                    for (int gi = 0; gi < nbox; ++gi) {
+                        int c1, c2, c3;
+                        tcb_group_coords(g, tile2 * 2 + gi, c1, c2, c3);
+                        tma_prefetch_l2_4d(&tma_qkv, h2 * 64, c1, c2, c3);
+                        tma_prefetch_l2_4d(&tma_qkv, I + h2 * 64, c1, c2, c3);
+                        tma_prefetch_l2_4d(&tma_qkv, 2 * I + h2 * 64, c1, c2, c3);
+                        tma_prefetch_l2_4d(&tma_do, h2 * 64, c1, c2, c3);
+                    }
                 }
             }
         }
@@ -452,7 +491,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
                         ++next_s;
                     }
                 }
-                if (next_p < next_s && mbar_try_wait(&bars->p_full, (uint32_t)next_p & 1)) {   // P~ and dS written (generic proxy + the writers' fence)
+                if (next_p < next_s && mbar_try_wait(&bars->p_full[next_p & 1], (uint32_t)(next_p >> 1) & 1)) {   // P~ and dS written (generic proxy + the writers' fence)
                     const int st = (int)(next_p & 1);
                     TCB_T(next_p, 5);
                     const uint32_t qb = smem_u32(op_s + (size_t)st * 4 * TC_TILE);
@@ -471,7 +510,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
                         umma_bf16(d0 + 128, a, b_k + (uint64_t)(k * 128), idesc_q, k != 0);
                     }
                     umma_commit(&bars->o_full[st]);
-                    umma_commit(&bars->pds_free);
+                    umma_commit(&bars->pds_free[st]);
                     umma_commit(&bars->kv_empty[st]);          // Q, K, V, dO of this stage are dead: the next loads may start
                     ++next_p;
                 }
@@ -482,16 +521,26 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
         if (elect_one()) {
             for (int64_t it = 0; it < n_items; ++it) {
                 const int64_t tile = blockIdx.x + (it / g.H) * gridDim.x; const int h = (int)(it % g.H);
-                const int row0 = (int)(tile * TC_ROWS);
-                mbar_wait(&bars->stg_full, (uint32_t)it & 1);
+                mbar_wait(&bars->stg_full[it & 1], (uint32_t)(it >> 1) & 1);
                 TCB_T(it, 7);
-                tma_store_2d(&tma_dqkv, stg_s, h * 64, row0);
-                tma_store_2d(&tma_dqkv, stg_s + TC_TILE, I + h * 64, row0);
-                tma_store_2d(&tma_dqkv, stg_s + 2 * TC_TILE, 2 * I + h * 64, row0);
+                if (nbox == 1) {
+                    const int row0 = (int)(tile * TC_ROWS);
+                    tma_store_2d(&tma_dqkv, stg_s, h * 64, row0);
+                    tma_store_2d(&tma_dqkv, stg_s + TC_TILE, I + h * 64, row0);
+                    tma_store_2d(&tma_dqkv, stg_s + 2 * TC_TILE, 2 * I + h * 64, row0);
+                } else
+                for (int gi = 0; gi < nbox; ++gi) {
+                    int c1, c2, c3;
+                    tcb_group_coords(g, tile * 2 + gi, c1, c2, c3);
+                    const uint8_t* src = stg_s + gi * 64 * 128;
+                    tma_store_4d(&tma_dqkv, src, h * 64, c1, c2, c3);
+                    tma_store_4d(&tma_dqkv, src + TC_TILE, I + h * 64, c1, c2, c3);
+                    tma_store_4d(&tma_dqkv, src + 2 * TC_TILE, 2 * I + h * 64, c1, c2, c3);
+                }
                 tma_store_commit();
                 tma_store_wait_read();
                 TCB_T(it, 8);
-                mbar_arrive(&bars->stg_free);
+                mbar_arrive(&bars->stg_free[it & 1]);
             }
         }
     } else if (warp < 16) {
@@ -505,19 +554,33 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
         const float sl2 = g.scale * 1.4426950408889634f;
         const uint32_t lane_base = (uint32_t)((wl & 3) * 32) << 16;
         const uint32_t swz = (uint32_t)(r & 7);
-        const bool full_blocks = g.N == 64;               // every row attends to its whole 64-key block (the spatial stack)
+        const bool full_blocks = g.N == 64 && g.groups % 2 == 0;   // every row of every tile attends to its whole 64-key block (the spatial stack)
         const uint64_t seed = drop.seed + (drop.seed_dev ? __ldg(drop.seed_dev) : 0ull);
         const uint32_t t16 = drop.thresh >> 16;
         float* my_part = dpart + (grp * 2 + half) * 128 + r;
         const float* other_part = dpart + (grp * 2 + (half ^ 1)) * 128 + r;
-        int64_t cur_tile = -1, grow = -1; int klo = 0, khi = 0;
+        // which of this thread's 32 key columns belong to the sequence of slot (r & 63): sequence-major packing -> a run of N
+        // slots, position-major -> every G-th slot.  Pure slot geometry: the same for every tile.
+        uint32_t vmask_geom = 0;
+        {
+            const int slot = r & 63, used = g.G * g.N;
+            for (int j = 0; j < 32; ++j) {
+                const int c = c0 + j;
+                const bool same = g.gpb == 0 ? (c / g.N == slot / g.N) : (c % g.G == slot % g.G);
+                vmask_geom |= (uint32_t)(same && c < used && slot < used) << j;
+            }
+        }
+        int64_t cur_tile = -1, grow = -1; uint32_t vmask = 0;
         for (int64_t it = grp; it < n_items; it += 2) {
             const uint32_t ph = (uint32_t)(it >> 1) & 1;
             const int64_t tile = blockIdx.x + (it / g.H) * gridDim.x; const int h = (int)(it % g.H);
             if (tile != cur_tile) {
                 cur_tile = tile;
-                grow = tc_row(g, tile, r, klo);
-                khi = grow >= 0 ? klo + g.N : 0;
+                int64_t seq; int pos;
+                const int64_t group = tile * 2 + blk;
+                const bool ok = group < g.groups && slot_to(g, group, 0, r & 63, seq, pos);
+                grow = ok ? row_of(g, seq, pos) : -1;
+                vmask = ok ? vmask_geom : 0u;
             }
             const float L = grow >= 0 ? __ldg(lse + grow * g.H + h) * 1.4426950408889634f : 0.f;
             // dropout pair index of (row, column pair jj): tile_pair_base_tc + (r & 63) * 32 + jj  -- split into the hash's 32-bit halves
@@ -541,11 +604,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
             uint32_t pfp[16], dsp[16];
             float D;
             if (drop.on()) {
-                if (full_blocks) D = tcb_softmax_pass1<true, true>(p, q, pfp, sl2, L, g.scale, c0, klo, khi, hash_lo, hash_hi, t16, drop.scale);
-                else D = tcb_softmax_pass1<false, true>(p, q, pfp, sl2, L, g.scale, c0, klo, khi, hash_lo, hash_hi, t16, drop.scale);
+                if (full_blocks) D = tcb_softmax_pass1<true, true>(p, q, pfp, sl2, L, g.scale, vmask, hash_lo, hash_hi, t16, drop.scale);
+                else D = tcb_softmax_pass1<false, true>(p, q, pfp, sl2, L, g.scale, vmask, hash_lo, hash_hi, t16, drop.scale);
             } else {
-                if (full_blocks) D = tcb_softmax_pass1<true, false>(p, q, pfp, sl2, L, g.scale, c0, klo, khi, hash_lo, hash_hi, t16, drop.scale);
-                else D = tcb_softmax_pass1<false, false>(p, q, pfp, sl2, L, g.scale, c0, klo, khi, hash_lo, hash_hi, t16, drop.scale);
+                if (full_blocks) D = tcb_softmax_pass1<true, false>(p, q, pfp, sl2, L, g.scale, vmask, hash_lo, hash_hi, t16, drop.scale);
+                else D = tcb_softmax_pass1<false, false>(p, q, pfp, sl2, L, g.scale, vmask, hash_lo, hash_hi, t16, drop.scale);
             }
             *my_part = D;
             asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory");
@@ -553,7 +616,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
 #pragma unroll
             for (int j = 0; j < 16; ++j) dsp[j] = pack_bf(p[2 * j] * (q[2 * j] - D), p[2 * j + 1] * (q[2 * j + 1] - D));
             // everything above overlaps the previous item's dV / dK / dQ MMAs; the single P~ / dS buffer is free once they completed
-            if (it > 0) mbar_wait(&bars->pds_free, (uint32_t)(it - 1) & 1);
+            if (it > 0) mbar_wait(&bars->pds_free[(it - 1) & 1], (uint32_t)((it - 1) >> 1) & 1);
             uint8_t* prow = p_s + (size_t)blk * TCB_CHUNK + r * 128;
 #pragma unroll
             for (int pc = 0; pc < 4; ++pc) {
@@ -563,11 +626,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
             }
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(&bars->p_full);
+            mbar_arrive(&bars->p_full[st]);
             if (r == 0 && half == 0) TCB_T(it, 4);
             // ---- epilogue: dQ / dK / dV rows (fp32, TMEM) -> bf16 -> staging tiles -> TMA store ----
             mbar_wait(&bars->o_full[st], ph);
-            if (it > 0) mbar_wait(&bars->stg_free, (uint32_t)(it - 1) & 1);   // the previous item's stores have read the staging tiles
+            if (it > 0) mbar_wait(&bars->stg_free[(it - 1) & 1], (uint32_t)((it - 1) >> 1) & 1);   // the previous item's stores have read the staging tiles
             if (r == 0 && half == 0) TCB_T(it, 6);
             tc_fence_after();
             uint8_t* stage = stg_s;
@@ -586,7 +649,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
             tc_fence_before();
             mbar_arrive(&bars->tmem_free[st]);
             fence_proxy_async();
-            mbar_arrive(&bars->stg_full);
+            mbar_arrive(&bars->stg_full[st]);
         }
     }
     tc_fence_before();
@@ -595,26 +658,45 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
 #undef TCB_T
 }
 
-bool attention_tc_contiguous(const AttnGeom& g) {
-    return g.tiles == 1 && g.inner == 1 && 64 % g.N == 0 && ((g.groups + 1) / 2) * TC_ROWS < (int64_t)2147483647;
+bool attention_bwd_tc_supported(const AttnGeom& g) {
+    const int64_t n_blk = g.inner > 0 ? g.n_seq / g.inner : 0;
+    return g.tiles == 1 && g.groups > 0 && g.groups * g.G < (int64_t)2147483647 && n_blk < (int64_t)2147483647 &&
+           ((g.groups + 1) / 2) * g.H < ((int64_t)1 << 40);
+}
+
+// 4-D view of an activation matrix [R, cols] whose box {64, box1, box2, 1} is one slot group (attn_geom.cuh):
+//   inner == 1: (col, pos [N], seq [n_seq], 1)           box {64, N, G, 1}   -> slot = j * N + pos
+//   inner  > 1: (col, s [inner], pos [N], blk [n_seq/inner])  box {64, G, N, 1}   -> slot = pos * G + j
+static int tcb_tmap(CUtensorMap* m, const AttnGeom& g, const bf16* base, int64_t cols, int nbox) {
+    if (nbox == 1) return make_tmap_bf16(m, base, g.n_seq * g.N, cols, cols, TC_ROWS);   // contiguous tiles: rank-2 map, 128-row box
+    if (g.gpb == 0) {
+        const int64_t dims[4] = {cols, g.N, g.n_seq, 1}, strides[3] = {cols, (int64_t)g.N * cols, g.n_seq * g.N * cols};
+        return make_tmap_bf16_4d(m, base, dims, strides, g.N, g.G);
+    }
+    const int64_t dims[4] = {cols, g.inner, g.N, g.n_seq / g.inner};
+    const int64_t strides[3] = {cols, (int64_t)g.inner * cols, (int64_t)g.N * g.inner * cols};
+    return make_tmap_bf16_4d(m, base, dims, strides, g.G, g.N);
 }
 
 int attention_bwd_tc(const AttnGeom& g, const bf16* qkv, const float* lse, const bf16* d_out, bf16* d_qkv, Drop drop, cudaStream_t st) {
-    MSST_REQUIRE(attention_tc_contiguous(g), "attention_bwd_tc: needs tiles of 128 consecutive rows (inner == 1, N | 64)");
+    MSST_REQUIRE(attention_bwd_tc_supported(g), "attention_bwd_tc: needs packed short sequences (N <= 64)");
     const int64_t n_tiles = (g.groups + 1) / 2;
     static PerDeviceOnce once;
     if (once.first()) MSST_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcbSmem));
-    const int64_t R = g.n_seq * g.N, I = (int64_t)g.H * 64;
+    const int64_t I = (int64_t)g.H * 64;
     CUtensorMap t_qkv, t_do, t_dqkv;
-    if (int rc = make_tmap_bf16(&t_qkv, qkv, R, 3 * I, 3 * I, TC_ROWS)) return rc;
-    if (int rc = make_tmap_bf16(&t_do, d_out, R, I, I, TC_ROWS)) return rc;
-    if (int rc = make_tmap_bf16(&t_dqkv, d_qkv, R, 3 * I, 3 * I, TC_ROWS)) return rc;
+    const int nbox = (g.gpb == 0 && g.G * g.N == 64) ? 1 : 2;
+    if (int rc = tcb_tmap(&t_qkv, g, qkv, 3 * I, nbox)) return rc;
+    if (int rc = tcb_tmap(&t_do, g, d_out, I, nbox)) return rc;
+    if (int rc = tcb_tmap(&t_dqkv, g, d_qkv, 3 * I, nbox)) return rc;
     const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
+    static int pf_dist = -1;
+    if (pf_dist < 0) { const char* e = getenv("MSST_ATTN_PF"); pf_dist = e ? atoi(e) : TCB_PREFETCH; }
     static long long* dbg = nullptr;
     static int dbg_on = -1;
     if (dbg_on < 0) { const char* e = getenv("MSST_ATTN_DBG"); dbg_on = e ? atoi(e) : 0; if (dbg_on) { cudaMalloc(&dbg, 32 * 16 * 8); } }
     if (dbg_on) cudaMemsetAsync(dbg, 0, 32 * 16 * 8, st);
-    attn_bwd_tc_kernel<<<grid, TCB_THREADS, kTcbSmem, st>>>(t_qkv, t_do, t_dqkv, g, lse, drop, n_tiles, dbg);
+    attn_bwd_tc_kernel<<<grid, TCB_THREADS, kTcbSmem, st>>>(t_qkv, t_do, t_dqkv, g, lse, drop, n_tiles, nbox, pf_dist, dbg);
     MSST_LAUNCH_CHECK();
     if (dbg_on) {
         static int printed = 0;

@@ -470,6 +470,24 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int64_t rows, int64_t cols,
     return make_tmap(m, base, rows, cols, ld, box_rows);
 }
 
+// 4-D bf16 tensor view (dims[0] = contiguous columns; strides in ELEMENTS for dims 1..3), box {64, box1, box2, 1}, SWIZZLE_128B,
+// OOB -> zeros on load / clipped on store.  Used by the attention kernels to fetch the strided rows of a slot group as one box.
+int make_tmap_bf16_4d(CUtensorMap* m, const void* base, const int64_t dims[4], const int64_t strides[3], int box1, int box2) {
+    EncodeTiledFn enc = get_encode();
+    MSST_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+    MSST_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA operand must be 16-byte aligned");
+    cuuint64_t d[4], sb[3];
+    for (int i = 0; i < 4; ++i) d[i] = (cuuint64_t)dims[i];
+    for (int i = 0; i < 3; ++i) { sb[i] = (cuuint64_t)strides[i] * 2; MSST_REQUIRE(sb[i] % 16 == 0, "TMA strides must be multiples of 16 bytes"); }
+    cuuint32_t box[4] = {64u, (cuuint32_t)box1, (cuuint32_t)box2, 1u};
+    cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), d, sb, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MSST_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (4-D) failed with code %d (dims %lld %lld %lld %lld, box 64 %d %d 1)", (int)r,
+                 (long long)dims[0], (long long)dims[1], (long long)dims[2], (long long)dims[3], box1, box2);
+    return MSST_OK;
+}
+
 static uint32_t pow2_cols(int c) { uint32_t v = 32; while ((int)v < c) v <<= 1; return v; }
 
 int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st) {

@@ -51,8 +51,8 @@ int attention_bwd_bf16(const msst_attn_dims* d, const __nv_bfloat16* qkv, const 
 // attention_tc.cu (tcgen05 forward, N <= 64)
 struct AttnGeom;
 int attention_fwd_tc(const AttnGeom& g, const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, Drop drop, cudaStream_t st);
-// tcgen05 backward for tiles of 128 consecutive rows (attention_tc_contiguous: inner == 1, N divides 64 -- the spatial stack)
-bool attention_tc_contiguous(const AttnGeom& g);
+// tcgen05 backward for packed short sequences (N <= 64), contiguous or strided rows (both transformer stacks)
+bool attention_bwd_tc_supported(const AttnGeom& g);
 int attention_bwd_tc(const AttnGeom& g, const __nv_bfloat16* qkv, const float* lse, const __nv_bfloat16* d_out, __nv_bfloat16* d_qkv,
                      Drop drop, cudaStream_t st);
 
