@@ -625,8 +625,8 @@ int attention_fwd_bf16(const msst_attn_dims* d, const bf16* qkv, bf16* out, floa
     const Drop drop = make_drop(d->drop_p, d->seed, d->site, d->seed_dev);
     if (g.tiles == 1) {
         static int use_tc = -1;
-        if (use_tc < 0) { const char* e = getenv("MSST_ATTN_TC"); use_tc = e ? atoi(e) : 0; }
-        if (use_tc && g.gpb == 0) return attention_fwd_tc(g, qkv, out, lse, drop, st);   // tcgen05 / TMEM forward (attention_tc.cu; sequence-major packing only)
+        if (use_tc < 0) { const char* e = getenv("MSST_ATTN_TC"); use_tc = e ? atoi(e) : 1; }   // default: tcgen05 kernel; 0 = mma.sync
+        if (use_tc && attention_bwd_tc_supported(g)) return attention_fwd_tc(g, qkv, out, lse, drop, st);   // tcgen05 / TMEM forward (attention_tc.cu)
     }
     if (g.tiles == 1) {   // N <= 64: head-looping, cp.async double-buffered kernel
         static PerDeviceOnce attr_set;

@@ -1,17 +1,17 @@
-// Kernel (3), bf16 mode, N <= 64: attention forward on the 5th-generation tensor cores (tcgen05 + TMEM).
+// Kernel (3), bf16 mode, packed short sequences (N <= 64): attention forward AND backward on the 5th-generation tensor cores
+// (tcgen05 + TMEM), operands by TMA, results by TMA store.
 //
-// One CTA works on 128 slots (two 64-slot groups of attn_geom.cuh) x one head at a time and loops persistently over
-// (tile, head) items.  Per item:
-//   producer       : TMA (cp.async.bulk.tensor, one 128x64 box per operand) when the tile's slots are consecutive rows
-//                    (spatial stack), otherwise two warps gather the strided rows (spectral stack) with cp.async into the
-//                    same SWIZZLE_128B K-major layout, completion signalled on an mbarrier (cp.async.mbarrier.arrive)
-//   MMA warp       : S[128x128] = Q K^T  -> TMEM (tcgen05.mma, one elected thread);   later  O[128x64] = P V -> TMEM
-//                    (P from smem K-major, V as MN-major B operand: no transpose anywhere)
-//   softmax warps  : two ping-pong warpgroups (even / odd items), thread = row.  tcgen05.ld of the row's own 64-key block, mask (same sequence), exp2, row sum and Philox-free
-//                    pair-hash dropout entirely thread-local (no shuffles), P (bf16) -> smem; epilogue: O row / l -> global, lse
-// Only the two diagonal 64x64 blocks of S are meaningful (block-diagonal mask); the off-diagonal halves of the P tile are
-// zeroed once and never written.  smem/TMEM stages are double-buffered so the tensor work of item i+1 overlaps the softmax of i.
-// The kernel is HBM-bound: 3*128 B in + 128 B out per (slot, head).
+// One persistent CTA per SM works on 128 slots (two 64-slot groups of attn_geom.cuh) x one head at a time.  Warp roles:
+//   warp 16  TMA producer (one elected thread; also allocates TMEM): one box per operand per slot group -- 2-D boxes when the
+//            tile is 128 consecutive rows (spatial stack), 4-D boxes over the (col, s, pos, blk) view for strided sequences
+//            (spectral stack) -- plus an L2 prefetch of the next item's boxes
+//   warp 17  MMA issuer (one elected thread): a small state machine that issues whichever contraction has its inputs ready
+//   warp 18  TMA store of the staged result tiles (nobody else ever waits for a store to drain)
+//   warps 0-7 / 8-15  two softmax + epilogue groups that ping-pong over items; thread (r, half) owns row r and 32 of the 64
+//            columns of the row's diagonal block (tcgen05.ld 32x32b: thread = TMEM lane), row statistics are exchanged between
+//            the two halves through shared memory
+// Only the two diagonal 64x64 blocks of S (and dP) are meaningful (block-diagonal mask): P~ / dS are kept as compact tiles
+// whose off-diagonal parts share one block of zeros.  See the section comments for the per-direction data flow.
 #include "common.cuh"
 #include "kernels.h"
 #include "attn_geom.cuh"
@@ -27,273 +27,15 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int64_t rows, int64_t cols,
 int make_tmap_bf16_4d(CUtensorMap* m, const void* base, const int64_t dims[4], const int64_t strides[3], int box1, int box2);
 
 constexpr int TC_ROWS = 128;
-constexpr int TC_THREADS = 384;            // warps 0-3 softmax group A (even items), 4-5 producers, 6 MMA, 7 TMEM alloc, 8-11 softmax group B
-constexpr int TC_PRODUCERS = 64;
 constexpr uint32_t TC_TILE = TC_ROWS * 128;   // bytes of one [128 rows][64 bf16] tile (16 KB)
 
-struct alignas(8) TcBars {
-    uint64_t full[2], kv_empty[2], s_full[2], p_full[2], o_full[2], tmem_free[2];
-    uint32_t tmem_base;
-};
-
-// smem: [2 stages][Q,K,V][16 KB] | [2 stages][P chunk0, chunk1][16 KB] | barriers
-constexpr size_t kTcSmem = 2 * 3 * TC_TILE + 2 * 2 * TC_TILE + sizeof(TcBars) + 1024;
-
-__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
-    const int sz = valid ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ uint32_t pack_bf(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
-// dropout pair indexing / hash identical to attention_bf16.cu (the backward kernel regenerates the same mask)
+// dropout pair indexing / hash identical to attention_bf16.cu (every kernel regenerates the same mask)
 __device__ __forceinline__ uint64_t tile_pair_base_tc(const AttnGeom& g, int64_t group, int h) {
     return ((uint64_t)group * g.H + h) * (uint64_t)(TS * TS / 2);
-}
-__device__ __forceinline__ uint32_t tc_pair_hash(const Drop& d, uint64_t idx) {
-    const uint64_t s = d.seed + (d.seed_dev ? __ldg(d.seed_dev) : 0ull);
-    uint32_t x = ((uint32_t)idx + (uint32_t)(s >> 32)) * 0x9E3779B1u ^ ((uint32_t)(idx >> 32) * 0x85EBCA77u) ^ (uint32_t)s ^ (d.site * 0xC2B2AE3Du);
-    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
-    return x;
-}
-// global row (or -1) of slot r (0..127) of a tile
-__device__ __forceinline__ int64_t tc_row(const AttnGeom& g, int64_t tile, int r, int& slot_lo) {
-    const int64_t group = tile * 2 + (r >> 6);
-    int64_t seq; int pos;
-    const bool ok = group < g.groups && slot_to(g, group, 0, r & 63, seq, pos);
-    slot_lo = ((r & 63) / g.N) * g.N;
-    return ok ? row_of(g, seq, pos) : -1;
-}
-
-// use_tma != 0: the 128 slots of a tile are 128 consecutive rows (inner == 1, N divides 64) -> one TMA box per operand
-__global__ void __launch_bounds__(TC_THREADS, 1)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, AttnGeom g, const bf16* __restrict__ qkv, bf16* __restrict__ out,
-                   float* __restrict__ lse, Drop drop, int64_t n_tiles, int use_tma) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* qkv_s = smem;                                  // [2][3][16 KB]
-    uint8_t* p_s = smem + 2 * 3 * TC_TILE;                  // [2][2][16 KB]
-    TcBars* bars = reinterpret_cast<TcBars*>(p_s + 2 * 2 * TC_TILE);
-    const int warp = threadIdx.x >> 5;
-    const int I = g.H * 64;
-    const int64_t ld = 3 * (int64_t)I;
-
-    if (warp == 6 && elect_one()) {
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&bars->full[s], use_tma ? 1 : TC_PRODUCERS); mbar_init(&bars->kv_empty[s], 1); mbar_init(&bars->s_full[s], 1);
-            mbar_init(&bars->p_full[s], 128); mbar_init(&bars->o_full[s], 1); mbar_init(&bars->tmem_free[s], 128);
-        }
-        fence_barrier_init();
-    }
-    if (warp == 4 && use_tma && elect_one()) prefetch_tmap(&tma_qkv);
-    if (warp == 7) tmem_alloc(&bars->tmem_base, 512);
-    // zero Q/K/V stages and the P tiles once: the off-diagonal halves of P are never written afterwards
-    for (uint32_t i = threadIdx.x; i < (2 * 3 + 2 * 2) * TC_TILE / 16; i += TC_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = bars->tmem_base;
-    const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0), idesc_o = make_idesc_bf16(128, 64, 0, 1);
-
-    // items of this CTA: it = 0 .. n_items-1  <->  (tile = blockIdx.x + (it / H) * gridDim.x, head = it % H);
-    // stage = it & 1, k-th use of a stage = it >> 1 (barrier phase parity (it >> 1) & 1)
-    const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-    const int64_t n_items = my_tiles * g.H;
-
-    if (warp == 4 || warp == 5) {
-        // ===== producers =====
-        if (use_tma) {
-            if (warp == 4 && elect_one()) {
-                for (int64_t it = 0; it < n_items; ++it) {
-                    const int st = (int)(it & 1); const uint32_t ph = (uint32_t)(it >> 1) & 1;
-                    const int64_t tile = blockIdx.x + (it / g.H) * gridDim.x; const int h = (int)(it % g.H);
-                    mbar_wait(&bars->kv_empty[st], ph ^ 1);
-                    uint8_t* base = qkv_s + (size_t)st * 3 * TC_TILE;
-                    mbar_arrive_expect_tx(&bars->full[st], 3 * TC_TILE);
-                    tma_load_2d(base, &tma_qkv, &bars->full[st], h * 64, (int)(tile * TC_ROWS));
-                    tma_load_2d(base + TC_TILE, &tma_qkv, &bars->full[st], I + h * 64, (int)(tile * TC_ROWS));
-                    tma_load_2d(base + 2 * TC_TILE, &tma_qkv, &bars->full[st], 2 * I + h * 64, (int)(tile * TC_ROWS));
-                }
-            }
-        } else {
-            // gather: thread covers 16-byte piece pc of rows (pt >> 3) + 8k, k = 0..15
-            const int pt = threadIdx.x - 128, pc = pt & 7;
-            int64_t prow[16];
-            int64_t cur_tile = -1;
-            for (int64_t it = 0; it < n_items; ++it) {
-                const int st = (int)(it & 1); const uint32_t ph = (uint32_t)(it >> 1) & 1;
-                const int64_t tile = blockIdx.x + (it / g.H) * gridDim.x; const int h = (int)(it % g.H);
-                if (tile != cur_tile) {
-                    cur_tile = tile;
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) { int lo; prow[k] = tc_row(g, tile, (pt >> 3) + 8 * k, lo); }
-                }
-                mbar_wait(&bars->kv_empty[st], ph ^ 1);
-                const uint32_t base = smem_u32(qkv_s + (size_t)st * 3 * TC_TILE);
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const int r = (pt >> 3) + 8 * k;
-                    const bf16* src = qkv + (prow[k] < 0 ? 0 : prow[k]) * ld + h * 64 + pc * 8;
-                    const uint32_t dst = base + r * 128 + ((pc ^ (r & 7)) << 4);
-                    cp_async16_zfill(dst, src, prow[k] >= 0);
-                    cp_async16_zfill(dst + TC_TILE, src + I, prow[k] >= 0);
-                    cp_async16_zfill(dst + 2 * TC_TILE, src + 2 * I, prow[k] >= 0);
-                }
-                cp_async_mbar_arrive(&bars->full[st]);
-            }
-        }
-    } else if (warp == 6) {
-        // ===== MMA issuer: S(it+1) is issued before waiting for the softmax of item it =====
-        if (elect_one()) {
-            auto issue_s = [&](int64_t it) {
-                const int st = (int)(it & 1); const uint32_t ph = (uint32_t)(it >> 1) & 1;
-                const uint32_t qb = smem_u32(qkv_s + (size_t)st * 3 * TC_TILE);
-                mbar_wait(&bars->tmem_free[st], ph ^ 1);       // S / O TMEM stage drained by the epilogue of item it - 2
-                mbar_wait(&bars->full[st], ph);                // Q, K, V landed
-                fence_proxy_async();
-                tc_fence_after();
-                const uint64_t dq = make_smem_desc(qb, 16, 1024), dk = make_smem_desc(qb + TC_TILE, 16, 1024);
-                for (int k = 0; k < 4; ++k)                    // S = Q K^T, K = 64 = 4 x UMMA_K
-                    umma_bf16(tmem_base + st * 128, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k != 0);
-                umma_commit(&bars->s_full[st]);
-            };
-            if (n_items > 0) issue_s(0);
-            for (int64_t it = 0; it < n_items; ++it) {
-                const int st = (int)(it & 1); const uint32_t ph = (uint32_t)(it >> 1) & 1;
-                if (it + 1 < n_items) issue_s(it + 1);
-                const uint32_t qb = smem_u32(qkv_s + (size_t)st * 3 * TC_TILE);
-                const uint32_t pb = smem_u32(p_s + (size_t)st * 2 * TC_TILE);
-                mbar_wait(&bars->p_full[st], ph);              // P written by the softmax warps (generic proxy + their fence)
-                fence_proxy_async();
-                tc_fence_after();
-                const uint64_t dv = make_smem_desc(qb + 2 * TC_TILE, TC_TILE, 1024);
-                for (int k = 0; k < 8; ++k) {                  // O = P V, K = 128 keys = 8 x UMMA_K
-                    const uint64_t dp = make_smem_desc(pb + (k >> 2) * TC_TILE, 16, 1024) + (uint64_t)((k & 3) * 2);
-                    umma_bf16(tmem_base + 256 + st * 64, dp, dv + (uint64_t)(k * 128), idesc_o, k != 0);
-                }
-                umma_commit(&bars->o_full[st]);
-                umma_commit(&bars->kv_empty[st]);              // Q, K, V (and P) of this stage are free again
-            }
-        }
-    } else if (warp < 4 || warp >= 8) {
-        // ===== two softmax + epilogue warpgroups (ping-pong): group A = even items / stage 0, group B = odd items / stage 1.
-        // thread r = row r of the tile; everything row-wise is thread-local (no shuffles) =====
-        const int grp = warp >= 8 ? 1 : 0;
-        const int r = threadIdx.x & 127;
-        const int blk = r >> 6;                                 // which 64-key block (== which slot group of the tile)
-        const int st = grp;
-        const float sl2 = g.scale * 1.4426950408889634f;
-        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-        int64_t cur_tile = -1, grow = -1; int klo = 0, khi = 0;
-        for (int64_t it = grp; it < n_items; it += 2) {
-            const uint32_t ph = (uint32_t)(it >> 1) & 1;
-            const int64_t tile = blockIdx.x + (it / g.H) * gridDim.x; const int h = (int)(it % g.H);
-            if (tile != cur_tile) {
-                cur_tile = tile;
-                grow = tc_row(g, tile, r, klo);
-                khi = grow >= 0 ? klo + g.N : 0;
-            }
-            const int64_t group = tile * 2 + blk;
-            mbar_wait(&bars->s_full[st], ph);
-            tc_fence_after();
-            float s[64];
-            {
-                uint32_t a[32], b[32];
-                const uint32_t scol = tmem_base + lane_base + st * 128 + blk * 64;
-                tmem_ld_32x32(scol, a);
-                tmem_ld_32x32(scol + 32, b);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) { s[j] = __uint_as_float(a[j]); s[32 + j] = __uint_as_float(b[j]); }
-            }
-            float mx = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < 64; ++j) {
-                s[j] = (j >= klo && j < khi) ? s[j] * sl2 : -INFINITY;
-                mx = fmaxf(mx, s[j]);
-            }
-            const float sub = mx == -INFINITY ? 0.f : mx;
-            float l = 0.f;
-#pragma unroll
-            for (int j = 0; j < 64; ++j) { s[j] = exp2f(s[j] - sub); l += s[j]; }
-            if (drop.on()) {
-                const uint64_t base = tile_pair_base_tc(g, group, h) + (uint64_t)((r & 63) * 32);
-                const uint32_t t16 = drop.thresh >> 16;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const uint32_t hsh = tc_pair_hash(drop, base + j);
-                    s[2 * j] *= (hsh & 0xFFFFu) >= t16 ? drop.scale : 0.f;
-                    s[2 * j + 1] *= (hsh >> 16) >= t16 ? drop.scale : 0.f;
-                }
-            }
-            // P row (bf16) -> smem P tile of this stage: chunk = own key block, SWIZZLE_128B K-major
-            {
-                uint8_t* prow = p_s + (size_t)st * 2 * TC_TILE + (size_t)blk * TC_TILE + r * 128;
-#pragma unroll
-                for (int pc = 0; pc < 8; ++pc)
-                    *reinterpret_cast<uint4*>(prow + ((pc ^ (r & 7)) << 4)) =
-                        make_uint4(pack_bf(s[pc * 8], s[pc * 8 + 1]), pack_bf(s[pc * 8 + 2], s[pc * 8 + 3]),
-                                   pack_bf(s[pc * 8 + 4], s[pc * 8 + 5]), pack_bf(s[pc * 8 + 6], s[pc * 8 + 7]));
-            }
-            fence_proxy_async();
-            tc_fence_before();
-            mbar_arrive(&bars->p_full[st]);
-            // ---- epilogue of the same item (the other group works on the next item meanwhile) ----
-            mbar_wait(&bars->o_full[st], ph);
-            tc_fence_after();
-            uint32_t v[32], w[32];
-            tmem_ld_32x32(tmem_base + lane_base + 256 + st * 64, v);
-            tmem_ld_32x32(tmem_base + lane_base + 256 + st * 64 + 32, w);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(&bars->tmem_free[st]);
-            if (grow >= 0) {
-                const float inv = l > 0.f ? 1.f / l : 0.f;
-                bf16* dst = out + grow * I + h * 64;
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    *reinterpret_cast<uint4*>(dst + c * 8) =
-                        make_uint4(pack_bf(__uint_as_float(v[c * 8]) * inv, __uint_as_float(v[c * 8 + 1]) * inv),
-                                   pack_bf(__uint_as_float(v[c * 8 + 2]) * inv, __uint_as_float(v[c * 8 + 3]) * inv),
-                                   pack_bf(__uint_as_float(v[c * 8 + 4]) * inv, __uint_as_float(v[c * 8 + 5]) * inv),
-                                   pack_bf(__uint_as_float(v[c * 8 + 6]) * inv, __uint_as_float(v[c * 8 + 7]) * inv));
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    *reinterpret_cast<uint4*>(dst + 32 + c * 8) =
-                        make_uint4(pack_bf(__uint_as_float(w[c * 8]) * inv, __uint_as_float(w[c * 8 + 1]) * inv),
-                                   pack_bf(__uint_as_float(w[c * 8 + 2]) * inv, __uint_as_float(w[c * 8 + 3]) * inv),
-                                   pack_bf(__uint_as_float(w[c * 8 + 4]) * inv, __uint_as_float(w[c * 8 + 5]) * inv),
-                                   pack_bf(__uint_as_float(w[c * 8 + 6]) * inv, __uint_as_float(w[c * 8 + 7]) * inv));
-                lse[grow * g.H + h] = (sub + log2f(l)) * 0.6931471805599453f;
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 7) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
-}
-
-int attention_fwd_tc(const AttnGeom& g, const bf16* qkv, bf16* out, float* lse, Drop drop, cudaStream_t st) {
-    const int64_t n_tiles = (g.groups + 1) / 2;
-    static PerDeviceOnce once;
-    if (once.first()) MSST_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
-    // contiguous tiles (e.g. the spatial stack: inner == 1, full 64-slot groups): TMA; otherwise a cp.async row gather
-    const int use_tma = (g.inner == 1 && 64 % g.N == 0 && n_tiles * TC_ROWS < (int64_t)2147483647) ? 1 : 0;
-    CUtensorMap tm;
-    memset(&tm, 0, sizeof(tm));
-    if (use_tma) {
-        const int64_t R = g.n_seq * g.N;
-        if (int rc = make_tmap_bf16(&tm, qkv, R, 3 * (int64_t)g.H * 64, 3 * (int64_t)g.H * 64, TC_ROWS)) return rc;
-    }
-    const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
-    attn_fwd_tc_kernel<<<grid, TC_THREADS, kTcSmem, st>>>(tm, g, qkv, out, lse, drop, n_tiles, use_tma);
-    MSST_LAUNCH_CHECK();
-    return MSST_OK;
 }
 
 // =========================================================================================================
@@ -710,6 +452,293 @@ int attention_bwd_tc(const AttnGeom& g, const bf16* qkv, const float* lse, const
             fflush(stdout);
         }
     }
+    return MSST_OK;
+}
+
+// =========================================================================================================
+// Forward on tcgen05 / TMEM, same tile / warp-role structure as the backward above.  Per (128-slot tile, head) item:
+//   S = Q K^T -> TMEM [128 x 128];  softmax threads (row, half): row max and row sum exchanged between the two halves through
+//   smem, P~ = dropout(exp2(S*scale*log2e - max)) (unnormalised, bf16) -> smem;  O = P~ V -> TMEM [128 x 64] (V as MN-major B);
+//   epilogue: O / l -> bf16 -> staging tile -> TMA store, lse -> global.
+// 3 operand stages (Q, K, V: 48 KB each), one P~ buffer and one S/O TMEM slot per softmax group, one staging tile.
+// HBM-bound: 3 * 128 B in + 128 B out (+ 4 B lse) per (slot, head).
+// =========================================================================================================
+struct alignas(8) TcfBars {
+    uint64_t full[3], kv_empty[3], s_full[2], p_full[2], o_full[2], tmem_free[2], stg_free[2], stg_full[2];
+    uint32_t tmem_base;
+};
+constexpr int TCF_STAGES = 3;
+// smem: [3 stages][Q, K, V][16 KB] | P~ per group (2 x 24 KB) | O staging (16 KB) | row max / row sum exchange | barriers
+constexpr size_t kTcfSmem = TCF_STAGES * 3 * TC_TILE + 2 * TCB_PD + TC_TILE + 2 * 2 * 2 * 128 * sizeof(float) + sizeof(TcfBars);
+
+__global__ void __launch_bounds__(TCB_THREADS, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_out, AttnGeom g,
+                   float* __restrict__ lse, Drop drop, int64_t n_tiles, int nbox, int pf_dist) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if (smem_u32(smem) & 1023u) __trap();
+    uint8_t* op_s = smem;                                   // [3][3][16 KB]
+    uint8_t* p_s = smem + TCF_STAGES * 3 * TC_TILE;         // P~ of group 0, group 1 (24 KB each, see TCB_PD)
+    uint8_t* stg_s = p_s + 2 * TCB_PD;                      // O staging for the TMA store
+    float* xch = reinterpret_cast<float*>(stg_s + TC_TILE); // [group][max | sum][half][128]
+    TcfBars* bars = reinterpret_cast<TcfBars*>(xch + 2 * 2 * 2 * 128);
+    const int warp = threadIdx.x >> 5;
+    const int I = g.H * 64;
+
+    if (warp == 17 && elect_one()) {
+        for (int s = 0; s < TCF_STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->kv_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bars->s_full[s], 1); mbar_init(&bars->p_full[s], 256); mbar_init(&bars->o_full[s], 1);
+            mbar_init(&bars->tmem_free[s], 256); mbar_init(&bars->stg_free[s], 1); mbar_init(&bars->stg_full[s], 256);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 16) {
+        tmem_alloc(&bars->tmem_base, 512);
+        if (elect_one()) { prefetch_tmap(&tma_qkv); prefetch_tmap(&tma_out); }
+    }
+    // zero once: operand rows a group's box does not cover and the shared zero blocks of the P~ tiles
+    for (uint32_t i = threadIdx.x; i < (TCF_STAGES * 3 * TC_TILE + 2 * TCB_PD) / 16; i += TCB_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+    const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0), idesc_o = make_idesc_bf16(128, 64, 0, 1);
+
+    const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const int64_t n_items = my_tiles * g.H;
+    const uint32_t box_bytes = (uint32_t)(g.G * g.N) * 128u * (nbox == 1 ? 2u : 1u);
+
+    if (warp == 16) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            int stg = 0; uint32_t ph = 0;
+            for (int64_t it = 0; it < n_items; ++it) {
+                const int64_t tile = blockIdx.x + (it / g.H) * gridDim.x; const int h = (int)(it % g.H);
+                mbar_wait(&bars->kv_empty[stg], ph ^ 1);
+                uint8_t* base = op_s + (size_t)stg * 3 * TC_TILE;
+                mbar_arrive_expect_tx(&bars->full[stg], 3 * nbox * box_bytes);
+                if (nbox == 1) {
+                    const int row0 = (int)(tile * TC_ROWS);
+                    tma_load_2d(base, &tma_qkv, &bars->full[stg], h * 64, row0);
+                    tma_load_2d(base + TC_TILE, &tma_qkv, &bars->full[stg], I + h * 64, row0);
+                    tma_load_2d(base + 2 * TC_TILE, &tma_qkv, &bars->full[stg], 2 * I + h * 64, row0);
+                } else
+                for (int gi = 0; gi < nbox; ++gi) {
+                    int c1, c2, c3;
+                    tcb_group_coords(g, tile * 2 + gi, c1, c2, c3);
+                    uint8_t* dst = base + gi * 64 * 128;
+                    tma_load_4d(dst, &tma_qkv, &bars->full[stg], h * 64, c1, c2, c3);
+                    tma_load_4d(dst + TC_TILE, &tma_qkv, &bars->full[stg], I + h * 64, c1, c2, c3);
+                    tma_load_4d(dst + 2 * TC_TILE, &tma_qkv, &bars->full[stg], 2 * I + h * 64, c1, c2, c3);
+                }
+                if (pf_dist > 0 && it + pf_dist < n_items) {
+                    const int64_t it2 = it + pf_dist;
+                    const int64_t tile2 = blockIdx.x + (it2 / g.H) * gridDim.x; const int h2 = (int)(it2 % g.H);
+                    if (nbox == 1) {
+                        const int row2 = (int)(tile2 * TC_ROWS);
+                        tma_prefetch_l2_2d(&tma_qkv, h2 * 64, row2);
+                        tma_prefetch_l2_2d(&tma_qkv, I + h2 * 64, row2);
+                        tma_prefetch_l2_2d(&tma_qkv, 2 * I + h2 * 64, row2);
+                    } else
+                    for (int gi = 0; gi < nbox; ++gi) {
+                        int c1, c2, c3;
+                        tcb_group_coords(g, tile2 * 2 + gi, c1, c2, c3);
+                        tma_prefetch_l2_4d(&tma_qkv, h2 * 64, c1, c2, c3);
+                        tma_prefetch_l2_4d(&tma_qkv, I + h2 * 64, c1, c2, c3);
+                        tma_prefetch_l2_4d(&tma_qkv, 2 * I + h2 * 64, c1, c2, c3);
+                    }
+                }
+                if (++stg == TCF_STAGES) { stg = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 17) {
+        // ===== MMA issuer: S of item next_s / O of item next_p, whichever has its inputs ready; S runs at most one item ahead =====
+        if (elect_one()) {
+            int64_t next_s = 0, next_p = 0;
+            int stg_s1 = 0, stg_p = 0; uint32_t ph_s1 = 0;
+            while (next_p < n_items) {
+                if (next_s < n_items && next_s <= next_p + 1) {
+                    const int slot = (int)(next_s & 1); const uint32_t phg = (uint32_t)(next_s >> 1) & 1;
+                    if (mbar_try_wait(&bars->tmem_free[slot], phg ^ 1) && mbar_try_wait(&bars->full[stg_s1], ph_s1)) {
+                        tc_fence_after();
+                        const uint32_t qb = smem_u32(op_s + (size_t)stg_s1 * 3 * TC_TILE);
+                        const uint64_t dq = make_smem_desc(qb, 16, 1024), dk = make_smem_desc(qb + TC_TILE, 16, 1024);
+                        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + slot * 256, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k != 0);
+                        umma_commit(&bars->s_full[slot]);
+                        ++next_s;
+                        if (++stg_s1 == TCF_STAGES) { stg_s1 = 0; ph_s1 ^= 1; }
+                    }
+                }
+                if (next_p < next_s) {
+                    const int slot = (int)(next_p & 1);
+                    if (mbar_try_wait(&bars->p_full[slot], (uint32_t)(next_p >> 1) & 1)) {
+                        fence_proxy_async();
+                        tc_fence_after();
+                        const uint32_t vb = smem_u32(op_s + (size_t)stg_p * 3 * TC_TILE + 2 * TC_TILE);
+                        const uint32_t pb = smem_u32(p_s + (size_t)slot * TCB_PD);
+                        const uint64_t b_v = make_smem_desc(vb, TC_TILE, 1024);
+                        for (int k = 0; k < 8; ++k) {   // O = P~ V : reduction over the 128 keys (2 chunks x 4 steps), V as MN-major B
+                            const uint64_t a = make_smem_desc(pb + (k >> 2) * TCB_CHUNK, 16, 1024) + (uint64_t)((k & 3) * 2);
+                            umma_bf16(tmem_base + slot * 256 + 128, a, b_v + (uint64_t)(k * 128), idesc_o, k != 0);
+                        }
+                        umma_commit(&bars->o_full[slot]);
+                        umma_commit(&bars->kv_empty[stg_p]);
+                        ++next_p;
+                        if (++stg_p == TCF_STAGES) stg_p = 0;
+                    }
+                }
+            }
+        }
+    } else if (warp == 18) {
+        // ===== TMA store of the staged O tile =====
+        if (elect_one()) {
+            for (int64_t it = 0; it < n_items; ++it) {
+                const int64_t tile = blockIdx.x + (it / g.H) * gridDim.x; const int h = (int)(it % g.H);
+                mbar_wait(&bars->stg_full[it & 1], (uint32_t)(it >> 1) & 1);
+                if (nbox == 1) tma_store_2d(&tma_out, stg_s, h * 64, (int)(tile * TC_ROWS));
+                else
+                for (int gi = 0; gi < nbox; ++gi) {
+                    int c1, c2, c3;
+                    tcb_group_coords(g, tile * 2 + gi, c1, c2, c3);
+                    tma_store_4d(&tma_out, stg_s + gi * 64 * 128, h * 64, c1, c2, c3);
+                }
+                tma_store_commit();
+                tma_store_wait_read();
+                mbar_arrive(&bars->stg_free[it & 1]);
+            }
+        }
+    } else if (warp < 16) {
+        // ===== two softmax + epilogue groups of 8 warps; thread (r, half) owns row r and 32 of its 64 columns =====
+        const int grp = warp >> 3, wl = warp & 7, half = wl >> 2;
+        const int r = (wl & 3) * 32 + (threadIdx.x & 31);
+        const int blk = r >> 6;
+        const int c0 = half * 32;
+        const float sl2 = g.scale * 1.4426950408889634f;
+        const uint32_t lane_base = (uint32_t)((wl & 3) * 32) << 16;
+        const uint32_t swz = (uint32_t)(r & 7);
+        const bool full_blocks = g.N == 64 && g.groups % 2 == 0;
+        const uint64_t seed = drop.seed + (drop.seed_dev ? __ldg(drop.seed_dev) : 0ull);
+        const uint32_t t16 = drop.thresh >> 16;
+        float* my_max = xch + ((grp * 2 + 0) * 2 + half) * 128 + r;
+        float* my_sum = xch + ((grp * 2 + 1) * 2 + half) * 128 + r;
+        const float* other_max = xch + ((grp * 2 + 0) * 2 + (half ^ 1)) * 128 + r;
+        const float* other_sum = xch + ((grp * 2 + 1) * 2 + (half ^ 1)) * 128 + r;
+        uint8_t* prow = p_s + (size_t)grp * TCB_PD + (size_t)blk * TCB_CHUNK + r * 128;
+        uint32_t vmask_geom = 0;
+        {
+            const int slot = r & 63, used = g.G * g.N;
+            for (int j = 0; j < 32; ++j) {
+                const int c = c0 + j;
+                const bool same = g.gpb == 0 ? (c / g.N == slot / g.N) : (c % g.G == slot % g.G);
+                vmask_geom |= (uint32_t)(same && c < used && slot < used) << j;
+            }
+        }
+        int64_t cur_tile = -1, grow = -1; uint32_t vmask = 0;
+        for (int64_t it = grp; it < n_items; it += 2) {
+            const uint32_t ph = (uint32_t)(it >> 1) & 1;
+            const int64_t tile = blockIdx.x + (it / g.H) * gridDim.x; const int h = (int)(it % g.H);
+            if (tile != cur_tile) {
+                cur_tile = tile;
+                int64_t seq; int pos;
+                const int64_t group = tile * 2 + blk;
+                const bool ok = group < g.groups && slot_to(g, group, 0, r & 63, seq, pos);
+                grow = ok ? row_of(g, seq, pos) : -1;
+                vmask = ok ? (full_blocks ? 0xFFFFFFFFu : vmask_geom) : 0u;
+            }
+            const uint64_t hidx = tile_pair_base_tc(g, tile * 2 + blk, h) + (uint64_t)((r & 63) * 32 + (c0 >> 1));
+            const uint32_t hash_lo = (uint32_t)hidx + (uint32_t)(seed >> 32);
+            const uint32_t hash_hi = ((uint32_t)(hidx >> 32) * 0x85EBCA77u) ^ (uint32_t)seed ^ (drop.site * 0xC2B2AE3Du);
+            mbar_wait(&bars->s_full[grp], ph);
+            tc_fence_after();
+            float p[32];
+            {
+                uint32_t a[32];
+                tmem_ld_32x32(tmem_base + lane_base + grp * 256 + blk * 64 + c0, a);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) p[j] = __uint_as_float(a[j]) * sl2;
+            }
+            float mx = -INFINITY;
+            if (full_blocks) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, p[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { p[j] = (vmask >> j) & 1u ? p[j] : -INFINITY; mx = fmaxf(mx, p[j]); }
+            }
+            *my_max = mx;
+            asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory");
+            mx = fmaxf(mx, *other_max);
+            const float sub = mx == -INFINITY ? 0.f : mx;
+            float l = 0.f;
+            uint32_t pfp[16];
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+                float p0 = ex2_approx(p[2 * jj] - sub), p1 = ex2_approx(p[2 * jj + 1] - sub);
+                l += p0 + p1;
+                if (drop.on()) {
+                    uint32_t x = (hash_lo + (uint32_t)jj) * 0x9E3779B1u ^ hash_hi;
+                    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+                    p0 *= (x & 0xFFFFu) >= t16 ? drop.scale : 0.f;
+                    p1 *= (x >> 16) >= t16 ? drop.scale : 0.f;
+                }
+                pfp[jj] = pack_bf(p0, p1);
+            }
+            *my_sum = l;
+            // this group's P~ buffer was last read by the O MMAs of item it - 2, whose completion this group awaited (o_full)
+#pragma unroll
+            for (int pc = 0; pc < 4; ++pc)
+                *reinterpret_cast<uint4*>(prow + (((uint32_t)(half * 4 + pc) ^ swz) << 4)) = make_uint4(pfp[pc * 4], pfp[pc * 4 + 1], pfp[pc * 4 + 2], pfp[pc * 4 + 3]);
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(&bars->p_full[grp]);
+            asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory");
+            l += *other_sum;
+            const float inv = l > 0.f ? 1.f / l : 0.f;
+            if (half == 0 && grow >= 0) lse[grow * g.H + h] = (sub + log2f(l)) * 0.6931471805599453f;
+            // ---- epilogue: O row / l -> bf16 -> staging -> TMA store ----
+            mbar_wait(&bars->o_full[grp], ph);
+            if (it > 0) mbar_wait(&bars->stg_free[(it - 1) & 1], (uint32_t)((it - 1) >> 1) & 1);
+            tc_fence_after();
+            {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + lane_base + grp * 256 + 128 + c0, v);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&bars->tmem_free[grp]);
+                uint8_t* trow = stg_s + r * 128;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    *reinterpret_cast<uint4*>(trow + (((uint32_t)(half * 4 + c) ^ swz) << 4)) =
+                        make_uint4(pack_bf(__uint_as_float(v[c * 8]) * inv, __uint_as_float(v[c * 8 + 1]) * inv), pack_bf(__uint_as_float(v[c * 8 + 2]) * inv, __uint_as_float(v[c * 8 + 3]) * inv),
+                                   pack_bf(__uint_as_float(v[c * 8 + 4]) * inv, __uint_as_float(v[c * 8 + 5]) * inv), pack_bf(__uint_as_float(v[c * 8 + 6]) * inv, __uint_as_float(v[c * 8 + 7]) * inv));
+            }
+            fence_proxy_async();
+            mbar_arrive(&bars->stg_full[it & 1]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 16) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+int attention_fwd_tc(const AttnGeom& g, const bf16* qkv, bf16* out, float* lse, Drop drop, cudaStream_t st) {
+    MSST_REQUIRE(attention_bwd_tc_supported(g), "attention_fwd_tc: needs packed short sequences (N <= 64)");
+    const int64_t n_tiles = (g.groups + 1) / 2;
+    static PerDeviceOnce once;
+    if (once.first()) MSST_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcfSmem));
+    const int64_t I = (int64_t)g.H * 64;
+    const int nbox = (g.gpb == 0 && g.G * g.N == 64) ? 1 : 2;
+    CUtensorMap t_qkv, t_out;
+    if (int rc = tcb_tmap(&t_qkv, g, qkv, 3 * I, nbox)) return rc;
+    if (int rc = tcb_tmap(&t_out, g, out, I, nbox)) return rc;
+    static int pf_dist = -1;
+    if (pf_dist < 0) { const char* e = getenv("MSST_ATTN_PF"); pf_dist = e ? atoi(e) : TCB_PREFETCH; }
+    const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
+    attn_fwd_tc_kernel<<<grid, TCB_THREADS, kTcfSmem, st>>>(t_qkv, t_out, g, lse, drop, n_tiles, nbox, pf_dist);
+    MSST_LAUNCH_CHECK();
     return MSST_OK;
 }
 

@@ -48,7 +48,7 @@ int attention_fwd_bf16(const msst_attn_dims* d, const __nv_bfloat16* qkv, __nv_b
 int attention_bwd_bf16(const msst_attn_dims* d, const __nv_bfloat16* qkv, const __nv_bfloat16* out, const float* lse,
                        const __nv_bfloat16* d_out, __nv_bfloat16* d_qkv, cudaStream_t st);
 
-// attention_tc.cu (tcgen05 forward, N <= 64)
+// attention_tc.cu (tcgen05 / TMEM forward and backward, N <= 64)
 struct AttnGeom;
 int attention_fwd_tc(const AttnGeom& g, const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, Drop drop, cudaStream_t st);
 // tcgen05 backward for packed short sequences (N <= 64), contiguous or strided rows (both transformer stacks)

@@ -124,43 +124,10 @@ def test_bf16_training_dropout_runs_and_is_seed_deterministic():
     assert torch.isfinite(y).all()
 
 
-def test_tcgen05_attention_forward_opt_in():
-    """Experimental tcgen05/TMEM attention forward (attention_tc.cu, MSST_ATTN_TC=1; default off because the mma.sync
-    kernel is currently faster): parity of forward AND of the regular backward on its outputs, incl. dropout-mask agreement."""
-    import os, subprocess, sys
-    code = r'''
-import torch, sys
-sys.path.insert(0, ".")
-from maskedsst_b200 import ops
-from tests.test_gpu_components import ref_attention
-from tests.helpers import rel_l2
-torch.manual_seed(0)
-for n_seq, N, inner, H in [(10, 64, 1, 8), (128, 5, 64, 8), (128, 20, 64, 8), (6, 22, 2, 4), (1, 1, 1, 1), (33, 64, 1, 3)]:
-    R, I = n_seq * N, H * 64
-    qkv = torch.randn(R, 3 * I).bfloat16(); w = torch.randn(R, I).bfloat16()
-    a = qkv.double().requires_grad_(True)
-    want = ref_attention(a, n_seq, N, inner, H, 64); (want * w.double()).sum().backward()
-    b = qkv.cuda().requires_grad_(True)
-    got = ops.attention(b, n_seq=n_seq, N=N, inner=inner, heads=H, dim_head=64)
-    (got.float() * w.cuda().float()).sum().backward()
-    assert rel_l2(got, want) < 6e-3 and rel_l2(b.grad, a.grad) < 1.5e-2, (n_seq, N, rel_l2(got, want))
-# dropout: the backward kernel must regenerate the forward's mask -> gradient of sum(out) w.r.t. V equals column sums of P~
-qkv = torch.randn(4 * 64, 3 * 128).bfloat16().cuda().requires_grad_(True)
-o1 = ops.attention(qkv, n_seq=4, N=64, heads=2, dim_head=64, drop_p=0.3, seed=11, site=3)
-o2 = ops.attention(qkv, n_seq=4, N=64, heads=2, dim_head=64, drop_p=0.3, seed=11, site=3)
-assert torch.equal(o1, o2)
-print("TC_OK")
-'''
-    env = dict(os.environ, MSST_ATTN_TC="1")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0 and "TC_OK" in r.stdout, r.stdout + r.stderr
-
-
-def test_tcgen05_attention_backward_matches_mma_sync_kernel():
-    """The default backward for contiguous tiles (spatial stack) is the tcgen05 / TMEM kernel (attention_tc.cu); the mma.sync
-    kernel (MSST_ATTN_BWD_TC=0, also the spectral-stack kernel) must give the same gradients -- with dropout on, which only
-    holds if both regenerate exactly the forward's mask."""
+def test_tcgen05_attention_kernels_match_mma_sync_kernels():
+    """Default attention for packed short sequences (both transformer stacks) = the tcgen05 / TMEM kernels (attention_tc.cu).
+    The mma.sync kernels (MSST_ATTN_TC=0 / MSST_ATTN_BWD_TC=0; also the long-sequence path's building blocks) must give the same
+    outputs and gradients -- with dropout on, which only holds if all four kernels regenerate exactly the same mask."""
     import os, subprocess, sys, tempfile
     code = r'''
 import sys, torch
@@ -168,13 +135,14 @@ sys.path.insert(0, ".")
 from maskedsst_b200 import ops
 torch.manual_seed(3)
 out = {}
-for k, (n_seq, N, H, p) in enumerate([(40, 64, 8, 0.3), (33, 64, 3, 0.0), (9, 32, 2, 0.2), (7, 16, 8, 0.1), (300, 64, 8, 0.1)]):
+for k, (n_seq, N, inner, H, p) in enumerate([(40, 64, 1, 8, 0.3), (33, 64, 1, 3, 0.0), (9, 32, 1, 2, 0.2), (7, 16, 1, 8, 0.1), (300, 64, 1, 8, 0.1),
+                                             (128, 5, 64, 8, 0.1), (192, 20, 64, 8, 0.1), (6, 22, 2, 4, 0.25), (5, 22, 1, 2, 0.2), (1, 1, 1, 1, 0.0)]):
     R, I = n_seq * N, H * 64
     qkv = torch.randn(R, 3 * I).bfloat16().cuda().requires_grad_(True)
     w = torch.randn(R, I).bfloat16().cuda()
-    o = ops.attention(qkv, n_seq=n_seq, N=N, heads=H, dim_head=64, drop_p=p, seed=11, site=3)
+    o = ops.attention(qkv, n_seq=n_seq, N=N, inner=inner, heads=H, dim_head=64, drop_p=p, seed=11, site=3)
     (o.float() * w.float()).sum().backward()
-    out[k] = qkv.grad.float().cpu()
+    out[k] = (o.detach().float().cpu(), qkv.grad.float().cpu())
 torch.save(out, sys.argv[1])
 '''
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -182,12 +150,13 @@ torch.save(out, sys.argv[1])
     with tempfile.TemporaryDirectory() as td:
         for flag in ("1", "0"):
             path = os.path.join(td, f"g{flag}.pt")
-            r = subprocess.run([sys.executable, "-c", code, path], cwd=root, env=dict(os.environ, MSST_ATTN_BWD_TC=flag),
+            r = subprocess.run([sys.executable, "-c", code, path], cwd=root, env=dict(os.environ, MSST_ATTN_TC=flag, MSST_ATTN_BWD_TC=flag),
                                capture_output=True, text=True, timeout=600)
             assert r.returncode == 0, r.stdout + r.stderr
             res[flag] = torch.load(path)
     for k in res["1"]:
-        a, b = res["1"][k], res["0"][k]
-        assert torch.isfinite(a).all()
-        # same mask + same bf16 roundings of P~ / dS: only the fp32 accumulation order differs
-        assert rel_l2(a, b) < 2e-3, (k, rel_l2(a, b))
+        (o1, g1), (o0, g0) = res["1"][k], res["0"][k]
+        assert torch.isfinite(o1).all() and torch.isfinite(g1).all()
+        # same mask; the forward kernels round P at different points (before / after the 1/l normalisation): one bf16 ulp
+        assert rel_l2(o1, o0) < 6e-3, (k, rel_l2(o1, o0))
+        assert rel_l2(g1, g0) < 8e-3, (k, rel_l2(g1, g0))
