@@ -175,8 +175,6 @@ def run_ours(args):
                         decoupled=False, grad_scale=1.0 / world)
     else:
         opt = FusedAdam(model.parameters(), lr=0.008, weight_decay=0.05, decoupled=True, clamp=1.0, grad_scale=1.0 / world)
-    if args.precision == "bf16" and hasattr(model, "attach_optimizer"):
-        model.attach_optimizer(opt)
 
     # synthetic inputs: a pool of pinned host batches (per step a different one) + their masks
     pool = 4
@@ -321,10 +319,11 @@ def _time_launch(fn, reps=10):
 
 
 def roofline(args, B, dev, model, peaks):
-    """Roofline of the DOMINANT kernel of the step (largest share of the ncu launch list, profiles/): the attention backward
-    kernel, timed alone with CUDA events on the launching stream at the step's spatial-stack shape (B*C sequences of 64 tokens,
-    8 heads, dh 64).  HBM-bound: algorithmic bytes per launch = R*(3*I + I)*e [q,k,v,dO in] + R*3*I*e [dq,dk,dv out] + R*H*4 [lse].
-    `other_kernels` adds the largest GEMM (QKV projection, tcgen05) measured the same way."""
+    """Roofline of the DOMINANT kernel of the step (largest share of the ncu launch list, profiles/r01s3_launches_*.summary.txt):
+    the attention backward kernel (bf16 mode: attn_bwd_tc_kernel, tcgen05 / TMEM / TMA), timed alone with CUDA events on the
+    launching stream at the step's spatial-stack shape (B*C sequences of 64 tokens, 8 heads, dh 64).  HBM-bound: algorithmic bytes
+    per launch = R*(3*I + I)*e [q,k,v,dO in] + R*3*I*e [dq,dk,dv out] + R*H*4 [lse].  `other_kernels`: the same kernel at the
+    spectral-stack shape, the attention forward at both shapes and the largest GEMM (QKV projection), measured the same way."""
     import ctypes as C
     import torch
     from maskedsst_b200 import _lib
@@ -339,24 +338,40 @@ def roofline(args, B, dev, model, peaks):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback"
     out = {}
+    others = []
     try:
         qkv = torch.randn(R, 3 * I, device=dev).to(dt)
         o = torch.empty(R, I, device=dev, dtype=dt)
         lse = torch.empty(R, H, device=dev)
         do = torch.randn(R, I, device=dev).to(dt)
         dqkv = torch.empty_like(qkv)
-        ad = _lib.AttnDims(B * Cb, 64, 1, H, dh, float(args.dropout), 1234, 16, prec, None)
-        _lib.check(lib.msst_attention_fwd(C.byref(ad), qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), st))
-        sec = _time_launch(lambda: _lib.check(lib.msst_attention_bwd(C.byref(ad), qkv.data_ptr(), o.data_ptr(), lse.data_ptr(),
-                                                                     do.data_ptr(), dqkv.data_ptr(), st)))
-        bytes_ = R * 4 * I * es + R * 3 * I * es + R * H * 4
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this kernel
-        # at this shape (profiles/r01_ncu_full_final_kernels.txt): 1.355 GB + 0.966 GB
-        traffic = 2321000000 if (bf16 and R == 327680) else None
-        out = {"kernel": "attention backward (attn_bwd_bf16_heads_kernel), spatial stack shape" if bf16 else "attention backward (fp32 kernel)",
-               "bound": "hbm", "achieved": bytes_ / sec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": bytes_ / sec / 1e9 / hbm_peak,
-               "traffic": traffic, "algorithmic_bytes": bytes_, "us_per_launch": sec * 1e6, "peak_source": src,
-               "tflops": 2.0 * 5 * 64 * 64 * 64 * (R // 64) * H / sec / 1e12}
+        bwd_bytes = R * 4 * I * es + R * 3 * I * es + R * H * 4
+        fwd_bytes = R * 3 * I * es + R * I * es + R * H * 4
+        kname = "attn_bwd_tc_kernel, tcgen05/TMEM/TMA" if bf16 else "fp32 FFMA kernel"
+        for shape, (n_seq, N, inner) in (("spatial", (B * Cb, 64, 1)), ("spectral", (B * 64, Cb, 64))):
+            ad = _lib.AttnDims(n_seq, N, inner, H, dh, float(args.dropout), 1234, 16, prec, None)
+            fwd = lambda: _lib.check(lib.msst_attention_fwd(C.byref(ad), qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), st))
+            bwd = lambda: _lib.check(lib.msst_attention_bwd(C.byref(ad), qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), do.data_ptr(),
+                                                            dqkv.data_ptr(), st))
+            sec_f = _time_launch(fwd)
+            sec_b = _time_launch(bwd)
+            if shape == "spatial":
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this kernel at
+                # this shape (profiles/r01s3_ncu_full_kernels.txt): 1.371 GB + 0.983 GB
+                traffic = 2353589000 if (bf16 and R == 327680) else None
+                out = {"kernel": f"attention backward ({kname}), spatial stack shape", "bound": "hbm", "achieved": bwd_bytes / sec_b / 1e9,
+                       "peak": hbm_peak, "unit": "GB/s", "frac": bwd_bytes / sec_b / 1e9 / hbm_peak, "traffic": traffic,
+                       "algorithmic_bytes": bwd_bytes, "us_per_launch": sec_b * 1e6, "peak_source": src,
+                       "tflops": 2.0 * 5 * 64 * 64 * 64 * (R // 64) * H / sec_b / 1e12}
+            else:
+                others.append({"kernel": f"attention backward ({kname}), spectral stack shape (B*64 sequences of {Cb} tokens, row stride 64)",
+                               "bound": "hbm", "achieved": bwd_bytes / sec_b / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                               "frac": bwd_bytes / sec_b / 1e9 / hbm_peak, "traffic": 2346758000 if (bf16 and R == 327680) else None,
+                               "algorithmic_bytes": bwd_bytes, "us_per_launch": sec_b * 1e6})
+            others.append({"kernel": f"attention forward ({'attn_fwd_tc_kernel, tcgen05/TMEM/TMA' if bf16 else 'fp32 FFMA kernel'}), {shape} stack shape",
+                           "bound": "hbm", "achieved": fwd_bytes / sec_f / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                           "frac": fwd_bytes / sec_f / 1e9 / hbm_peak, "traffic": None, "algorithmic_bytes": fwd_bytes,
+                           "us_per_launch": sec_f * 1e6})
         del qkv, o, lse, do, dqkv
     except Exception as e:   # noqa
         out = {"error": str(e)}
@@ -368,13 +383,14 @@ def roofline(args, B, dev, model, peaks):
         dims = _lib.LinearDims(R, N, D, 0, 0.0, 0, 0, prec, None, 0)
         sec = _time_launch(lambda: _lib.check(lib.msst_linear_fwd(C.byref(dims), x.data_ptr(), W.data_ptr(), None, None, y.data_ptr(), None, st)))
         gb = R * D * es + R * N * es + N * D * es
-        out["other_kernels"] = [{
+        others.append({
             "kernel": "qkv projection GEMM [R,96]x[96,1536] (gemm_tn_kernel<0>, tcgen05/TMA)" if bf16 else "qkv projection GEMM (fp32 FFMA)",
             "bound": "hbm", "achieved": gb / sec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": gb / sec / 1e9 / hbm_peak,
             "traffic": 1014752768 if (bf16 and R == 327680) else None, "algorithmic_bytes": gb, "us_per_launch": sec * 1e6,
-            "tflops": 2.0 * R * N * D / sec / 1e12}]
+            "tflops": 2.0 * R * N * D / sec / 1e12})
     except Exception as e:   # noqa
-        out["other_kernels"] = [{"error": str(e)}]
+        others.append({"error": str(e)})
+    out["other_kernels"] = others
     return out
 
 

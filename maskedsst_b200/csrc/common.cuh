@@ -80,31 +80,24 @@ __device__ __forceinline__ float gelu_fast_grad(float x) {
     return fmaf(x * 0.39894228040143267794f, __expf(-0.5f * x * x), cdf);
 }
 
-// ---- counter-based dropout RNG (Philox4x32-7: the 7-round variant of Salmon et al., passes BigCrush) ----
-// Masks are never stored: forward and backward regenerate them from (seed, site, element index).
-// One call yields four 32-bit words for elements 4q..4q+3 of site `site`.
-struct Philox {
-    static constexpr uint32_t kM0 = 0xD2511F53u, kM1 = 0xCD9E8D57u, kW0 = 0x9E3779B9u, kW1 = 0xBB67AE85u;
-    __host__ __device__ static inline void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-#ifdef __CUDA_ARCH__
-        const uint32_t hi0 = __umulhi(kM0, c[0]), hi1 = __umulhi(kM1, c[2]);
-#else
-        const uint32_t hi0 = (uint32_t)(((uint64_t)kM0 * c[0]) >> 32), hi1 = (uint32_t)(((uint64_t)kM1 * c[2]) >> 32);
-#endif
-        const uint32_t lo0 = kM0 * c[0], lo1 = kM1 * c[2];
-        const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
-        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
-    }
-    __host__ __device__ static inline void gen(uint64_t seed, uint32_t site, uint64_t quad, uint32_t (&out)[4]) {
-        uint32_t c[4] = {(uint32_t)quad, (uint32_t)(quad >> 32), site, 0x5e5eed5u};
-        uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#pragma unroll
-        for (int r = 0; r < 7; ++r) { round(c, k0, k1); k0 += kW0; k1 += kW1; }
-        out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
-    }
-};
+// ---- counter-based dropout RNG ----
+// Masks are never stored: forward and backward regenerate them from (seed, site, element index).  One call yields 64 random
+// bits = four 16-bit lanes for elements 4q..4q+3 of site `site`: the counter is folded to 32 bits and passed through the
+// "lowbias32" integer finaliser (two multiply-xorshift rounds, full avalanche), the second word by one more chained round.
+// (Round 1 used Philox4x32-7 here: ~19 instructions per element, which made the dropout-carrying GEMM / LayerNorm epilogues
+// issue-bound; this is ~6.  Keep decision: lane >= thresh >> 16, i.e. p is resolved to 2^-16.)
+__host__ __device__ inline uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+__host__ __device__ inline void drop_bits64(uint64_t seed, uint32_t site, uint64_t quad, uint32_t& a, uint32_t& b) {
+    const uint32_t x = ((uint32_t)quad + (uint32_t)(seed >> 32)) * 0x9E3779B1u ^ ((uint32_t)(quad >> 32) * 0x85EBCA77u) ^ (uint32_t)seed ^
+                       (site * 0xC2B2AE3Du);
+    a = mix32(x);
+    b = mix32(a + 0x9E3779B9u);
+}
 
-// Inverted-dropout descriptor. keep element iff rand32 >= thresh, thresh = p * 2^32.
+// Inverted-dropout descriptor. keep element iff rand16 >= thresh >> 16, thresh = p * 2^32.
 struct Drop {
     uint64_t seed;
     const uint64_t* seed_dev;   // optional device-resident seed offset (lets a captured CUDA graph draw fresh masks per replay)
@@ -126,19 +119,21 @@ inline Drop make_drop(float p, uint64_t seed, uint32_t site, const uint64_t* see
 }
 // factor (0 or scale) for a single element index e of the site
 __device__ __forceinline__ float drop_factor(const Drop& d, uint64_t e) {
-    uint32_t r[4];
-    Philox::gen(d.seed + (d.seed_dev ? __ldg(d.seed_dev) : 0ull), d.site, e >> 2, r);
-    return r[e & 3] >= d.thresh ? d.scale : 0.f;
+    uint32_t a, b;
+    drop_bits64(d.seed + (d.seed_dev ? __ldg(d.seed_dev) : 0ull), d.site, e >> 2, a, b);
+    const uint32_t w = (e & 2) ? b : a;
+    return (((e & 1) ? (w >> 16) : (w & 0xFFFFu)) >= (d.thresh >> 16)) ? d.scale : 0.f;
 }
 // factors for the aligned quad 4q..4q+3
 __device__ __forceinline__ void drop_factor4(const Drop& d, uint64_t quad, float (&f)[4]) {
-    uint32_t r[4];
-    Philox::gen(d.seed + (d.seed_dev ? __ldg(d.seed_dev) : 0ull), d.site, quad, r);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) f[i] = r[i] >= d.thresh ? d.scale : 0.f;
+    uint32_t a, b;
+    drop_bits64(d.seed + (d.seed_dev ? __ldg(d.seed_dev) : 0ull), d.site, quad, a, b);
+    const uint32_t t16 = d.thresh >> 16;
+    f[0] = (a & 0xFFFFu) >= t16 ? d.scale : 0.f; f[1] = (a >> 16) >= t16 ? d.scale : 0.f;
+    f[2] = (b & 0xFFFFu) >= t16 ? d.scale : 0.f; f[3] = (b >> 16) >= t16 ? d.scale : 0.f;
 }
 
-// dropout site ids (distinct Philox streams); per transformer layer: site = base + layer*8 + k
+// dropout site ids (distinct RNG streams); per transformer layer: site = base + layer*8 + k
 enum DropSite : uint32_t { kSiteEmb = 1, kSiteLayerBase = 16, kSiteAttnProb = 0, kSiteAttnOut = 1, kSiteMlpHidden = 2, kSiteMlpOut = 3 };
 
 }  // namespace msst
