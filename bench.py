@@ -384,7 +384,7 @@ def roofline(args, B, dev, model, peaks):
         sec = _time_launch(lambda: _lib.check(lib.msst_linear_fwd(C.byref(dims), x.data_ptr(), W.data_ptr(), None, None, y.data_ptr(), None, st)))
         gb = R * D * es + R * N * es + N * D * es
         others.append({
-            "kernel": "qkv projection GEMM [R,96]x[96,1536] (gemm_tn_kernel<0>, tcgen05/TMA)" if bf16 else "qkv projection GEMM (fp32 FFMA)",
+            "kernel": "qkv projection GEMM [R,96]x[96,1536] (gemm_tn_kernel<7>: tcgen05 + TMA loads + TMA-store epilogue)" if bf16 else "qkv projection GEMM (fp32 FFMA)",
             "bound": "hbm", "achieved": gb / sec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": gb / sec / 1e9 / hbm_peak,
             "traffic": 1014752768 if (bf16 and R == 327680) else None, "algorithmic_bytes": gb, "us_per_launch": sec * 1e6,
             "tflops": 2.0 * R * N * D / sec / 1e12})

@@ -39,10 +39,12 @@ struct GemmTnParams {
     __nv_bfloat16* pre_act; const __nv_bfloat16* aux; int act; Drop drop;
     const float* ln_w; const float* ln_b; __nv_bfloat16* ln_out; float* ln_stats;   // MODE 6: fused LayerNorm of the output rows
     int debug;   // MSST_GEMM_DEBUG bits (profiling experiments only): 1 skip global stores, 2 skip epilogue body, 4 skip MMA issue
+    int stages;  // operand ring depth actually used (<= GB_STAGES; MODE 7 trades one stage for the output staging tiles)
 };
 
 struct alignas(8) GemmBars {
     uint64_t full[GB_STAGES], empty[GB_STAGES], tmem_full[2], tmem_empty[2];
+    uint64_t stg_full[2], stg_free[2];     // MODE 7: staging tiles written / read by the TMA store
     uint32_t tmem_base;
 };
 
@@ -199,19 +201,26 @@ __device__ __forceinline__ void epilogue_rows(const GemmTnParams& p, const float
 
 template <int MODE>
 __global__ void __launch_bounds__(GB_THREADS, 1)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmTnParams p) {
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_c,
+               const GemmTnParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t b_bytes = (uint32_t)p.block_n * GB_K * 2;
     const uint32_t stage_bytes = GB_A_BYTES + b_bytes;
-    GemmBars* bars = reinterpret_cast<GemmBars*>(smem + (size_t)GB_STAGES * stage_bytes);
+    // MODE 7 (bf16 store-only output through TMA): [stages][A|B] | 2 x [block_n/64][128 rows][128 B] staging | barriers
+    const uint32_t stg_bytes = (uint32_t)(p.block_n / 64) * GB_A_BYTES;
+    uint8_t* stg_base = smem + (size_t)p.stages * stage_bytes;
+    GemmBars* bars = reinterpret_cast<GemmBars*>(smem + (size_t)p.stages * stage_bytes + (MODE == 7 ? 2 * (size_t)stg_bytes : 0));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t num_tiles = p.tiles_m * p.tiles_n;
 
-    if (warp == 0 && elect_one()) { prefetch_tmap(&tma_a); prefetch_tmap(&tma_b); }
+    if (warp == 0 && elect_one()) { prefetch_tmap(&tma_a); prefetch_tmap(&tma_b); if (MODE == 7) prefetch_tmap(&tma_c); }
     if (warp == 1 && elect_one()) {
         for (int s = 0; s < GB_STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&bars->tmem_full[s], 1); mbar_init(&bars->tmem_empty[s], GB_EPI_WARPS); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bars->tmem_full[s], 1); mbar_init(&bars->tmem_empty[s], GB_EPI_WARPS);
+            mbar_init(&bars->stg_full[s], GB_EPI_WARPS); mbar_init(&bars->stg_free[s], 1);
+        }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(&bars->tmem_base, p.tmem_cols);
@@ -233,7 +242,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     mbar_arrive_expect_tx(&bars->full[stage], stage_bytes);
                     tma_load_2d(sa, &tma_a, &bars->full[stage], kb * GB_K, (int)(m_blk * GB_M));
                     tma_load_2d(sa + GB_A_BYTES, &tma_b, &bars->full[stage], kb * GB_K, n_blk * p.block_n);
-                    if (++stage == GB_STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -257,10 +266,60 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     for (int k = 0; k < ksteps; ++k)   // +32 B per UMMA_K step inside the 128 B swizzle row
                         umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, (kb | k) != 0);
                     umma_commit(&bars->empty[stage]);
-                    if (++stage == GB_STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&bars->tmem_full[acc]);
             }
+        }
+    } else if (MODE == 7 && warp == 3) {
+        // ===== MODE 7: TMA store of the staged bf16 output tiles (one 128 x 64 box per 64 columns) =====
+        if (elect_one()) {
+            int it = 0;
+            for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                const int n_blk = (int)(tile % p.tiles_n);
+                const int64_t m_blk = tile / p.tiles_n;
+                mbar_wait(&bars->stg_full[buf], (uint32_t)(it >> 1) & 1);
+                const uint8_t* src = stg_base + (size_t)buf * stg_bytes;
+                for (int t = 0; t < p.block_n / 64; ++t) {
+                    const int col = n_blk * p.block_n + t * 64;
+                    if (col < p.N) tma_store_2d(&tma_c, src + (size_t)t * GB_A_BYTES, col, (int)(m_blk * GB_M));
+                }
+                tma_store_commit();
+                if (it > 0) {   // the PREVIOUS tile's stores have read their staging buffer: hand it back (this tile's may still be in flight)
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    mbar_arrive(&bars->stg_free[buf ^ 1]);
+                }
+            }
+            tma_store_wait_read();
+        }
+    } else if (MODE == 7 && warp >= 4) {
+        // ===== MODE 7 epilogue: TMEM -> registers -> bf16 -> swizzled staging tile (thread = output row) =====
+        const int q = (warp - 4) & 3, sub = (warp - 4) >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t swz = (uint32_t)(row & 7);
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
+            uint8_t* dst = stg_base + (size_t)acc * stg_bytes + (size_t)row * 128;
+            mbar_wait(&bars->tmem_full[acc], acc_phase);
+            if (it >= 2) mbar_wait(&bars->stg_free[acc], (uint32_t)((it - 2) >> 1) & 1);   // stores of tile it - 2 have read this buffer
+            tc_fence_after();
+            for (int c = sub; c < p.block_n / 32; c += GB_EPI_WARPS / 4) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n + c * 32), v);
+                tmem_ld_wait();
+                uint8_t* trow = dst + (size_t)(c >> 1) * GB_A_BYTES;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    *reinterpret_cast<uint4*>(trow + ((((uint32_t)((c & 1) * 4 + i)) ^ swz) << 4)) =
+                        make_uint4(pack_bf16(__uint_as_float(v[i * 8]), __uint_as_float(v[i * 8 + 1])), pack_bf16(__uint_as_float(v[i * 8 + 2]), __uint_as_float(v[i * 8 + 3])),
+                                   pack_bf16(__uint_as_float(v[i * 8 + 4]), __uint_as_float(v[i * 8 + 5])), pack_bf16(__uint_as_float(v[i * 8 + 6]), __uint_as_float(v[i * 8 + 7])));
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&bars->tmem_empty[acc]); mbar_arrive(&bars->stg_full[acc]); }
         }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> smem transpose -> coalesced global =====
@@ -270,11 +329,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // (fp32) or 32-byte (bf16) row segments instead of 32 scattered 16-byte pieces.
         constexpr int CH = gb_chunk(MODE), PITCH = CH + 4, LPR = CH / 4;   // lanes per row in the read-back phase
         const int q = (warp - 4) & 3, sub = (warp - 4) >> 2;
-        float* stg = reinterpret_cast<float*>(smem + (size_t)GB_STAGES * stage_bytes + 256) + (size_t)(warp - 4) * (32 * PITCH);
+        float* stg = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes + 256) + (size_t)(warp - 4) * (32 * PITCH);
         const int sub_r = lane / LPR, c4 = (lane % LPR) * 4;
         // MODE 6: finished fp32 rows of this TMEM lane quarter, [32 rows][block_n + 4]
         const int rb_pitch = p.block_n + 4;
-        float* rowbuf = reinterpret_cast<float*>(smem + (size_t)GB_STAGES * stage_bytes + 256 + gb_epi_smem(MODE)) + (size_t)q * 32 * rb_pitch;
+        float* rowbuf = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes + 256 + gb_epi_smem(MODE)) + (size_t)q * 32 * rb_pitch;
         float4 lnw4 = make_float4(0.f, 0.f, 0.f, 0.f), lnb4 = lnw4;
         if (MODE == 6 && lane * 4 < p.N) { lnw4 = *reinterpret_cast<const float4*>(p.ln_w + lane * 4); lnb4 = *reinterpret_cast<const float4*>(p.ln_b + lane * 4); }
         int it = 0;
@@ -523,8 +582,22 @@ int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st) {
     }
     else if (vec && !a.out_fp32 && a.bias && a.act == 1 && a.pre_act && !a.residual) mode = 3;
     else if (vec && !a.out_fp32 && !a.bias && a.act == 2 && a.aux && !a.residual && !a.pre_act) mode = 4;
-    const size_t smem = (size_t)GB_STAGES * (GB_A_BYTES + (size_t)p.block_n * GB_K * 2) + 256 + gb_epi_smem(mode) + 1024 +
-                        (mode == 6 ? (size_t)4 * 32 * (p.block_n + 4) * 4 : 0);
+    // store-only bf16 output (QKV projection, dO data gradient): the epilogue packs rows into swizzled staging tiles and a
+    // dedicated warp streams them out with TMA stores (MSST_GEMM_TMA_STORE=0 selects the st.global epilogue, MODE 0)
+    CUtensorMap tc = ta;
+    p.stages = GB_STAGES;
+    if (mode == 0 && a.N % 64 == 0 && p.block_n == 256 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0) {   // wide outputs only (measured: no gain at N = 64)
+        static int use_tma_store = -1;
+        if (use_tma_store < 0) { const char* e = getenv("MSST_GEMM_TMA_STORE"); use_tma_store = e ? atoi(e) : 1; }
+        if (use_tma_store) {
+            if (int rc = make_tmap(&tc, a.out, a.M, a.N, a.N, GB_M)) return rc;
+            mode = 7;
+            p.stages = 2;
+        }
+    }
+    const size_t smem = mode == 7 ? (size_t)p.stages * (GB_A_BYTES + (size_t)p.block_n * GB_K * 2) + 2 * (size_t)(p.block_n / 64) * GB_A_BYTES + 256 + 1024
+                                  : (size_t)GB_STAGES * (GB_A_BYTES + (size_t)p.block_n * GB_K * 2) + 256 + gb_epi_smem(mode) + 1024 +
+                                        (mode == 6 ? (size_t)4 * 32 * (p.block_n + 4) * 4 : 0);
     const int64_t tiles = p.tiles_m * p.tiles_n;
     const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
     static PerDeviceOnce attr_set;
@@ -536,15 +609,17 @@ int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st) {
         MSST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         MSST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         MSST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MSST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     }
     switch (mode) {
-        case 0: gemm_tn_kernel<0><<<grid, GB_THREADS, smem, st>>>(ta, tb, p); break;
-        case 1: gemm_tn_kernel<1><<<grid, GB_THREADS, smem, st>>>(ta, tb, p); break;
-        case 2: gemm_tn_kernel<2><<<grid, GB_THREADS, smem, st>>>(ta, tb, p); break;
-        case 3: gemm_tn_kernel<3><<<grid, GB_THREADS, smem, st>>>(ta, tb, p); break;
-        case 4: gemm_tn_kernel<4><<<grid, GB_THREADS, smem, st>>>(ta, tb, p); break;
-        case 6: gemm_tn_kernel<6><<<grid, GB_THREADS, smem, st>>>(ta, tb, p); break;
-        default: gemm_tn_kernel<5><<<grid, GB_THREADS, smem, st>>>(ta, tb, p); break;
+        case 0: gemm_tn_kernel<0><<<grid, GB_THREADS, smem, st>>>(ta, tb, tc, p); break;
+        case 1: gemm_tn_kernel<1><<<grid, GB_THREADS, smem, st>>>(ta, tb, tc, p); break;
+        case 2: gemm_tn_kernel<2><<<grid, GB_THREADS, smem, st>>>(ta, tb, tc, p); break;
+        case 3: gemm_tn_kernel<3><<<grid, GB_THREADS, smem, st>>>(ta, tb, tc, p); break;
+        case 4: gemm_tn_kernel<4><<<grid, GB_THREADS, smem, st>>>(ta, tb, tc, p); break;
+        case 6: gemm_tn_kernel<6><<<grid, GB_THREADS, smem, st>>>(ta, tb, tc, p); break;
+        case 7: gemm_tn_kernel<7><<<grid, GB_THREADS, smem, st>>>(ta, tb, tc, p); break;
+        default: gemm_tn_kernel<5><<<grid, GB_THREADS, smem, st>>>(ta, tb, tc, p); break;
     }
     MSST_LAUNCH_CHECK();
     return MSST_OK;
