@@ -13,7 +13,7 @@
  *   - return value: 0 = ok, otherwise an MSST_ERR_* code; msst_last_error() gives the message
  *   - token order t = c*S + s (spectral block major), patch vector order (p0 p1 p2), qkv rows q|k|v each
  *     head-major (h d)  -- reference vit_spatial_spectral.py:198,218,68-69
- *   - dropout masks are never stored: (seed, site, element index) -> Philox4x32-7; p = 0 disables;
+ *   - dropout masks are never stored: (seed, site, element index) -> counter hash (lowbias32, 16-bit lanes); p = 0 disables;
  *     `seed_dev` (optional device uint64) is added to the seed so a captured CUDA graph draws fresh masks per replay
  */
 #ifndef MSST_H_
