@@ -1,5 +1,5 @@
 // Small HBM-bound helpers of the bf16 path:
-//   cast_rows   : fp32|bf16 [M,N] -> (optional Philox dropout) -> bf16 copy (optional) + column sums (optional, bias grads)
+//   cast_rows   : fp32|bf16 [M,N] -> (optional counter-hash dropout) -> bf16 copy (optional) + column sums (optional, bias grads)
 //   weights_bf16: fp32 weight matrices -> bf16 copy and bf16 transposed copy (operands of the forward / data-gradient GEMMs)
 #include "common.cuh"
 #include "kernels.h"
@@ -7,7 +7,7 @@
 namespace msst {
 
 // One thread owns a fixed set of 4 consecutive columns: block = (N/4) x rows_per_block threads, grid-stride over rows,
-// so a Philox call serves one aligned quad and the column sums stay in registers until one flush per block.
+// so one RNG call serves one aligned quad and the column sums stay in registers until one flush per block.
 template <typename TIn>
 __global__ void cast_rows_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ y, float* __restrict__ colsum, int64_t M, int N,
                                  int rows_per_block, Drop drop) {

@@ -2,7 +2,7 @@
 //
 //   gemm_tn_kernel   C[M,N] = epilogue(A[M,K] . B[N,K]^T)        both operands K-major (row-major, K contiguous)
 //                    -> forward linears (A = activations, B = W) and data gradients (A = dY, B = W^T copy)
-//                    epilogue: +bias, GELU(erf) / GELU' (x aux), Philox dropout, +fp32 residual, bf16 or fp32 store
+//                    epilogue: +bias, GELU(erf) / GELU' (x aux), counter-hash dropout, +fp32 residual, bf16 or fp32 store
 //   gemm_wgrad_kernel  dW[N,K] += dY[M,N]^T . X[M,K]              both operands MN-major (the reduction dim M is the
 //                    row dim in memory), split over M across CTAs, fp32 red.global epilogue
 //
@@ -22,10 +22,10 @@ using namespace ptx;
 
 constexpr int GB_M = 128;          // UMMA M (rows of A per tile) -- accumulator row i lives in TMEM lane i
 constexpr int GB_K = 64;           // bf16 elements per k-block = 128 B = one SWIZZLE_128B row
-constexpr int GB_STAGES = 3;            // 3 x (16 KB A + <=32 KB B) + 36 KB epilogue staging < 227 KB
-constexpr int GB_EPI_WARPS = 16;      // 4 per TMEM lane quarter: the epilogue math (GELU, Philox) is the throughput limiter
+constexpr int GB_STAGES = 6;            // upper bound of the operand ring; the depth actually used (p.stages) is what fits next to the epilogue staging
+constexpr int GB_EPI_WARPS = 16;      // 4 per TMEM lane quarter: the epilogue math (GELU, dropout hash) is the throughput limiter
 constexpr int GB_THREADS = 128 + 32 * GB_EPI_WARPS;   // TMA, MMA, TMEM-alloc, spare + epilogue warps
-// accumulator columns per epilogue step: 16 for the math-heavy epilogues (GELU / Philox / residual: more warps busy on the
+// accumulator columns per epilogue step: 16 for the math-heavy epilogues (GELU / dropout / residual: more warps busy on the
 // N = 64 / 96 tiles), 32 for the store-only ones (whole 64/128-byte row segments per store instruction)
 __host__ __device__ constexpr int gb_chunk(int mode) { return (mode == 2 || mode == 3 || mode == 4 || mode == 6) ? 16 : 32; }
 __host__ __device__ constexpr int gb_epi_smem(int mode) { return GB_EPI_WARPS * 32 * (gb_chunk(mode) + 4) * 4; }
@@ -585,7 +585,15 @@ int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st) {
     // store-only bf16 output (QKV projection, dO data gradient): the epilogue packs rows into swizzled staging tiles and a
     // dedicated warp streams them out with TMA stores (MSST_GEMM_TMA_STORE=0 selects the st.global epilogue, MODE 0)
     CUtensorMap tc = ta;
-    p.stages = GB_STAGES;
+    {   // as many operand stages as fit (long-K data gradients keep more loads in flight), at least 3 worth of the old layout
+        const size_t stage_b = GB_A_BYTES + (size_t)p.block_n * GB_K * 2;
+        const size_t fixed = 256 + gb_epi_smem(mode) + 1024 + (mode == 6 ? (size_t)4 * 32 * (p.block_n + 4) * 4 : 0);
+        int st_fit = (int)((227 * 1024 - fixed) / stage_b);
+        if (st_fit > GB_STAGES) st_fit = GB_STAGES;
+        if (st_fit > p.num_kb + 1) st_fit = p.num_kb + 1 > 2 ? p.num_kb + 1 : 2;
+        MSST_REQUIRE(st_fit >= 2, "bf16 GEMM: shared memory budget");
+        p.stages = st_fit;
+    }
     if (mode == 0 && a.N % 64 == 0 && p.block_n == 256 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0) {   // wide outputs only (measured: no gain at N = 64)
         static int use_tma_store = -1;
         if (use_tma_store < 0) { const char* e = getenv("MSST_GEMM_TMA_STORE"); use_tma_store = e ? atoi(e) : 1; }
@@ -596,7 +604,7 @@ int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st) {
         }
     }
     const size_t smem = mode == 7 ? (size_t)p.stages * (GB_A_BYTES + (size_t)p.block_n * GB_K * 2) + 2 * (size_t)(p.block_n / 64) * GB_A_BYTES + 256 + 1024
-                                  : (size_t)GB_STAGES * (GB_A_BYTES + (size_t)p.block_n * GB_K * 2) + 256 + gb_epi_smem(mode) + 1024 +
+                                  : (size_t)p.stages * (GB_A_BYTES + (size_t)p.block_n * GB_K * 2) + 256 + gb_epi_smem(mode) + 1024 +
                                         (mode == 6 ? (size_t)4 * 32 * (p.block_n + 4) * 4 : 0);
     const int64_t tiles = p.tiles_m * p.tiles_n;
     const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);

@@ -17,7 +17,7 @@ _seed_counter = itertools.count(1)
 
 
 def next_seed() -> int:
-    """Fresh 64-bit Philox key per training forward, derived from torch's seed (torch.manual_seed reproducible)."""
+    """Fresh 64-bit dropout key per training forward, derived from torch's seed (torch.manual_seed reproducible)."""
     return (torch.initial_seed() * 0x9E3779B97F4A7C15 + next(_seed_counter) * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
 
 
