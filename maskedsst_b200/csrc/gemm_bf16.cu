@@ -28,7 +28,7 @@ constexpr int GB_THREADS = 128 + 32 * GB_EPI_WARPS;   // TMA, MMA, TMEM-alloc, s
 // accumulator columns per epilogue step: 16 for the math-heavy epilogues (GELU / dropout / residual: more warps busy on the
 // N = 64 / 96 tiles), 32 for the store-only ones (whole 64/128-byte row segments per store instruction)
 __host__ __device__ constexpr int gb_chunk(int mode) { return (mode == 2 || mode == 3 || mode == 4 || mode == 6) ? 16 : 32; }
-__host__ __device__ constexpr int gb_epi_smem(int mode) { return GB_EPI_WARPS * 32 * (gb_chunk(mode) + 4) * 4; }
+__host__ __device__ constexpr int gb_epi_smem(int mode) { return (mode == 7 || mode == 8) ? 0 : GB_EPI_WARPS * 32 * (gb_chunk(mode) + 4) * 4; }
 constexpr uint32_t GB_A_BYTES = GB_M * GB_K * 2;   // 16 KB
 
 struct GemmTnParams {
@@ -38,6 +38,7 @@ struct GemmTnParams {
     const float* bias; const float* residual; void* out; int out_fp32;
     __nv_bfloat16* pre_act; const __nv_bfloat16* aux; int act; Drop drop;
     const float* ln_w; const float* ln_b; __nv_bfloat16* ln_out; float* ln_stats;   // MODE 6: fused LayerNorm of the output rows
+    const float* lnb_x; const float* lnb_stats; float* lnb_dw; float* lnb_db; __nv_bfloat16* lnb_cast; float* lnb_colsum;   // MODE 8: fused LayerNorm backward
     int debug;   // MSST_GEMM_DEBUG bits (profiling experiments only): 1 skip global stores, 2 skip epilogue body, 4 skip MMA issue
     int stages;  // operand ring depth actually used (<= GB_STAGES; MODE 7 trades one stage for the output staging tiles)
 };
@@ -62,6 +63,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 //   2: fp32 out = acc + bias [dropout] + residual      (out-projection, MLP second linear)
 //   3: bf16 out = [dropout] gelu(acc + bias), pre_act = acc + bias   (MLP first linear)
 //   4: bf16 out = acc * gelu'(aux) [dropout]            (data-gradient through the MLP hidden layer)
+//   7: bf16 out through swizzled staging tiles + TMA stores (wide store-only outputs)
+//   8: fp32 out = LayerNorm-backward(acc) + residual, LN weight/bias gradients, optional bf16 dropout cast (see GemmBf16Args)
 //   6: MODE 2 + LayerNorm of the finished rows (bf16) + its statistics: the pre-norm of the NEXT sub-block is produced by
 //      the GEMM that finishes the residual stream row (needs the whole row in one tile: N == block_n <= 128)
 // residual (MODE 2) / GELU' argument (MODE 4) of this lane's 8 row segments, fetched BEFORE the accumulator is waited for:
@@ -321,6 +324,105 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             __syncwarp();
             if (lane == 0) { mbar_arrive(&bars->tmem_empty[acc]); mbar_arrive(&bars->stg_full[acc]); }
         }
+    } else if (MODE == 8 && warp >= 4) {
+        // ===== MODE 8 epilogue: the accumulator rows are dy of a LayerNorm -> LN backward in place of a dy round trip =====
+        // phase A: thread = row copies its TMEM row into rowbuf; phase B: warp `sub` of quarter q owns rows 8*sub..8*sub+7,
+        // lane -> 4 columns (same arithmetic as ln_bwd4_kernel), x / skip-gradient rows prefetched before the accumulator wait
+        const int q = (warp - 4) & 3, sub = (warp - 4) >> 2;
+        const int rb_pitch = p.block_n + 4;
+        float* rowbuf = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes + 256) + (size_t)q * 32 * rb_pitch;
+        const int c = lane * 4;
+        const bool act = c < p.N;
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 w4 = act ? *reinterpret_cast<const float4*>(p.ln_w + c) : z4;
+        const float ws[4] = {w4.x, w4.y, w4.z, w4.w};
+        const float inv_n = 1.f / (float)p.N;
+        float aw[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f}, ac[4] = {0.f, 0.f, 0.f, 0.f};
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
+            const int64_t row_base = tile * GB_M + q * 32;      // tiles_n == 1
+            const int64_t r0 = row_base + sub * 8;
+            float4 xv[8], av[8];
+            float mean[8], rstd[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const bool ok = r0 + k < p.M;
+                mean[k] = ok ? p.lnb_stats[2 * (r0 + k)] : 0.f; rstd[k] = ok ? p.lnb_stats[2 * (r0 + k) + 1] : 0.f;
+                xv[k] = (ok && act) ? *reinterpret_cast<const float4*>(p.lnb_x + (r0 + k) * p.N + c) : z4;
+            }
+            mbar_wait(&bars->tmem_full[acc], acc_phase);
+            tc_fence_after();
+            for (int ch = sub; ch < p.block_n / 32; ch += GB_EPI_WARPS / 4) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n + ch * 32), v);
+                tmem_ld_wait();
+                float* dst = rowbuf + lane * rb_pitch + ch * 32;
+#pragma unroll
+                for (int g8 = 0; g8 < 8; ++g8)
+                    *reinterpret_cast<float4*>(dst + g8 * 4) = make_float4(__uint_as_float(v[g8 * 4]), __uint_as_float(v[g8 * 4 + 1]),
+                                                                            __uint_as_float(v[g8 * 4 + 2]), __uint_as_float(v[g8 * 4 + 3]));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)   // skip-connection gradient rows (issued here: the TMEM registers are dead, x rows already landed)
+                av[k] = (r0 + k < p.M && act && p.residual) ? *reinterpret_cast<const float4*>(p.residual + (r0 + k) * p.N + c) : z4;
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int64_t r = r0 + k;
+                if (r >= p.M) break;
+                const float4 d4 = act ? *reinterpret_cast<const float4*>(rowbuf + (sub * 8 + k) * rb_pitch + c) : z4;
+                const float xs[4] = {xv[k].x, xv[k].y, xv[k].z, xv[k].w}, ds[4] = {d4.x, d4.y, d4.z, d4.w};
+                const float as[4] = {av[k].x, av[k].y, av[k].z, av[k].w};
+                float xh[4], g[4], c1 = 0.f, c2 = 0.f;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    xh[t] = act ? (xs[t] - mean[k]) * rstd[k] : 0.f;
+                    aw[t] += ds[t] * xh[t]; ab[t] += ds[t];
+                    g[t] = ds[t] * ws[t];
+                    c1 += g[t]; c2 += g[t] * xh[t];
+                }
+                c1 = warp_sum(c1) * inv_n; c2 = warp_sum(c2) * inv_n;
+                if (act) {
+                    float o[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) o[t] = rstd[k] * (g[t] - c1 - xh[t] * c2) + as[t];
+                    const int64_t off = r * p.N + c;
+                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = make_float4(o[0], o[1], o[2], o[3]);
+                    if (p.lnb_cast) {
+                        if (p.drop.on()) {
+                            float f[4];
+                            drop_factor4(p.drop, (uint64_t)off >> 2, f);
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) o[t] *= f[t];
+                        }
+                        *reinterpret_cast<uint2*>(p.lnb_cast + off) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) ac[t] += o[t];
+                    }
+                }
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");   // rowbuf is free for the next tile
+        }
+        // column sums of this CTA: 16 warps -> smem -> one atomic per column
+        asm volatile("bar.sync 5, 512;" ::: "memory");
+        float* red = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes + 256);   // [3][16][128], aliases rowbuf
+        const int ew = warp - 4;
+        if (act) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { red[(0 * 16 + ew) * 128 + c + t] = aw[t]; red[(1 * 16 + ew) * 128 + c + t] = ab[t]; red[(2 * 16 + ew) * 128 + c + t] = ac[t]; }
+        }
+        asm volatile("bar.sync 5, 512;" ::: "memory");
+        for (int f = threadIdx.x - 128; f < p.N; f += GB_EPI_WARPS * 32) {
+            float sw = 0.f, sb = 0.f, sc = 0.f;
+            for (int k = 0; k < 16; ++k) { sw += red[(0 * 16 + k) * 128 + f]; sb += red[(1 * 16 + k) * 128 + f]; sc += red[(2 * 16 + k) * 128 + f]; }
+            atomicAdd(p.lnb_dw + f, sw);
+            atomicAdd(p.lnb_db + f, sb);
+            if (p.lnb_colsum) atomicAdd(p.lnb_colsum + f, sc);
+        }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> smem transpose -> coalesced global =====
         // 16 warps: warp (4 + q + 4*sub) owns TMEM lane quarter q and the 16-column chunks c == sub (mod 4).
@@ -547,6 +649,12 @@ int make_tmap_bf16_4d(CUtensorMap* m, const void* base, const int64_t dims[4], c
     return MSST_OK;
 }
 
+// MODE 6 / 8: finished fp32 rows of the four TMEM lane quarters; MODE 8 re-uses the area for its final [3][16][128] column reduction
+static size_t gb_rowbuf_smem(int mode, int block_n) {
+    if (mode != 6 && mode != 8) return 0;
+    const size_t rb = (size_t)4 * 32 * (block_n + 4) * 4;
+    return (mode == 8 && rb < (size_t)3 * 16 * 128 * 4) ? (size_t)3 * 16 * 128 * 4 : rb;
+}
 static uint32_t pow2_cols(int c) { uint32_t v = 32; while ((int)v < c) v <<= 1; return v; }
 
 int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st) {
@@ -566,6 +674,7 @@ int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st) {
     p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.out_fp32 = a.out_fp32; p.pre_act = a.pre_act; p.aux = a.aux;
     p.act = a.act; p.drop = a.drop;
     p.ln_w = a.ln_w; p.ln_b = a.ln_b; p.ln_out = a.ln_out; p.ln_stats = a.ln_stats;
+    p.lnb_x = a.lnb_x; p.lnb_stats = a.lnb_stats; p.lnb_dw = a.lnb_dw; p.lnb_db = a.lnb_db; p.lnb_cast = a.lnb_cast; p.lnb_colsum = a.lnb_colsum;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MSST_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
     CUtensorMap ta, tb;
     if (int rc = make_tmap(&ta, a.A, a.M, a.K, a.K, GB_M)) return rc;
@@ -575,6 +684,11 @@ int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st) {
     const bool vec = (a.N % 4 == 0);
     if (vec && !a.pre_act && !a.bias && !a.residual && a.act == 0 && !a.drop.on()) mode = a.out_fp32 ? 1 : 0;
     else if (vec && a.out_fp32 && a.bias && a.residual && a.act == 0 && !a.pre_act) mode = 2;
+    if (a.lnb_x) {
+        MSST_REQUIRE(a.out_fp32 && !a.bias && !a.pre_act && a.act == 0 && !a.ln_out && p.tiles_n == 1 && a.N <= 128 && a.N % 4 == 0 && a.ln_w &&
+                     a.lnb_stats && a.lnb_dw && a.lnb_db, "bf16 GEMM: the fused LayerNorm-backward epilogue needs a plain fp32-out GEMM with N <= 128 (N=%d)", a.N);
+        mode = 8;
+    }
     if (a.ln_out) {
         MSST_REQUIRE(mode == 2 && p.tiles_n == 1 && a.N <= 128 && a.ln_w && a.ln_b && a.ln_stats,
                      "bf16 GEMM: the fused LayerNorm epilogue needs fp32 out + bias + residual and N <= 128 (N=%d)", a.N);
@@ -587,7 +701,7 @@ int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st) {
     CUtensorMap tc = ta;
     {   // as many operand stages as fit (long-K data gradients keep more loads in flight), at least 3 worth of the old layout
         const size_t stage_b = GB_A_BYTES + (size_t)p.block_n * GB_K * 2;
-        const size_t fixed = 256 + gb_epi_smem(mode) + 1024 + (mode == 6 ? (size_t)4 * 32 * (p.block_n + 4) * 4 : 0);
+        const size_t fixed = 256 + gb_epi_smem(mode) + 1024 + gb_rowbuf_smem(mode, p.block_n);
         int st_fit = (int)((227 * 1024 - fixed) / stage_b);
         if (st_fit > GB_STAGES) st_fit = GB_STAGES;
         if (st_fit > p.num_kb + 1) st_fit = p.num_kb + 1 > 2 ? p.num_kb + 1 : 2;
@@ -605,7 +719,7 @@ int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st) {
     }
     const size_t smem = mode == 7 ? (size_t)p.stages * (GB_A_BYTES + (size_t)p.block_n * GB_K * 2) + 2 * (size_t)(p.block_n / 64) * GB_A_BYTES + 256 + 1024
                                   : (size_t)p.stages * (GB_A_BYTES + (size_t)p.block_n * GB_K * 2) + 256 + gb_epi_smem(mode) + 1024 +
-                                        (mode == 6 ? (size_t)4 * 32 * (p.block_n + 4) * 4 : 0);
+                                        gb_rowbuf_smem(mode, p.block_n);
     const int64_t tiles = p.tiles_m * p.tiles_n;
     const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
     static PerDeviceOnce attr_set;
@@ -618,6 +732,7 @@ int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st) {
         MSST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         MSST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         MSST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MSST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     }
     switch (mode) {
         case 0: gemm_tn_kernel<0><<<grid, GB_THREADS, smem, st>>>(ta, tb, tc, p); break;
@@ -627,6 +742,7 @@ int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st) {
         case 4: gemm_tn_kernel<4><<<grid, GB_THREADS, smem, st>>>(ta, tb, tc, p); break;
         case 6: gemm_tn_kernel<6><<<grid, GB_THREADS, smem, st>>>(ta, tb, tc, p); break;
         case 7: gemm_tn_kernel<7><<<grid, GB_THREADS, smem, st>>>(ta, tb, tc, p); break;
+        case 8: gemm_tn_kernel<8><<<grid, GB_THREADS, smem, st>>>(ta, tb, tc, p); break;
         default: gemm_tn_kernel<5><<<grid, GB_THREADS, smem, st>>>(ta, tb, tc, p); break;
     }
     MSST_LAUNCH_CHECK();

@@ -32,6 +32,12 @@ struct GemmBf16Args {
     Drop drop;
     // optional fused LayerNorm of the finished output rows (fp32 out + bias + residual GEMMs with N <= 128):
     const float* ln_w; const float* ln_b; __nv_bfloat16* ln_out; float* ln_stats;
+    // optional fused LayerNorm BACKWARD of the output rows (plain fp32-out data-gradient GEMMs with N <= 128): the accumulator row
+    // is dy of a LayerNorm whose input rows were lnb_x (statistics lnb_stats, weight ln_w).  The GEMM then writes
+    //   out[r,:] = LN'(dy)[r,:] + residual[r,:]   (fp32; `residual` = gradient arriving over the skip connection)
+    // accumulates lnb_dw += sum_r dy*xhat, lnb_db += sum_r dy, and optionally emits lnb_cast = bf16(dropout(out)) (Drop = `drop`)
+    // with its column sums added to lnb_colsum -- i.e. layernorm_bwd() including its fused cast, without the dy round trip.
+    const float* lnb_x; const float* lnb_stats; float* lnb_dw; float* lnb_db; __nv_bfloat16* lnb_cast; float* lnb_colsum;
 };
 int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st);
 int gemm_wgrad_bf16(const __nv_bfloat16* dy, const __nv_bfloat16* x, float* dW, int64_t M, int N, int K, cudaStream_t st);

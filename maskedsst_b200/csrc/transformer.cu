@@ -10,6 +10,7 @@
 // The residual stream, LN statistics and lse are always fp32.
 #include "common.cuh"
 #include "kernels.h"
+#include <stdlib.h>
 
 namespace msst {
 
@@ -78,6 +79,16 @@ static Bf16Weights layer_weights(const TfLayout& L, char* ws, int l) {
     char* b = ws + L.w_base + L.wlayer_bytes * l;
     return {(bf16*)(b + L.o_wq), (bf16*)(b + L.o_wqT), (bf16*)(b + L.o_wo), (bf16*)(b + L.o_woT),
             (bf16*)(b + L.o_w1), (bf16*)(b + L.o_w1T), (bf16*)(b + L.o_w2), (bf16*)(b + L.o_w2T)};
+}
+
+// MSST_GEMM_LNB=1: LayerNorm backward fused into the epilogue of the data-gradient GEMM that produces its dy (gemm MODE 8).
+// Parity-tested, but OFF by default: measured 21.5 vs 21.1 ms/step -- the 16 epilogue warps (96 registers, one row buffer) hide
+// the x / skip-gradient load latency worse than the stand-alone kernel's 64 warps per SM, and the K = 1536 GEMM is otherwise
+// at 0.94 of the HBM peak.
+static bool lnb_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MSST_GEMM_LNB"); v = e ? atoi(e) : 0; }
+    return v != 0;
 }
 
 static GemmBf16Args gemm_args(const bf16* A, const bf16* B, int64_t M, int N, int K, void* out, int out_fp32) {
@@ -175,18 +186,38 @@ static int tf_bwd_bf16(const msst_tf_dims* d, const msst_layer_params* layers, c
         if (int rc = gemm_tn_bf16(a, st)) return rc;
         if (int rc = cast_rows_bf16(du, nullptr, gr.b1, R, M, none, st)) return rc;
         if (int rc = gemm_wgrad_bf16(du, (const bf16*)(lw + L.o_h2), gr.w1, R, M, D, st)) return rc;
-        if (int rc = gemm_tn_bf16(gemm_args(du, w.w1T, R, D, M, dh, 1), st)) return rc;
-        // LN2 backward -> dxa (fp32) + fused: dyb = bf16(dropout_attn_out(dxa)), db_out += colsum
-        if (int rc = layernorm_bwd(xmid, p.ln2_w, stats2, dh, dcur, dxa, gr.ln2_w, gr.ln2_b, R, D, st, dyb,
-                                   make_drop(d->drop_p, d->seed, site + kSiteAttnOut, d->seed_dev), gr.b_out)) return rc;
+        // LN2 backward -> dxa (fp32) + fused: dyb = bf16(dropout_attn_out(dxa)), db_out += colsum.  With fuse_lnb the LayerNorm
+        // backward runs in the epilogue of the data-gradient GEMM that produces its dy (no [R,D] fp32 round trip, one launch less)
+        const bool fuse_lnb = (D % 4 == 0 && D <= 128) && lnb_enabled();
+        if (fuse_lnb) {
+            GemmBf16Args b = gemm_args(du, w.w1T, R, D, M, dxa, 1);
+            b.residual = dcur; b.ln_w = p.ln2_w; b.lnb_x = xmid; b.lnb_stats = stats2; b.lnb_dw = gr.ln2_w; b.lnb_db = gr.ln2_b;
+            b.lnb_cast = dyb; b.lnb_colsum = gr.b_out; b.drop = make_drop(d->drop_p, d->seed, site + kSiteAttnOut, d->seed_dev);
+            if (int rc = gemm_tn_bf16(b, st)) return rc;
+        } else {
+            if (int rc = gemm_tn_bf16(gemm_args(du, w.w1T, R, D, M, dh, 1), st)) return rc;
+            if (int rc = layernorm_bwd(xmid, p.ln2_w, stats2, dh, dcur, dxa, gr.ln2_w, gr.ln2_b, R, D, st, dyb,
+                                       make_drop(d->drop_p, d->seed, site + kSiteAttnOut, d->seed_dev), gr.b_out)) return rc;
+        }
         // ---- attention branch ----
         if (int rc = gemm_wgrad_bf16(dyb, o, gr.w_out, R, D, I, st)) return rc;
         if (int rc = gemm_tn_bf16(gemm_args(dyb, w.woT, R, I, D, dO, 0), st)) return rc;
         msst_attn_dims ad{d->n_seq, d->N, d->inner, d->H, d->dh, d->drop_p, d->seed, site + kSiteAttnProb, d->prec, d->seed_dev};
         if (int rc = attention_bwd_bf16(&ad, qkv, o, lse, dO, dqkv, st)) return rc;
         if (int rc = gemm_wgrad_bf16(dqkv, (const bf16*)(lw + L.o_h1), gr.w_qkv, R, 3 * I, D, st)) return rc;
-        if (int rc = gemm_tn_bf16(gemm_args(dqkv, w.wqT, R, D, 3 * I, dh, 1), st)) return rc;
         float* dx = (l == 0) ? d_x_in : dxb;
+        if (fuse_lnb) {   // LN1 backward in the epilogue of the Wqkv data-gradient GEMM (+ the cast for layer l-1's MLP branch)
+            GemmBf16Args b = gemm_args(dqkv, w.wqT, R, D, 3 * I, dx, 1);
+            b.residual = dxa; b.ln_w = p.ln1_w; b.lnb_x = x; b.lnb_stats = stats1; b.lnb_dw = gr.ln1_w; b.lnb_db = gr.ln1_b;
+            if (l > 0) {
+                b.lnb_cast = dyb; b.lnb_colsum = grads[l - 1].b2; b.drop = make_drop(d->drop_p, d->seed, site - 8u + kSiteMlpOut, d->seed_dev);
+                dyb_ready = true;
+            }
+            if (int rc = gemm_tn_bf16(b, st)) return rc;
+            dcur = dx;
+            continue;
+        }
+        if (int rc = gemm_tn_bf16(gemm_args(dqkv, w.wqT, R, D, 3 * I, dh, 1), st)) return rc;
         // LN1 backward -> dx (fp32) + fused for the next iteration (layer l-1): dyb = bf16(dropout_mlp_out(dx)), db2(l-1)
         if (l > 0) {
             if (int rc = layernorm_bwd(x, p.ln1_w, stats1, dh, dxa, dx, gr.ln1_w, gr.ln1_b, R, D, st, dyb,
