@@ -160,3 +160,42 @@ torch.save(out, sys.argv[1])
         # same mask; the forward kernels round P at different points (before / after the 1/l normalisation): one bf16 ulp
         assert rel_l2(o1, o0) < 6e-3, (k, rel_l2(o1, o0))
         assert rel_l2(g1, g0) < 8e-3, (k, rel_l2(g1, g0))
+
+
+def test_fused_layernorm_backward_epilogue_opt_in():
+    """gemm MODE 8 (MSST_GEMM_LNB=1: LayerNorm backward inside the data-gradient GEMM epilogue) is off by default (slower);
+    it must still produce the same gradients as the stand-alone LayerNorm-backward kernels, dropout on."""
+    import os, subprocess, sys, tempfile
+    code = r'''
+import sys, torch
+sys.path.insert(0, ".")
+import maskedsst_b200 as M
+from oracle import maskedsst_oracle as O
+from tests.test_gpu_parity import make_encoder
+torch.manual_seed(0)
+spec = O.Spec(**O.HOUSTON, depth=2)
+m = M.SimMIMSpatialSpectral(encoder=make_encoder(spec, dropout=0.1), masking_ratio=0.7, mask_patch_size=4, tube_masking=True,
+                            to_pixels_per_spectral_block=True).train()
+m.load_state_dict(O.synthetic_state_dict(spec, seed=4, simmim=True))
+m.encoder.precision = "bf16"
+m.cuda()
+x = O.synthetic_cube(spec, 6, seed=4, zero_pad_bands=2).cuda()
+import numpy as np
+np.random.seed(0)
+loss = m(x)
+loss.backward()
+torch.save({"loss": loss.detach().cpu(), **{k: p.grad.float().cpu() for k, p in m.named_parameters() if p.grad is not None}}, sys.argv[1])
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    with tempfile.TemporaryDirectory() as td:
+        for flag in ("1", "0"):
+            path = os.path.join(td, f"g{flag}.pt")
+            r = subprocess.run([sys.executable, "-c", code, path], cwd=root, env=dict(os.environ, MSST_GEMM_LNB=flag),
+                               capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stdout + r.stderr
+            res[flag] = torch.load(path)
+    assert torch.equal(res["1"]["loss"], res["0"]["loss"])
+    for k, v in res["0"].items():
+        if k != "loss" and float(v.norm()) > 1e-9:
+            assert rel_l2(res["1"][k], v) < 2e-3, (k, rel_l2(res["1"][k], v))
