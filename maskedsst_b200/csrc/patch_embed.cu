@@ -144,8 +144,13 @@ patch_embed_bwd_kernel(EmbedGeom g, int n_wb, const float* __restrict__ img, con
     constexpr int TPW = kTok / 8;
 
     float bj[NJ], pw[NJ];
-    float a_postw[NJ], a_postb[NJ], a_bias[NJ], a_mt[NJ], a_pos[TPW][NJ], a_W[NJ][PMAX];
-    float a_prew[PMAX], a_preb[PMAX];
+    // a_G[f][p] = sum_tok dy[tok,f] * xhat[tok,p].  Everything downstream of dy is linear in it, so the per-token work stops here:
+    //   dW[f,p]   = pre_w[p] * G[f,p] + pre_b[p] * dbias[f]            (h = xhat * pre_w + pre_b)
+    //   dpre_w[p] = sum_f W[f,p] * G[f,p],   dpre_b[p] = sum_f W[f,p] * dbias[f]
+    // are formed once per CTA at the flush (no dh = W^T dy GEMV + 10 warp reductions per token).  Only the PatchEmbed/SimMIM
+    // target gradient d_patches_ln enters the pre-norm gradients directly: lane p accumulates it (a_plw / a_plb).
+    float a_postw[NJ], a_postb[NJ], a_bias[NJ], a_mt[NJ], a_pos[TPW][NJ], a_G[NJ][PMAX];
+    float a_plw = 0.f, a_plb = 0.f;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
         const int f = lane + 32 * j;
@@ -154,10 +159,8 @@ patch_embed_bwd_kernel(EmbedGeom g, int n_wb, const float* __restrict__ img, con
 #pragma unroll
         for (int k = 0; k < TPW; ++k) a_pos[k][j] = 0.f;
 #pragma unroll
-        for (int p = 0; p < PMAX; ++p) a_W[j][p] = 0.f;
+        for (int p = 0; p < PMAX; ++p) a_G[j][p] = 0.f;
     }
-#pragma unroll
-    for (int p = 0; p < PMAX; ++p) a_prew[p] = a_preb[p] = 0.f;
 
     for (int b = blockIdx.y; b < g.B; b += gridDim.y) {
         // this warp's 8 token gradients + mask bytes are fetched up front: their DRAM latency overlaps the slab load / pre-norm
@@ -188,12 +191,15 @@ patch_embed_bwd_kernel(EmbedGeom g, int n_wb, const float* __restrict__ img, con
                 a_pos[k][j] += dt[j];
             }
             const bool masked = masked_all[k];
+            if (d_patches_ln && lane < P) {   // gradient that reaches the LayerNormed patches directly (PatchEmbed SimMIM target)
+                const float dl = d_patches_ln[row * P + lane];
+                a_plw = fmaf(dl, xs[tok * ld + lane], a_plw);
+                a_plb += dl;
+            }
             if (masked) {
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) a_mt[j] += dt[j];
-                if (!d_patches_ln) continue;
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) dt[j] = 0.f;   // embedding path gets no token gradient
+                continue;                                   // embedding path gets no token gradient
             }
             float y[NJ], sum = 0.f;
 #pragma unroll
@@ -227,17 +233,9 @@ patch_embed_bwd_kernel(EmbedGeom g, int n_wb, const float* __restrict__ img, con
 #pragma unroll
             for (int p = 0; p < PMAX; ++p) {
                 if (p < P) {
-                    const float hv = hs[tok * ld + p];
-                    float dh = 0.f;
+                    const float xh = xs[tok * ld + p];
 #pragma unroll
-                    for (int j = 0; j < NJ; ++j) {
-                        a_W[j][p] = fmaf(dy[j], hv, a_W[j][p]);
-                        dh = fmaf(Ws[(lane + 32 * j) * ld + p], dy[j], dh);
-                    }
-                    dh = warp_sum(dh);
-                    if (d_patches_ln) dh += d_patches_ln[row * P + p];
-                    a_prew[p] = fmaf(dh, xs[tok * ld + p], a_prew[p]);
-                    a_preb[p] += dh;
+                    for (int j = 0; j < NJ; ++j) a_G[j][p] = fmaf(dy[j], xh, a_G[j][p]);
                 }
             }
         }
@@ -267,35 +265,52 @@ patch_embed_bwd_kernel(EmbedGeom g, int n_wb, const float* __restrict__ img, con
     flush_feat(a_postb, d_post_b);
     flush_feat(a_bias, d_bias + wb * D);
     if (d_mask_token) flush_feat(a_mt, d_mask_token);
+    // dW, dpre_w, dpre_b from G and dbias (see the accumulator comment); per column p: cross-warp sum of G[:,p] and dbias, then
+    // each feature thread adds its dW entry and its term of the two pre-norm sums (block-reduced, one atomic per CTA and p)
+    float prew_part[PMAX], preb_part[PMAX];
+#pragma unroll
+    for (int p = 0; p < PMAX; ++p) prew_part[p] = preb_part[p] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) red[warp * D + lane + 32 * j] = a_bias[j];
+    __syncthreads();
+    float dbias_f = 0.f;     // CTA-wide dbias of feature f = threadIdx.x (threads >= D idle)
+    if (threadIdx.x < D) for (int w = 0; w < 8; ++w) dbias_f += red[w * D + threadIdx.x];
 #pragma unroll
     for (int p = 0; p < PMAX; ++p) {
         if (p < P) {
-            float col[NJ];
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) col[j] = a_W[j][p];
             __syncthreads();
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) red[warp * D + lane + 32 * j] = col[j];
+            for (int j = 0; j < NJ; ++j) red[warp * D + lane + 32 * j] = a_G[j][p];
             __syncthreads();
-            for (int f = threadIdx.x; f < D; f += kThreads) {
-                float s = 0.f;
-                for (int w = 0; w < 8; ++w) s += red[w * D + f];
-                atomicAdd(d_W + ((int64_t)wb * D + f) * P + p, s);
+            if (threadIdx.x < D) {
+                const int f = threadIdx.x;
+                float G = 0.f;
+                for (int w = 0; w < 8; ++w) G += red[w * D + f];
+                atomicAdd(d_W + ((int64_t)wb * D + f) * P + p, fmaf(pre_w[p], G, pre_b[p] * dbias_f));
+                const float wfp = Ws[f * ld + p];
+                prew_part[p] = wfp * G;
+                preb_part[p] = wfp * dbias_f;
             }
         }
     }
-    __syncthreads();
-    if (lane == 0) {
+    // block-reduce the per-feature terms (D <= 128 <= kThreads features live in threads 0..D-1) + the direct d_patches_ln part
 #pragma unroll
-        for (int p = 0; p < PMAX; ++p) if (p < P) { red[warp * 2 * PMAX + p] = a_prew[p]; red[warp * 2 * PMAX + PMAX + p] = a_preb[p]; }
+    for (int p = 0; p < PMAX; ++p) {
+        if (p < P) {
+            float sw = warp_sum(prew_part[p]), sb = warp_sum(preb_part[p]);
+            __syncthreads();
+            if (lane == 0) { red[warp] = sw; red[8 + warp] = sb; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                float tw = 0.f, tb = 0.f;
+                for (int w = 0; w < 8; ++w) { tw += red[w]; tb += red[8 + w]; }
+                atomicAdd(d_pre_w + p, tw);
+                atomicAdd(d_pre_b + p, tb);
+            }
+        }
     }
-    __syncthreads();
-    for (int p = threadIdx.x; p < P; p += kThreads) {
-        float sw = 0.f, sb = 0.f;
-        for (int w = 0; w < 8; ++w) { sw += red[w * 2 * PMAX + p]; sb += red[w * 2 * PMAX + PMAX + p]; }
-        atomicAdd(d_pre_w + p, sw);
-        atomicAdd(d_pre_b + p, sb);
-    }
+    if (d_patches_ln && lane < P) { atomicAdd(d_pre_w + lane, a_plw); atomicAdd(d_pre_b + lane, a_plb); }
 }
 
 static int make_geom(const msst_embed_dims* d, const float* img, EmbedGeom& g) {
