@@ -68,7 +68,7 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 // bf16-mode variants: erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below bf16 resolution), ~3x fewer instructions
 __device__ __forceinline__ float erf_as(float x) {
     const float ax = fabsf(x);
-    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));   // rcp.approx (1 ulp): far inside the formula's own 1.5e-7
     float p = fmaf(1.061405429f, t, -1.453152027f);
     p = fmaf(p, t, 1.421413741f); p = fmaf(p, t, -0.284496736f); p = fmaf(p, t, 0.254829592f);
     const float r = 1.0f - p * t * __expf(-ax * ax);

@@ -40,6 +40,7 @@ struct GemmTnParams {
     const float* ln_w; const float* ln_b; __nv_bfloat16* ln_out; float* ln_stats;   // MODE 6: fused LayerNorm of the output rows
     const float* lnb_x; const float* lnb_stats; float* lnb_dw; float* lnb_db; __nv_bfloat16* lnb_cast; float* lnb_colsum;   // MODE 8: fused LayerNorm backward
     int debug;   // MSST_GEMM_DEBUG bits (profiling experiments only): 1 skip global stores, 2 skip epilogue body, 4 skip MMA issue
+    float* colsum;   // MODE 4, block_n <= 64: column sums of the (fp32, post-dropout) output rows += here (bias gradient of the hidden layer)
     int stages;  // operand ring depth actually used (<= GB_STAGES; MODE 7 trades one stage for the output staging tiles)
 };
 
@@ -90,7 +91,7 @@ __device__ __forceinline__ void epilogue_prefetch(const GemmTnParams& p, int64_t
 
 template <int MODE>
 __device__ __forceinline__ void epilogue_rows(const GemmTnParams& p, const float* stg, int64_t row_base, int col0, int sub_r, int c4,
-                                              const float4 (&pre)[gb_chunk(MODE) / 4], float* rowbuf, int rowbuf_pitch) {
+                                              const float4 (&pre)[gb_chunk(MODE) / 4], float* rowbuf, int rowbuf_pitch, float (&csum)[4]) {
     constexpr int ITER = gb_chunk(MODE) / 4, RPI = 128 / gb_chunk(MODE), PITCH = gb_chunk(MODE) + 4;
     if (MODE == 0 && (p.N & 7) == 0) {
         // store-only bf16 epilogue: lane -> 8 consecutive columns (one 16-byte store), 4 lanes per row, 8 rows per instruction
@@ -144,6 +145,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmTnParams& p, const float
 #pragma unroll
                 for (int t = 0; t < 4; ++t) f[t] *= d4[t];
             }
+            if (MODE == 4) { csum[0] += f[0]; csum[1] += f[1]; csum[2] += f[2]; csum[3] += f[3]; }
             if (MODE == 2 || MODE == 6) { f[0] += pre[i].x; f[1] += pre[i].y; f[2] += pre[i].z; f[3] += pre[i].w; }
             if (MODE == 6) *reinterpret_cast<float4*>(rowbuf + rr * rowbuf_pitch + col) = make_float4(f[0], f[1], f[2], f[3]);
             if (p.debug & 1) continue;
@@ -438,6 +440,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         float* rowbuf = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes + 256 + gb_epi_smem(MODE)) + (size_t)q * 32 * rb_pitch;
         float4 lnw4 = make_float4(0.f, 0.f, 0.f, 0.f), lnb4 = lnw4;
         if (MODE == 6 && lane * 4 < p.N) { lnw4 = *reinterpret_cast<const float4*>(p.ln_w + lane * 4); lnb4 = *reinterpret_cast<const float4*>(p.ln_b + lane * 4); }
+        float csum[4] = {0.f, 0.f, 0.f, 0.f};   // MODE 4: this lane's 4 output columns (fixed when block_n <= 64: one chunk per warp)
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
@@ -461,7 +464,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     *reinterpret_cast<float4*>(stg + lane * PITCH + g8 * 4) =
                         make_float4(__uint_as_float(v[g8 * 4]), __uint_as_float(v[g8 * 4 + 1]), __uint_as_float(v[g8 * 4 + 2]), __uint_as_float(v[g8 * 4 + 3]));
                 __syncwarp();
-                epilogue_rows<MODE>(p, stg, row_base, col0, sub_r, c4, pre, rowbuf, rb_pitch);
+                epilogue_rows<MODE>(p, stg, row_base, col0, sub_r, c4, pre, rowbuf, rb_pitch, csum);
             }
             if (first_chunk) { mbar_wait(&bars->tmem_full[acc], acc_phase); tc_fence_after(); }   // warp had no chunk in this tile
             tc_fence_before();
@@ -489,6 +492,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                                        pack_bf16(d2 * rstd * lnw4.z + lnb4.z, d3 * rstd * lnw4.w + lnb4.w));
                 }
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");   // rowbuf is free for the next tile
+            }
+        }
+        if (MODE == 4 && p.colsum) {
+            // lanes that share c4 (they differ in the row they served) -> one value per column group, then one atomic per column
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                float v = csum[t];
+                for (int o = LPR; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                const int col = sub * CH + c4 + t;
+                if (lane < LPR && col < p.N) atomicAdd(p.colsum + col, v);
             }
         }
     }
@@ -673,6 +686,7 @@ int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st) {
     p.tmem_cols = pow2_cols(2 * p.block_n);
     p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.out_fp32 = a.out_fp32; p.pre_act = a.pre_act; p.aux = a.aux;
     p.act = a.act; p.drop = a.drop;
+    p.colsum = nullptr;
     p.ln_w = a.ln_w; p.ln_b = a.ln_b; p.ln_out = a.ln_out; p.ln_stats = a.ln_stats;
     p.lnb_x = a.lnb_x; p.lnb_stats = a.lnb_stats; p.lnb_dw = a.lnb_dw; p.lnb_db = a.lnb_db; p.lnb_cast = a.lnb_cast; p.lnb_colsum = a.lnb_colsum;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MSST_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
@@ -696,6 +710,10 @@ int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st) {
     }
     else if (vec && !a.out_fp32 && a.bias && a.act == 1 && a.pre_act && !a.residual) mode = 3;
     else if (vec && !a.out_fp32 && !a.bias && a.act == 2 && a.aux && !a.residual && !a.pre_act) mode = 4;
+    if (a.colsum) {
+        MSST_REQUIRE(mode == 4 && p.tiles_n == 1 && p.block_n <= 64, "bf16 GEMM: the fused column sum needs the GELU' data-gradient epilogue with N <= 64 (N=%d)", a.N);
+        p.colsum = a.colsum;
+    }
     // store-only bf16 output (QKV projection, dO data gradient): the epilogue packs rows into swizzled staging tiles and a
     // dedicated warp streams them out with TMA stores (MSST_GEMM_TMA_STORE=0 selects the st.global epilogue, MODE 0)
     CUtensorMap tc = ta;

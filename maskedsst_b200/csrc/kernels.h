@@ -38,6 +38,8 @@ struct GemmBf16Args {
     // accumulates lnb_dw += sum_r dy*xhat, lnb_db += sum_r dy, and optionally emits lnb_cast = bf16(dropout(out)) (Drop = `drop`)
     // with its column sums added to lnb_colsum -- i.e. layernorm_bwd() including its fused cast, without the dy round trip.
     const float* lnb_x; const float* lnb_stats; float* lnb_dw; float* lnb_db; __nv_bfloat16* lnb_cast; float* lnb_colsum;
+    // optional (act == 2 data gradient with N <= 64): column sums of the output rows (before the bf16 rounding) += colsum
+    float* colsum;
 };
 int gemm_tn_bf16(const GemmBf16Args& a, cudaStream_t st);
 int gemm_wgrad_bf16(const __nv_bfloat16* dy, const __nv_bfloat16* x, float* dW, int64_t M, int N, int K, cudaStream_t st);

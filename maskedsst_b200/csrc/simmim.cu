@@ -27,16 +27,29 @@ __global__ void __launch_bounds__(DT) decode_fwd_kernel(DecGeom g, const float* 
                                                         float* __restrict__ pred, float* __restrict__ partial) {
     const int lane = threadIdx.x & 31;
     const int64_t total = (int64_t)g.B * g.nm;
-    for (int64_t it = (int64_t)blockIdx.x * (DT / 32) + (threadIdx.x >> 5); it < total; it += (int64_t)gridDim.x * (DT / 32)) {
-        const int b = (int)(it / g.nm);
-        const int t = (int)idx[it];
+    // the gather chain idx -> encoder row / target pixels is pure latency: the NEXT item's loads are issued before this item's math
+    const int64_t stride = (int64_t)gridDim.x * (DT / 32);
+    int64_t it = (int64_t)blockIdx.x * (DT / 32) + (threadIdx.x >> 5);
+    float e_n[NJ], tg_n = 0.f;
+    int t_n = 0;
+    auto fetch = [&](int64_t i) {
+        const int b = (int)(i / g.nm);
+        t_n = (int)idx[i];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) e_n[j] = enc[((int64_t)b * g.T + t_n) * g.D + lane + 32 * j];
+        tg_n = 0.f;
+        if (lane < g.P) tg_n = tgt_tok ? tgt_tok[((int64_t)b * g.T + t_n) * g.P + lane] : target_pixel(g, b, t_n, lane);
+    };
+    if (it < total) fetch(it);
+    for (; it < total; it += stride) {
+        const int t = t_n;
         const int blk = g.n_wb == 1 ? 0 : t / g.S;
         float e[NJ];
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) e[j] = enc[((int64_t)b * g.T + t) * g.D + lane + 32 * j];
+        for (int j = 0; j < NJ; ++j) e[j] = e_n[j];
         float tgb = 0.f;   // target_p - bias_p held by lane p
-        if (lane < g.P)
-            tgb = (tgt_tok ? tgt_tok[((int64_t)b * g.T + t) * g.P + lane] : target_pixel(g, b, t, lane)) - bias[blk * g.P + lane];
+        if (lane < g.P) tgb = tg_n - bias[blk * g.P + lane];
+        if (it + stride < total) fetch(it + stride);
         float mine = 0.f;  // lane p keeps dot product p
 #pragma unroll
         for (int p = 0; p < PMAX; ++p) {
@@ -120,17 +133,28 @@ __global__ void __launch_bounds__(DT) decode_bwd_kernel(DecGeom g, const float* 
             }
         }
     };
+    float e_n[NJ], tg_n = 0.f;
+    int t_n = 0;
+    auto fetch = [&](int64_t i) {     // next item's gather chain is issued before this item's math (see decode_fwd_kernel)
+        const int b = (int)(i / g.nm);
+        t_n = (int)idx[i];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) e_n[j] = enc[((int64_t)b * g.T + t_n) * g.D + lane + 32 * j];
+        tg_n = 0.f;
+        if (lane < g.P) tg_n = tgt_tok ? tgt_tok[((int64_t)b * g.T + t_n) * g.P + lane] : target_pixel(g, b, t_n, lane);
+    };
+    if (it0 < it1) fetch(it0);
     for (int64_t it = it0; it < it1; ++it) {
         const int b = (int)(it / g.nm);
-        const int t = (int)idx[it];
+        const int t = t_n;
         const int blk = g.n_wb == 1 ? 0 : t / g.S;
         if (blk != cur_blk) { flush(); cur_blk = blk; }
         float e[NJ], de[NJ];
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) { e[j] = enc[((int64_t)b * g.T + t) * g.D + lane + 32 * j]; de[j] = 0.f; }
+        for (int j = 0; j < NJ; ++j) { e[j] = e_n[j]; de[j] = 0.f; }
         float tgb = 0.f;   // lane p: target_p - bias_p (fetched before the reduction loop)
-        if (lane < g.P)
-            tgb = (tgt_tok ? tgt_tok[((int64_t)b * g.T + t) * g.P + lane] : target_pixel(g, b, t, lane)) - bias[blk * g.P + lane];
+        if (lane < g.P) tgb = tg_n - bias[blk * g.P + lane];
+        if (it + 1 < it1) fetch(it + 1);
 #pragma unroll
         for (int p = 0; p < PMAX; ++p) {
             if (p < g.P) {

@@ -183,8 +183,10 @@ static int tf_bwd_bf16(const msst_tf_dims* d, const msst_layer_params* layers, c
         if (int rc = gemm_wgrad_bf16(dyb, g, gr.w2, R, D, M, st)) return rc;
         GemmBf16Args a = gemm_args(dyb, w.w2T, R, M, D, du, 0);        // du = (dy . W2) * gelu'(u) * hidden-dropout
         a.aux = u; a.act = 2; a.drop = make_drop(d->drop_p, d->seed, site + kSiteMlpHidden, d->seed_dev);
+        const bool fuse_db1 = M <= 64 && M % 4 == 0;      // db1 = column sums of du, from the same epilogue
+        if (fuse_db1) a.colsum = gr.b1;
         if (int rc = gemm_tn_bf16(a, st)) return rc;
-        if (int rc = cast_rows_bf16(du, nullptr, gr.b1, R, M, none, st)) return rc;
+        if (!fuse_db1) { if (int rc = cast_rows_bf16(du, nullptr, gr.b1, R, M, none, st)) return rc; }
         if (int rc = gemm_wgrad_bf16(du, (const bf16*)(lw + L.o_h2), gr.w1, R, M, D, st)) return rc;
         // LN2 backward -> dxa (fp32) + fused: dyb = bf16(dropout_attn_out(dxa)), db_out += colsum.  With fuse_lnb the LayerNorm
         // backward runs in the epilogue of the data-gradient GEMM that produces its dy (no [R,D] fp32 round trip, one launch less)
