@@ -1,3 +1,4 @@
+"""Write-only vs read+write HBM bandwidth of the box (torch memset / copy of 1 GiB, CUDA events): the ceiling a write-heavy kernel can reach."""
 import torch
 x = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
 y = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
@@ -10,4 +11,3 @@ def t(f, n=10):
     return e0.elapsed_time(e1) / n * 1e3
 us = t(lambda: x.zero_()); print(f"memset 1 GiB: {us:.1f} us  {(1<<30)/us/1e3:.0f} GB/s (write only)")
 us = t(lambda: y.copy_(x)); print(f"copy 1 GiB: {us:.1f} us  {2*(1<<30)/us/1e3:.0f} GB/s (read+write)")
-us = t(lambda: x.sum(dtype=torch.int64)); print(f"read-reduce 1 GiB: {us:.1f} us  {(1<<30)/us/1e3:.0f} GB/s (read only)")
