@@ -637,6 +637,13 @@ int attention_fwd_bf16(const msst_attn_dims* d, const bf16* qkv, bf16* out, floa
         MSST_LAUNCH_CHECK();
         return MSST_OK;
     }
+    {   // N > 64: tcgen05 kernel (attention_tc.cu) from N = 512 on, where it beats the mma.sync kernel (318 vs 267 TF/s at N = 1024,
+        // 337 vs 278 at 4096; on par at 256).  MSST_ATTN_TC_LONG=1 forces it for every N > 64, =0 disables it.
+        static int use_tcl = -2;
+        if (use_tcl == -2) { const char* e = getenv("MSST_ATTN_TC_LONG"); use_tcl = e ? atoi(e) : -1; }
+        if ((use_tcl == 1 || (use_tcl == -1 && g.N >= 512)) && attention_fwd_tc_long_supported(g))
+            return attention_fwd_tc_long(g, qkv, out, lse, drop, st);
+    }
     {   // N > 64: 128-row query tiles, K/V streamed through a cp.async double buffer
         static PerDeviceOnce lattr;
         if (lattr.first()) {

@@ -742,4 +742,281 @@ int attention_fwd_tc(const AttnGeom& g, const bf16* qkv, bf16* out, float* lse, 
     return MSST_OK;
 }
 
+// =========================================================================================================
+// Long sequences (N > 64) forward on tcgen05 / TMEM: one work item = (sequence, head, 128-query tile), key tiles of 128
+// streamed through a 3-slot TMA ring.  Two passes over the keys instead of an online-softmax rescale of the TMEM accumulator:
+//   pass 1: S_j = Q K_j^T -> row max (all 16 softmax warps work on one S tile: thread = (row, 32 of its 128 columns))
+//   pass 2: S_j again, P~_j = dropout(exp2(S_j - max)) -> smem (double-buffered), O += P~_j V_j accumulates in TMEM over ALL
+//           key tiles (no correction step), row sums in registers; epilogue O / l -> staging -> TMA store.
+// The second Q K^T costs 1/3 more tensor work, which is idle anyway: the kernel is bound by the exponentials (MUFU).
+// Dropout pair indices are those of the mma.sync long kernels (64 x 64 tile coordinates), so the regular backward applies.
+// =========================================================================================================
+struct alignas(8) TclBars {
+    uint64_t q_full[2], q_empty[2], kv_full[3], kv_empty[3], s_full[2], s_free[2], p_full[2], p_free[2], o_full[2], o_free[2],
+             stg_full[2], stg_free[2];
+    uint32_t tmem_base;
+};
+// smem: Q [2][16 KB] | ring [3][K, V][16 KB] | P~ [2][2 chunks][16 KB] | O staging [16 KB] | row statistics exchange [4][128] | barriers
+constexpr size_t kTclSmem = 2 * TC_TILE + 3 * 2 * TC_TILE + 2 * 2 * TC_TILE + TC_TILE + 4 * 128 * sizeof(float) + sizeof(TclBars);
+
+__device__ __forceinline__ void tcl_item(const AttnGeom& g, int64_t item, int qtiles, int64_t& seq, int& h, int& qt) {
+    qt = (int)(item % qtiles); h = (int)((item / qtiles) % g.H); seq = item / ((int64_t)qtiles * g.H);
+}
+// TMA coordinates of rows [pos0, pos0 + 128) of sequence seq (see tcl_tmap)
+__device__ __forceinline__ void tcl_coords(const AttnGeom& g, int64_t seq, int pos0, int& c1, int& c2, int& c3) {
+    if (g.inner == 1) { c1 = pos0; c2 = (int)seq; c3 = 0; }
+    else { c1 = (int)(seq % g.inner); c2 = pos0; c3 = (int)(seq / g.inner); }
+}
+
+__global__ void __launch_bounds__(TCB_THREADS, 1)
+attn_fwd_tc_long_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_out, AttnGeom g,
+                        float* __restrict__ lse, Drop drop, int64_t n_items, int qtiles, int nk) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if (smem_u32(smem) & 1023u) __trap();
+    uint8_t* q_s = smem;                                    // [2][16 KB]
+    uint8_t* kv_s = q_s + 2 * TC_TILE;                      // [3][K | V][16 KB]
+    uint8_t* p_s = kv_s + 3 * 2 * TC_TILE;                  // [2][keys 0-63 | keys 64-127][16 KB]
+    uint8_t* stg_s = p_s + 2 * 2 * TC_TILE;
+    float* xch = reinterpret_cast<float*>(stg_s + TC_TILE); // [4 column quarters][128 rows]
+    TclBars* bars = reinterpret_cast<TclBars*>(xch + 4 * 128);
+    const int warp = threadIdx.x >> 5;
+    const int I = g.H * 64;
+
+    if (warp == 17 && elect_one()) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bars->q_full[s], 1); mbar_init(&bars->q_empty[s], 1); mbar_init(&bars->s_full[s], 1); mbar_init(&bars->s_free[s], 512);
+            mbar_init(&bars->p_full[s], 512); mbar_init(&bars->p_free[s], 1); mbar_init(&bars->o_full[s], 1); mbar_init(&bars->o_free[s], 512);
+            mbar_init(&bars->stg_full[s], 512); mbar_init(&bars->stg_free[s], 1);
+        }
+        for (int s = 0; s < 3; ++s) { mbar_init(&bars->kv_full[s], 1); mbar_init(&bars->kv_empty[s], 1); }
+        fence_barrier_init();
+    }
+    if (warp == 16) {
+        tmem_alloc(&bars->tmem_base, 512);
+        if (elect_one()) { prefetch_tmap(&tma_qkv); prefetch_tmap(&tma_out); }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+    const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0), idesc_o = make_idesc_bf16(128, 64, 0, 1);
+    const int64_t my_items = blockIdx.x < n_items ? (n_items - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+
+    if (warp == 16) {
+        // ===== TMA producer: Q once per item, then K_j (pass 1), then K_j + V_j (pass 2) through the ring =====
+        if (elect_one()) {
+            int ring = 0; uint32_t rph = 0;
+            for (int64_t n = 0; n < my_items; ++n) {
+                int64_t seq; int h, qt, c1, c2, c3;
+                tcl_item(g, blockIdx.x + n * gridDim.x, qtiles, seq, h, qt);
+                const int qs = (int)(n & 1);
+                mbar_wait(&bars->q_empty[qs], (uint32_t)((n >> 1) & 1) ^ 1);
+                tcl_coords(g, seq, qt * TC_ROWS, c1, c2, c3);
+                mbar_arrive_expect_tx(&bars->q_full[qs], TC_TILE);
+                tma_load_4d(q_s + (size_t)qs * TC_TILE, &tma_qkv, &bars->q_full[qs], h * 64, c1, c2, c3);
+                for (int pass = 0; pass < 2; ++pass)
+                    for (int j = 0; j < nk; ++j) {
+                        mbar_wait(&bars->kv_empty[ring], rph ^ 1);
+                        tcl_coords(g, seq, j * TC_ROWS, c1, c2, c3);
+                        uint8_t* dst = kv_s + (size_t)ring * 2 * TC_TILE;
+                        mbar_arrive_expect_tx(&bars->kv_full[ring], pass ? 2 * TC_TILE : TC_TILE);
+                        tma_load_4d(dst, &tma_qkv, &bars->kv_full[ring], I + h * 64, c1, c2, c3);
+                        if (pass) tma_load_4d(dst + TC_TILE, &tma_qkv, &bars->kv_full[ring], 2 * I + h * 64, c1, c2, c3);
+                        if (++ring == 3) { ring = 0; rph ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 17) {
+        // ===== MMA issuer.  Global step counter t over (item, pass, j); S of step t+1 is issued before the P~V of step t =====
+        if (elect_one()) {
+            const int64_t steps_per_item = 2 * (int64_t)nk, total = my_items * steps_per_item;
+            int64_t ts = 0, tp = 0;          // next S step / next step whose pass-2 work (P~ V) is to be issued or skipped
+            int ring_s = 0; uint32_t rph_s = 0; int ring_p = 0;
+            int64_t npv = 0;                 // pass-2 steps issued so far (P~ buffer = npv & 1)
+            while (tp < total) {
+                if (ts < total && ts <= tp + 1) {        // two S slots (a third measured slower: the softmax warps are the bottleneck)
+                    const int64_t n = ts / steps_per_item; const int rem = (int)(ts % steps_per_item);
+                    const int slot = (int)(ts & 1);
+                    bool ok = mbar_try_wait(&bars->s_free[slot], (uint32_t)((ts >> 1) & 1) ^ 1) && mbar_try_wait(&bars->kv_full[ring_s], rph_s);
+                    if (ok && rem == 0) ok = mbar_try_wait(&bars->q_full[n & 1], (uint32_t)(n >> 1) & 1);
+                    if (ok) {
+                        tc_fence_after();
+                        const uint64_t dq = make_smem_desc(smem_u32(q_s + (size_t)(n & 1) * TC_TILE), 16, 1024);
+                        const uint64_t dk = make_smem_desc(smem_u32(kv_s + (size_t)ring_s * 2 * TC_TILE), 16, 1024);
+                        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + slot * 128, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k != 0);
+                        umma_commit(&bars->s_full[slot]);
+                        if (rem < nk) umma_commit(&bars->kv_empty[ring_s]);      // pass 1: K is not needed again
+                        ++ts;
+                        if (++ring_s == 3) { ring_s = 0; rph_s ^= 1; }
+                    }
+                }
+                if (tp < ts) {
+                    const int64_t n = tp / steps_per_item; const int rem = (int)(tp % steps_per_item);
+                    if (rem < nk) { ++tp; if (++ring_p == 3) ring_p = 0; }       // pass-1 step: nothing to issue
+                    else {
+                        const int pb = (int)(npv & 1), os = (int)(n & 1), j = rem - nk;
+                        bool ok = mbar_try_wait(&bars->p_full[pb], (uint32_t)(npv >> 1) & 1);
+                        if (ok && j == 0) ok = mbar_try_wait(&bars->o_free[os], (uint32_t)((n >> 1) & 1) ^ 1);
+                        if (ok) {
+                            fence_proxy_async();
+                            tc_fence_after();
+                            const uint32_t pbase = smem_u32(p_s + (size_t)pb * 2 * TC_TILE);
+                            const uint64_t b_v = make_smem_desc(smem_u32(kv_s + (size_t)ring_p * 2 * TC_TILE + TC_TILE), TC_TILE, 1024);
+                            for (int k = 0; k < 8; ++k) {
+                                const uint64_t a = make_smem_desc(pbase + (k >> 2) * TC_TILE, 16, 1024) + (uint64_t)((k & 3) * 2);
+                                umma_bf16(tmem_base + 256 + os * 64, a, b_v + (uint64_t)(k * 128), idesc_o, (j | k) != 0);
+                            }
+                            umma_commit(&bars->kv_empty[ring_p]);
+                            umma_commit(&bars->p_free[pb]);
+                            if (j == nk - 1) { umma_commit(&bars->o_full[os]); umma_commit(&bars->q_empty[os]); }
+                            ++npv; ++tp;
+                            if (++ring_p == 3) ring_p = 0;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 18) {
+        // ===== TMA store of the staged O tile =====
+        if (elect_one()) {
+            for (int64_t n = 0; n < my_items; ++n) {
+                int64_t seq; int h, qt, c1, c2, c3;
+                tcl_item(g, blockIdx.x + n * gridDim.x, qtiles, seq, h, qt);
+                tcl_coords(g, seq, qt * TC_ROWS, c1, c2, c3);
+                mbar_wait(&bars->stg_full[n & 1], (uint32_t)(n >> 1) & 1);
+                tma_store_4d(&tma_out, stg_s, h * 64, c1, c2, c3);
+                tma_store_commit();
+                tma_store_wait_read();
+                mbar_arrive(&bars->stg_free[n & 1]);
+            }
+        }
+    } else if (warp < 16) {
+        // ===== 16 softmax warps on ONE S tile at a time: thread = (row r, column quarter cq) =====
+        const int cq = warp >> 2;
+        const int r = (warp & 3) * 32 + (threadIdx.x & 31);
+        const float sl2 = g.scale * 1.4426950408889634f;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t swz = (uint32_t)(r & 7);
+        const uint64_t seed = drop.seed + (drop.seed_dev ? __ldg(drop.seed_dev) : 0ull);
+        const uint32_t t16 = drop.thresh >> 16;
+        int64_t t = 0, npv = 0;
+        for (int64_t n = 0; n < my_items; ++n) {
+            int64_t seq; int h, qt;
+            tcl_item(g, blockIdx.x + n * gridDim.x, qtiles, seq, h, qt);
+            const int pos = qt * TC_ROWS + r;
+            const bool row_ok = pos < g.N;
+            float mx = -INFINITY, l = 0.f, sub = 0.f;
+            for (int pass = 0; pass < 2; ++pass) {
+                for (int j = 0; j < nk; ++j, ++t) {
+                    const int slot = (int)(t & 1);
+                    mbar_wait(&bars->s_full[slot], (uint32_t)(t >> 1) & 1);
+                    tc_fence_after();
+                    uint32_t a[32];
+                    tmem_ld_32x32(tmem_base + lane_base + slot * 128 + cq * 32, a);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    mbar_arrive(&bars->s_free[slot]);
+                    const int nvalid = g.N - j * TC_ROWS - cq * 32;            // this thread's columns 0 .. nvalid-1 are real keys
+                    if (pass == 0) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) if (c < nvalid) mx = fmaxf(mx, __uint_as_float(a[c]) * sl2);
+                    } else {
+                        uint32_t pk[16];
+                        // 64 x 64 tile coordinates of the mma.sync kernels: qt64 = 2*qt + r/64, kt64 = 2*j + cq/2, pair = (cq & 1)*16 + jj
+                        const uint64_t hidx = ((((uint64_t)seq * g.H + h) * g.tiles + (uint64_t)(2 * qt + (r >> 6))) * g.tiles + (uint64_t)(2 * j + (cq >> 1))) *
+                                                  (uint64_t)(TS * TS / 2) + (uint64_t)((r & 63) * 32 + (cq & 1) * 16);
+                        const uint32_t hash_lo = (uint32_t)hidx + (uint32_t)(seed >> 32);
+                        const uint32_t hash_hi = ((uint32_t)(hidx >> 32) * 0x85EBCA77u) ^ (uint32_t)seed ^ (drop.site * 0xC2B2AE3Du);
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) {
+                            float p0 = 2 * jj < nvalid ? ex2_approx(fmaf(__uint_as_float(a[2 * jj]), sl2, -sub)) : 0.f;
+                            float p1 = 2 * jj + 1 < nvalid ? ex2_approx(fmaf(__uint_as_float(a[2 * jj + 1]), sl2, -sub)) : 0.f;
+                            l += p0 + p1;
+                            if (drop.on()) {
+                                uint32_t x = (hash_lo + (uint32_t)jj) * 0x9E3779B1u ^ hash_hi;
+                                x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+                                p0 *= (x & 0xFFFFu) >= t16 ? drop.scale : 0.f;
+                                p1 *= (x >> 16) >= t16 ? drop.scale : 0.f;
+                            }
+                            pk[jj] = pack_bf(p0, p1);
+                        }
+                        const int pb = (int)(npv & 1);
+                        mbar_wait(&bars->p_free[pb], (uint32_t)((npv >> 1) & 1) ^ 1);   // the P~ V of two steps ago has read this buffer
+                        uint8_t* prow = p_s + (size_t)pb * 2 * TC_TILE + (size_t)(cq >> 1) * TC_TILE + r * 128;
+#pragma unroll
+                        for (int pc = 0; pc < 4; ++pc)
+                            *reinterpret_cast<uint4*>(prow + (((uint32_t)((cq & 1) * 4 + pc) ^ swz) << 4)) = make_uint4(pk[pc * 4], pk[pc * 4 + 1], pk[pc * 4 + 2], pk[pc * 4 + 3]);
+                        fence_proxy_async();
+                        tc_fence_before();
+                        mbar_arrive(&bars->p_full[pb]);
+                        ++npv;
+                    }
+                }
+                // combine the four column quarters of every row: max after pass 1, sum after pass 2
+                xch[cq * 128 + r] = pass == 0 ? mx : l;
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                const float v0 = xch[r], v1 = xch[128 + r], v2 = xch[256 + r], v3 = xch[384 + r];
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                if (pass == 0) { mx = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)); sub = mx == -INFINITY ? 0.f : mx; }
+                else l = (v0 + v1) + (v2 + v3);
+            }
+            // ---- epilogue: thread (r, cq) owns O columns cq*16 .. +15 ----
+            const int os = (int)(n & 1);
+            const float inv = l > 0.f ? 1.f / l : 0.f;
+            if (cq == 0 && row_ok) lse[row_of(g, seq, pos) * g.H + h] = (sub + log2f(l)) * 0.6931471805599453f;
+            mbar_wait(&bars->o_full[os], (uint32_t)(n >> 1) & 1);
+            if (n > 0) mbar_wait(&bars->stg_free[(n - 1) & 1], (uint32_t)((n - 1) >> 1) & 1);
+            tc_fence_after();
+            uint32_t v[16];
+            tmem_ld_32x16(tmem_base + lane_base + 256 + os * 64 + cq * 16, v);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&bars->o_free[os]);
+            uint8_t* trow = stg_s + r * 128;
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+                *reinterpret_cast<uint4*>(trow + (((uint32_t)(cq * 2 + c) ^ swz) << 4)) =
+                    make_uint4(pack_bf(__uint_as_float(v[c * 8]) * inv, __uint_as_float(v[c * 8 + 1]) * inv), pack_bf(__uint_as_float(v[c * 8 + 2]) * inv, __uint_as_float(v[c * 8 + 3]) * inv),
+                               pack_bf(__uint_as_float(v[c * 8 + 4]) * inv, __uint_as_float(v[c * 8 + 5]) * inv), pack_bf(__uint_as_float(v[c * 8 + 6]) * inv, __uint_as_float(v[c * 8 + 7]) * inv));
+            fence_proxy_async();
+            mbar_arrive(&bars->stg_full[n & 1]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 16) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// 4-D view whose box is 128 consecutive positions of ONE sequence (rows beyond the sequence end: zero on load, clipped on store)
+static int tcl_tmap(CUtensorMap* m, const AttnGeom& g, const bf16* base, int64_t cols) {
+    if (g.inner == 1) {
+        const int64_t dims[4] = {cols, g.N, g.n_seq, 1}, strides[3] = {cols, (int64_t)g.N * cols, g.n_seq * g.N * cols};
+        return make_tmap_bf16_4d(m, base, dims, strides, TC_ROWS, 1);
+    }
+    const int64_t dims[4] = {cols, g.inner, g.N, g.n_seq / g.inner};
+    const int64_t strides[3] = {cols, (int64_t)g.inner * cols, (int64_t)g.N * g.inner * cols};
+    return make_tmap_bf16_4d(m, base, dims, strides, 1, TC_ROWS);
+}
+
+bool attention_fwd_tc_long_supported(const AttnGeom& g) {
+    return g.tiles > 1 && g.n_seq > 0 && g.n_seq < (int64_t)2147483647 && (int64_t)g.N < (int64_t)2147483647 - 256;
+}
+
+int attention_fwd_tc_long(const AttnGeom& g, const bf16* qkv, bf16* out, float* lse, Drop drop, cudaStream_t st) {
+    MSST_REQUIRE(attention_fwd_tc_long_supported(g), "attention_fwd_tc_long: needs N > 64");
+    static PerDeviceOnce once;
+    if (once.first()) MSST_CUDA(cudaFuncSetAttribute(attn_fwd_tc_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTclSmem));
+    const int64_t I = (int64_t)g.H * 64;
+    const int qtiles = (g.N + TC_ROWS - 1) / TC_ROWS, nk = qtiles;
+    const int64_t n_items = g.n_seq * g.H * qtiles;
+    CUtensorMap t_qkv, t_out;
+    if (int rc = tcl_tmap(&t_qkv, g, qkv, 3 * I)) return rc;
+    if (int rc = tcl_tmap(&t_out, g, out, I)) return rc;
+    const int grid = (int)(n_items < kNumSMs ? n_items : kNumSMs);
+    attn_fwd_tc_long_kernel<<<grid, TCB_THREADS, kTclSmem, st>>>(t_qkv, t_out, g, lse, drop, n_items, qtiles, nk);
+    MSST_LAUNCH_CHECK();
+    return MSST_OK;
+}
+
 }  // namespace msst

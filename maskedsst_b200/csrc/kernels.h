@@ -61,6 +61,9 @@ struct AttnGeom;
 int attention_fwd_tc(const AttnGeom& g, const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, Drop drop, cudaStream_t st);
 // tcgen05 backward for packed short sequences (N <= 64), contiguous or strided rows (both transformer stacks)
 bool attention_bwd_tc_supported(const AttnGeom& g);
+// tcgen05 forward for long sequences (N > 64): two passes over the key tiles, O accumulated in TMEM without rescaling
+bool attention_fwd_tc_long_supported(const AttnGeom& g);
+int attention_fwd_tc_long(const AttnGeom& g, const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse, Drop drop, cudaStream_t st);
 int attention_bwd_tc(const AttnGeom& g, const __nv_bfloat16* qkv, const float* lse, const __nv_bfloat16* d_out, __nv_bfloat16* d_qkv,
                      Drop drop, cudaStream_t st);
 

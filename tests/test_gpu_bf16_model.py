@@ -199,3 +199,41 @@ torch.save({"loss": loss.detach().cpu(), **{k: p.grad.float().cpu() for k, p in 
     for k, v in res["0"].items():
         if k != "loss" and float(v.norm()) > 1e-9:
             assert rel_l2(res["1"][k], v) < 2e-3, (k, rel_l2(res["1"][k], v))
+
+
+def test_tcgen05_long_sequence_forward():
+    """N > 64: the tcgen05 two-pass forward (attention_fwd_tc_long; default from N = 512, forced here for every N > 64) against the
+    fp64 reference, ragged tails and strided sequences included; gradients come from the regular (mma.sync) backward on its
+    outputs / lse, and with dropout its output must agree with the mma.sync forward (same mask)."""
+    import os, subprocess, sys, tempfile
+    code = r'''
+import sys, torch
+sys.path.insert(0, ".")
+from maskedsst_b200 import ops
+from tests.test_gpu_components import ref_attention
+from tests.helpers import rel_l2
+torch.manual_seed(0)
+out = {}
+for k, (n_seq, N, inner, H) in enumerate([(3, 200, 1, 2), (2, 256, 2, 2), (5, 130, 1, 3), (1, 65, 1, 1), (4, 1000, 1, 2), (6, 128, 3, 2), (40, 512, 1, 8)]):
+    R, I = n_seq * N, H * 64
+    qkv = torch.randn(R, 3 * I).bfloat16(); w = torch.randn(R, I).bfloat16()
+    a = qkv.double().requires_grad_(True)
+    want = ref_attention(a, n_seq, N, inner, H, 64); (want * w.double()).sum().backward()
+    b = qkv.cuda().requires_grad_(True)
+    got = ops.attention(b, n_seq=n_seq, N=N, inner=inner, heads=H, dim_head=64)
+    (got.float() * w.cuda().float()).sum().backward()
+    assert rel_l2(got, want) < 6e-3 and rel_l2(b.grad, a.grad) < 1.5e-2, (n_seq, N, rel_l2(got, want), rel_l2(b.grad, a.grad))
+    out[k] = ops.attention(b.detach(), n_seq=n_seq, N=N, inner=inner, heads=H, dim_head=64, drop_p=0.2, seed=5, site=2).float().cpu()
+torch.save(out, sys.argv[1])
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    with tempfile.TemporaryDirectory() as td:
+        for flag in ("1", "0"):
+            path = os.path.join(td, f"o{flag}.pt")
+            r = subprocess.run([sys.executable, "-c", code, path], cwd=root, env=dict(os.environ, MSST_ATTN_TC_LONG=flag),
+                               capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stdout + r.stderr
+            res[flag] = torch.load(path)
+    for k in res["1"]:
+        assert rel_l2(res["1"][k], res["0"][k]) < 6e-3, (k, rel_l2(res["1"][k], res["0"][k]))
