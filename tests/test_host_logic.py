@@ -104,3 +104,45 @@ def test_device_mask_backend_semantics_on_cpu():
             assert torch.equal(mask.view(B, spec.C, 64), mask.view(B, spec.C, 64)[:, :1].expand(B, spec.C, 64))
         want = torch.from_numpy(O.MaskGen.indices(mask.numpy(), nm))             # the reference's slicing of nonzero()
         assert torch.equal(idx, want)
+
+
+def test_v1_module_surface_matches_reference_layout():
+    """ViTSpatialSpectral_V1 (reference :600-764) on CPU: state_dict keys / shapes == the reference layout (oracle.state_dict_layout,
+    verified against the reference by make_golden.py), alias keys of the SimMIM wrapper == the golden `extra_keys`, and the
+    constructor-time errors for the two combinations the reference can only fail on at run time."""
+    import numpy as np
+    import pytest
+    import maskedsst_b200 as M
+    from oracle import maskedsst_oracle as O
+    from tests.helpers import gold
+    for name, kw in [("houston_v1_intermediate", dict(**O.HOUSTON, v1=True)), ("houston_v1_linearmerge", dict(**O.HOUSTON, v1=True, v1_merge="linear", depth=2))]:
+        g = gold(name)
+        spec = O.Spec(**kw)
+        enc = M.ViTSpatialSpectral_V1(image_size=8, spatial_patch_size=1, spectral_patch_size=10, num_classes=20, dim=96, depth=spec.depth,
+                                      heads=8, mlp_dim=64, channels=50, merge=spec.v1_merge)
+        assert {k: tuple(v.shape) for k, v in enc.state_dict().items()} == dict(O.state_dict_layout(spec, False))
+        assert enc.num_spatial_patches == 8 and enc.num_patches == 320            # grid SIDE, not its square (:629)
+        sim = M.SimMIMSpatialSpectral(encoder=enc, masking_ratio=0.7, mask_patch_size=4, tube_masking=True, intermediate_losses=True)
+        extra = sorted(set(sim.state_dict()) - set(dict(O.state_dict_layout(spec, True, False))))
+        assert extra == [str(k) for k in g["extra_keys"]]
+        assert sim.state_dict()["patch_to_emb.2.weight"].data_ptr() == enc.to_patch_embedding[2].weight.data_ptr()   # aliases share storage
+        with pytest.raises(NotImplementedError):
+            M.SimMIMSpatialSpectral(encoder=enc, to_pixels_per_spectral_block=True)
+    v2 = M.ViTSpatialSpectral(image_size=8, spatial_patch_size=1, spectral_patch_size=10, num_classes=20, dim=96, depth=1, heads=8,
+                              mlp_dim=64, channels=50, spectral_pos_embed=False)
+    with pytest.raises(NotImplementedError):
+        M.SimMIMSpatialSpectral(encoder=v2, intermediate_losses=True)
+
+
+def test_raw_tiles_and_kernels_refuse_cpu_tensors():
+    """No CPU path: RawTiles and the ops raise instead of falling back."""
+    import numpy as np
+    import pytest
+    import torch
+    import maskedsst_b200 as M
+    with pytest.raises(RuntimeError):
+        M.RawTiles(torch.zeros(1, 48, 64, 64, dtype=torch.int16), np.zeros(48), np.ones(48), image_size=8)
+    enc = M.ViTSpatialSpectral(image_size=8, spatial_patch_size=1, spectral_patch_size=10, num_classes=20, dim=96, depth=1, heads=8,
+                               mlp_dim=64, channels=50, spectral_pos_embed=False)
+    with pytest.raises(RuntimeError):
+        enc(torch.zeros(1, 50, 8, 8))
