@@ -403,6 +403,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
 bool attention_bwd_tc_supported(const AttnGeom& g) {
     const int64_t n_blk = g.inner > 0 ? g.n_seq / g.inner : 0;
     return g.tiles == 1 && g.groups > 0 && g.groups * g.G < (int64_t)2147483647 && n_blk < (int64_t)2147483647 &&
+           g.n_seq * g.N < (int64_t)2147483647 - 256 &&   // TMA coordinates are 32-bit
+          
            ((g.groups + 1) / 2) * g.H < ((int64_t)1 << 40);
 }
 
