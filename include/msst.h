@@ -155,6 +155,16 @@ MSST_API int msst_attention_fwd(const msst_attn_dims* d, const void* qkv, void* 
 MSST_API int msst_attention_bwd(const msst_attn_dims* d, const void* qkv, const void* out, const float* lse,
                        const void* d_out, void* d_qkv, msst_stream_t stream);
 
+/* Fused projection + attention (bf16 / tcgen05 only; N <= 64, dh = 64, D in {32, 64, 96, 128}): Attention.forward
+ * vit_spatial_spectral.py:67-77 INCLUDING to_qkv (:59,68) in one kernel -- q, k, v never reach HBM.
+ *   h [R, D] bf16 = the pre-norm output, w_qkv [3*H*dh, D] bf16 (reference layout of to_qkv.weight), out [R, H*dh] bf16, lse [R, H]
+ * Backward recomputes q, k, v from h and returns d_qkv [R, 3*H*dh] bf16 (input of the weight gradient dW = d_qkv^T h) and
+ * d_h [R, D] fp32 = d_qkv . w_qkv (w_qkv_t = the transposed copy [D, 3*H*dh] bf16). */
+MSST_API int msst_attn_block_fwd(const msst_attn_dims* d, int D, const void* h, const void* w_qkv, void* out, float* lse,
+                                 msst_stream_t stream);
+MSST_API int msst_attn_block_bwd(const msst_attn_dims* d, int D, const void* h, const void* w_qkv, const void* w_qkv_t,
+                                 const void* d_out, const float* lse, void* d_qkv, float* d_h, msst_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Transformer stack: L x { x = attn(LN(x)) + x ; x = ff(LN(x)) + x }  (Transformer.forward :100-104),
  * all launches of one stack issued from native code.  Parameter pointers per layer, in reference

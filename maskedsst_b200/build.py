@@ -35,7 +35,19 @@ def _digest():
 
 
 def build(force=False, verbose=False):
+    """Serialised across processes (torchrun ranks may all find the library stale): an exclusive file lock around the whole
+    build, and the library is linked to a temporary name and renamed into place, so nobody ever dlopens a partial file."""
     os.makedirs(OBJ, exist_ok=True)
+    import fcntl
+    with open(os.path.join(OBJ, "build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose):
     stamp = os.path.join(OBJ, "digest.txt")
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
@@ -57,10 +69,12 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as ex:
         objs = list(ex.map(cc, _sources()))
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-lcuda"]
+    tmp = LIB + f".tmp{os.getpid()}"
+    cmd = [NVCC, "-shared", "-o", tmp] + objs + ["-lcudart", "-lcuda"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)
     with open(stamp, "w") as f:
         f.write(dig)
     return LIB

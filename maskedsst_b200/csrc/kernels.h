@@ -67,6 +67,14 @@ int attention_fwd_tc_long(const AttnGeom& g, const __nv_bfloat16* qkv, __nv_bflo
 int attention_bwd_tc(const AttnGeom& g, const __nv_bfloat16* qkv, const float* lse, const __nv_bfloat16* d_out, __nv_bfloat16* d_qkv,
                      Drop drop, cudaStream_t st);
 
+// attn_block_tc.cu (tcgen05): per-head QKV projection fused into the attention kernels, N <= 64 -- q/k/v never reach HBM
+bool attn_block_supported(const AttnGeom& g, int D);
+int attn_block_fwd(const AttnGeom& g, int D, const __nv_bfloat16* h, const __nv_bfloat16* w_qkv, __nv_bfloat16* out, float* lse, Drop drop,
+                   cudaStream_t st);
+// recomputes q/k/v from h; d_qkv [R, 3*H*64] bf16 (for the weight gradient) and d_h [R, D] fp32 = d_qkv . W_qkv (data gradient, accumulated over heads in TMEM)
+int attn_block_bwd(const AttnGeom& g, int D, const __nv_bfloat16* h, const __nv_bfloat16* w_qkv, const __nv_bfloat16* w_qkv_t,
+                   const __nv_bfloat16* d_out, const float* lse, __nv_bfloat16* d_qkv, float* d_h, Drop drop, cudaStream_t st);
+
 // attention_f32.cu
 int attention_fwd_f32(const msst_attn_dims* d, const float* qkv, float* out, float* lse, cudaStream_t st);
 int attention_bwd_f32(const msst_attn_dims* d, const float* qkv, const float* out, const float* lse, const float* d_out,

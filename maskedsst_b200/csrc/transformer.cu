@@ -10,6 +10,7 @@
 // The residual stream, LN statistics and lse are always fp32.
 #include "common.cuh"
 #include "kernels.h"
+#include "attn_geom.cuh"
 #include <stdlib.h>
 
 namespace msst {
@@ -24,6 +25,19 @@ struct TfLayout {
     int layer_slots;
 };
 
+// bf16 mode: the QKV projection runs inside the attention kernels (attn_block_tc.cu) whenever the geometry allows it: qkv is
+// never materialised (forward) and is recomputed from the saved LayerNorm output in the backward, which also folds the
+// projection's data gradient in.  MSST_ATTN_FUSED=0 selects the separate GEMM + attention kernels.
+static bool attn_fused(const msst_tf_dims* d) {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MSST_ATTN_FUSED"); v = e ? atoi(e) : 1; }
+    if (!v || d->prec != MSST_PREC_BF16 || d->dh != 64) return false;
+    msst_attn_dims ad{d->n_seq, d->N, d->inner, d->H, d->dh, 0.f, 0, 0, d->prec, nullptr};
+    AttnGeom g;
+    if (d->n_seq == 0 || make_attn_geom(&ad, g, false)) return false;
+    return attn_block_supported(g, d->D);
+}
+
 static TfLayout make_layout(const msst_tf_dims* d) {
     TfLayout L{};
     L.R = d->n_seq * d->N; L.I = d->H * d->dh;
@@ -32,7 +46,7 @@ static TfLayout make_layout(const msst_tf_dims* d) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
     L.o_stats1 = take(R * 2 * f); L.o_stats2 = take(R * 2 * f);
-    L.o_qkv = take(R * 3 * L.I * a); L.o_o = take(R * L.I * a); L.o_lse = take(R * d->H * f);
+    L.o_qkv = take(attn_fused(d) ? 0 : R * 3 * L.I * a); L.o_o = take(R * L.I * a); L.o_lse = take(R * d->H * f);
     L.o_xmid = take(R * d->D * f); L.o_u = take(R * d->M * a); L.o_g = take(R * d->M * a); L.o_xout = take(R * d->D * f);
     L.o_h1 = L.o_h2 = 0;
     if (d->prec == MSST_PREC_BF16 && d->save_for_backward) {   // LN outputs (bf16): 2 x 2D B/token saves 2 LN passes in backward
@@ -114,6 +128,7 @@ static int tf_fwd_bf16(const msst_tf_dims* d, const msst_layer_params* layers, c
     if (int rc = weights_to_bf16(tab, st)) return rc;
     bf16* h = (bf16*)(ws + L.s_h);
     const float* x = x_in;
+    const bool fused = attn_fused(d);
     for (int l = 0; l < d->L; ++l) {
         char* lw = ws + L.layer_bytes * (d->save_for_backward ? l : 0);
         const msst_layer_params& p = layers[l];
@@ -129,9 +144,15 @@ static int tf_fwd_bf16(const msst_tf_dims* d, const msst_layer_params* layers, c
         // only the first layer's LN1 is a stand-alone kernel
         const bool fuse_ln = (D % 4 == 0 && D <= 128);
         if (l == 0 || !fuse_ln) { if (int rc = layernorm_fwd(x, p.ln1_w, p.ln1_b, h1, 1, stats1, R, D, 1e-5f, st)) return rc; }
-        if (int rc = gemm_tn_bf16(gemm_args(h1, w.wq, R, 3 * I, D, qkv, 0), st)) return rc;
         msst_attn_dims ad{d->n_seq, d->N, d->inner, d->H, d->dh, d->drop_p, d->seed, site + kSiteAttnProb, d->prec, d->seed_dev};
-        if (int rc = attention_fwd_bf16(&ad, qkv, o, lse, st)) return rc;
+        if (fused) {
+            AttnGeom ag;
+            if (int rc = make_attn_geom(&ad, ag, false)) return rc;
+            if (int rc = attn_block_fwd(ag, D, h1, w.wq, o, lse, make_drop(d->drop_p, d->seed, site + kSiteAttnProb, d->seed_dev), st)) return rc;
+        } else {
+            if (int rc = gemm_tn_bf16(gemm_args(h1, w.wq, R, 3 * I, D, qkv, 0), st)) return rc;
+            if (int rc = attention_fwd_bf16(&ad, qkv, o, lse, st)) return rc;
+        }
         GemmBf16Args a = gemm_args(o, w.wo, R, D, I, xmid, 1);
         a.bias = p.b_out; a.residual = x; a.drop = make_drop(d->drop_p, d->seed, site + kSiteAttnOut, d->seed_dev);
         if (fuse_ln) { a.ln_w = p.ln2_w; a.ln_b = p.ln2_b; a.ln_out = h2; a.ln_stats = stats2; }
@@ -164,6 +185,7 @@ static int tf_bwd_bf16(const msst_tf_dims* d, const msst_layer_params* layers, c
     const float* dcur = d_x_out;
     const Drop none = make_drop(0.f, 0, 0);
     bool dyb_ready = false;
+    const bool fused = attn_fused(d);
     for (int l = d->L - 1; l >= 0; --l) {
         char* lw = ws + L.layer_bytes * l;
         const msst_layer_params& p = layers[l];
@@ -205,10 +227,17 @@ static int tf_bwd_bf16(const msst_tf_dims* d, const msst_layer_params* layers, c
         if (int rc = gemm_wgrad_bf16(dyb, o, gr.w_out, R, D, I, st)) return rc;
         if (int rc = gemm_tn_bf16(gemm_args(dyb, w.woT, R, I, D, dO, 0), st)) return rc;
         msst_attn_dims ad{d->n_seq, d->N, d->inner, d->H, d->dh, d->drop_p, d->seed, site + kSiteAttnProb, d->prec, d->seed_dev};
-        if (int rc = attention_bwd_bf16(&ad, qkv, o, lse, dO, dqkv, st)) return rc;
+        if (fused) {   // q/k/v recomputed from h1 inside the kernel, which also produces dh = dqkv . Wqkv (no data-gradient GEMM)
+            AttnGeom ag;
+            if (int rc = make_attn_geom(&ad, ag, false)) return rc;
+            if (int rc = attn_block_bwd(ag, D, (const bf16*)(lw + L.o_h1), w.wq, w.wqT, dO, lse, dqkv, dh,
+                                        make_drop(d->drop_p, d->seed, site + kSiteAttnProb, d->seed_dev), st)) return rc;
+        } else {
+            if (int rc = attention_bwd_bf16(&ad, qkv, o, lse, dO, dqkv, st)) return rc;
+        }
         if (int rc = gemm_wgrad_bf16(dqkv, (const bf16*)(lw + L.o_h1), gr.w_qkv, R, 3 * I, D, st)) return rc;
         float* dx = (l == 0) ? d_x_in : dxb;
-        if (fuse_lnb) {   // LN1 backward in the epilogue of the Wqkv data-gradient GEMM (+ the cast for layer l-1's MLP branch)
+        if (fuse_lnb && !fused) {   // LN1 backward in the epilogue of the Wqkv data-gradient GEMM (+ the cast for layer l-1's MLP branch)
             GemmBf16Args b = gemm_args(dqkv, w.wqT, R, D, 3 * I, dx, 1);
             b.residual = dxa; b.ln_w = p.ln1_w; b.lnb_x = x; b.lnb_stats = stats1; b.lnb_dw = gr.ln1_w; b.lnb_db = gr.ln1_b;
             if (l > 0) {
@@ -219,7 +248,7 @@ static int tf_bwd_bf16(const msst_tf_dims* d, const msst_layer_params* layers, c
             dcur = dx;
             continue;
         }
-        if (int rc = gemm_tn_bf16(gemm_args(dqkv, w.wqT, R, D, 3 * I, dh, 1), st)) return rc;
+        if (!fused) { if (int rc = gemm_tn_bf16(gemm_args(dqkv, w.wqT, R, D, 3 * I, dh, 1), st)) return rc; }
         // LN1 backward -> dx (fp32) + fused for the next iteration (layer l-1): dyb = bf16(dropout_mlp_out(dx)), db2(l-1)
         if (l > 0) {
             if (int rc = layernorm_bwd(x, p.ln1_w, stats1, dh, dxa, dx, gr.ln1_w, gr.ln1_b, R, D, st, dyb,
@@ -378,6 +407,22 @@ extern "C" int msst_attention_bwd(const msst_attn_dims* d, const void* qkv, cons
     if (d->prec == MSST_PREC_BF16)
         return attention_bwd_bf16(d, (const bf16*)qkv, (const bf16*)out, lse, (const bf16*)d_out, (bf16*)d_qkv, (cudaStream_t)stream);
     return attention_bwd_f32(d, (const float*)qkv, (const float*)out, lse, (const float*)d_out, (float*)d_qkv, (cudaStream_t)stream);
+}
+extern "C" int msst_attn_block_fwd(const msst_attn_dims* d, int D, const void* h, const void* w_qkv, void* out, float* lse, msst_stream_t stream) {
+    MSST_REQUIRE(d && d->prec == MSST_PREC_BF16, "attn_block_fwd: bf16 mode only");
+    AttnGeom g;
+    if (int rc = make_attn_geom(d, g, false)) return rc;
+    if (g.n_seq == 0) return MSST_OK;
+    return attn_block_fwd(g, D, (const bf16*)h, (const bf16*)w_qkv, (bf16*)out, lse, make_drop(d->drop_p, d->seed, d->site, d->seed_dev), (cudaStream_t)stream);
+}
+extern "C" int msst_attn_block_bwd(const msst_attn_dims* d, int D, const void* h, const void* w_qkv, const void* w_qkv_t, const void* d_out,
+                                   const float* lse, void* d_qkv, float* d_h, msst_stream_t stream) {
+    MSST_REQUIRE(d && d->prec == MSST_PREC_BF16, "attn_block_bwd: bf16 mode only");
+    AttnGeom g;
+    if (int rc = make_attn_geom(d, g, false)) return rc;
+    if (g.n_seq == 0) return MSST_OK;
+    return attn_block_bwd(g, D, (const bf16*)h, (const bf16*)w_qkv, (const bf16*)w_qkv_t, (const bf16*)d_out, lse, (bf16*)d_qkv, d_h,
+                          make_drop(d->drop_p, d->seed, d->site, d->seed_dev), (cudaStream_t)stream);
 }
 extern "C" int msst_dropout_apply(const float* x, float* y, int64_t n, float p, uint64_t seed, uint32_t site,
                                   const uint64_t* seed_dev, msst_stream_t stream) {

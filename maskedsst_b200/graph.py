@@ -42,12 +42,25 @@ class GraphedStep:
     def recapture(self):
         ops.set_device_seed(self.seed_t)
         try:
+            # the warm-up steps are real optimiser steps on the (stale) static inputs: snapshot the training state and put it
+            # back afterwards, so (re)capturing -- e.g. after every scheduler LR change -- never alters parameters, moments or
+            # the step counters
+            opt = self.opt
+            snap = (opt.param_arena.clone(), opt.exp_avg.clone(), opt.exp_avg_sq.clone(), opt._step, opt._step_t.clone(),
+                    None if opt.bf16_arena is None else opt.bf16_arena.clone(), self.seed_t.clone())
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(self.warmup):       # also runs every one-time cudaFuncSetAttribute outside the capture
                     self._step()
             torch.cuda.current_stream().wait_stream(side)
+            with torch.no_grad():
+                opt.param_arena.copy_(snap[0]); opt.exp_avg.copy_(snap[1]); opt.exp_avg_sq.copy_(snap[2])
+                opt._step = snap[3]; opt._step_t.copy_(snap[4])
+                if snap[5] is not None:
+                    opt.bf16_arena.copy_(snap[5])
+                self.seed_t.copy_(snap[6])
+                opt.zero_grad()
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self.static_loss = self._step()

@@ -76,6 +76,51 @@ class FusedAdam(torch.optim.Optimizer):
         self.exp_avg_sq = torch.zeros_like(self.param_arena)
         self.bf16_arena = None
         self._step = 0
+        # torch.optim.Adam(W) skips parameters whose .grad is None (e.g. encoder.mlp_head.* during SimMIM pre-training,
+        # unused V1 merge layers): no moment update and, above all, NO weight decay.  In the arena every parameter has a
+        # (zero) gradient view, so the set of parameters that actually received a gradient since zero_grad() is tracked
+        # with post-accumulate hooks and only their arena ranges are updated.
+        self._touched = set()
+        self._range_cache = {}
+        self._hooks = [p.register_post_accumulate_grad_hook(self._mark) for g in groups for p in g if p.requires_grad]
+
+    def _mark(self, p):
+        self._touched.add(id(p))
+
+    def mark_all_touched(self):
+        """For callers that write gradients into the arena without autograd."""
+        self._touched.update(self._offsets.keys())
+
+    def _ranges(self, gi):
+        """Contiguous arena ranges (within group gi) of the parameters that received a gradient."""
+        key = (gi, frozenset(self._touched))
+        r = self._range_cache.get(key)
+        if r is None:
+            r = []
+            for p in self.param_groups[gi]["params"]:
+                if id(p) not in self._touched:
+                    continue
+                off, n = self._offsets[id(p)]
+                end = off + (n + 3) // 4 * 4
+                if r and r[-1][1] == off:
+                    r[-1][1] = end
+                else:
+                    r.append([off, end])
+            if len(self._range_cache) > 64:
+                self._range_cache.clear()
+            self._range_cache[key] = r
+        return r
+
+    def _check_homes(self):
+        """nn.Module.zero_grad() / p.grad = None re-allocates gradients outside the arena: training would silently stop."""
+        for g in self.param_groups:
+            ps = g["params"]
+            for p in (ps[0], ps[-1]) if ps else ():
+                off, n = self._offsets[id(p)]
+                if p.grad is None or p.grad.data_ptr() != self.grad_arena[off: off + 1].data_ptr() or \
+                        p.data_ptr() != self.param_arena[off: off + 1].data_ptr():
+                    raise RuntimeError("FusedAdam: a parameter or its .grad no longer lives in the flat arena (was "
+                                       "model.zero_grad() / p.grad = None / model.to() called?).  Use optimizer.zero_grad().")
 
     def offset_of(self, p):
         return self._offsets[id(p)]
@@ -90,6 +135,7 @@ class FusedAdam(torch.optim.Optimizer):
     def zero_grad(self, set_to_none=False):
         """One memset; gradients stay views of the arena (set_to_none would break the flat layout)."""
         self.grad_arena.zero_()
+        self._touched = set()
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -104,24 +150,35 @@ class FusedAdam(torch.optim.Optimizer):
             step_dev = self._step_t.data_ptr()
         stream = torch.cuda.current_stream().cuda_stream
         lib = _lib.lib()
-        for g, (a, b) in zip(self.param_groups, self._group_ranges):
-            if b == a:
-                continue
-            args = _lib.AdamArgs(float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
-                                 float(g["weight_decay"]), int(bool(g["decoupled"])), float(g["clamp"]),
-                                 float(self.grad_scale), self._step, step_dev)
-            bf = None if self.bf16_arena is None else self.bf16_arena[a:b].data_ptr()
-            check(lib.msst_adam_step(C.byref(args), self.param_arena[a:b].data_ptr(), self.grad_arena[a:b].data_ptr(),
-                                     self.exp_avg[a:b].data_ptr(), self.exp_avg_sq[a:b].data_ptr(), bf, b - a, stream))
+        self._check_homes()
+        for gi, g in enumerate(self.param_groups):
+            for a, b in self._ranges(gi):
+                args = _lib.AdamArgs(float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
+                                     float(g["weight_decay"]), int(bool(g["decoupled"])), float(g["clamp"]),
+                                     float(self.grad_scale), self._step, step_dev)
+                bf = None if self.bf16_arena is None else self.bf16_arena[a:b].data_ptr()
+                check(lib.msst_adam_step(C.byref(args), self.param_arena[a:b].data_ptr(), self.grad_arena[a:b].data_ptr(),
+                                         self.exp_avg[a:b].data_ptr(), self.exp_avg_sq[a:b].data_ptr(), bf, b - a, stream))
         return loss
 
-    # optimizer state is three flat tensors + the step counter
+    # optimizer state is three flat tensors + the step counter (NOT a torch.optim state_dict: the moments are arena-shaped)
     def state_dict(self):
-        return {"step": self._step, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
+        step = int(self._step_t.item()) if self._step_t is not None else self._step   # graph replays advance only the device counter
+        return {"format": "maskedsst_b200.FusedAdam/1", "step": step, "arena_numel": self.param_arena.numel(),
+                "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
                 "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
 
     def load_state_dict(self, sd):
+        for k in ("step", "exp_avg", "exp_avg_sq", "param_groups"):
+            if k not in sd:
+                raise KeyError(f"FusedAdam.load_state_dict: missing key '{k}' (this is not a torch.optim.Adam state_dict: "
+                               "the moments are stored as flat arena tensors)")
+        if sd["exp_avg"].numel() != self.exp_avg.numel() or sd["exp_avg_sq"].numel() != self.exp_avg_sq.numel() or \
+                len(sd["param_groups"]) != len(self.param_groups):
+            raise ValueError("FusedAdam.load_state_dict: arena size / group count mismatch (different model or parameter order)")
         self._step = int(sd["step"])
+        if self._step_t is not None:
+            self._step_t.fill_(self._step)
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
         for g, s in zip(self.param_groups, sd["param_groups"]):

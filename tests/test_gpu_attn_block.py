@@ -1,0 +1,104 @@
+"""GPU: the fused projection + attention kernels (csrc/attn_block_tc.cu) called through the C ABI, against an fp64 torch
+reference of  to_qkv -> softmax(q k^T dh^-0.5) v  (reference Attention.forward, src/vit_spatial_spectral.py:67-77) and its
+autograd; plus bit-agreement of the dropout masks with the unfused tcgen05 kernels."""
+import ctypes as C
+
+import pytest
+import torch
+
+from maskedsst_b200 import _lib, ops
+from maskedsst_b200._lib import check, PREC_BF16
+from tests.helpers import rel_l2
+from tests.test_gpu_components import ref_attention
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+GEOMS = [
+    (10, 64, 1, 8, 96),       # spatial stack, full tiles
+    (7, 64, 1, 8, 96),        # odd number of 64-slot groups: the last tile is half empty
+    (128, 5, 64, 8, 96),      # Houston spectral stack: 12 sequences of 5 per group, rows strided by 64
+    (128, 20, 64, 8, 96),     # EnMAP spectral stack
+    (640, 5, 64, 8, 96),      # more tiles than one wave of a small grid would hold per CTA: multi-item loops
+    (6, 22, 2, 4, 64),        # ragged packing, 4 heads, D = 64
+    (37, 16, 1, 2, 128),      # contiguous short sequences with a partial last group, D = 128
+    (3, 1, 1, 1, 32),         # degenerate
+    (2368, 64, 1, 8, 96),     # 1184 tiles = 8 per CTA: steady-state pipeline, tile changes, h double buffer
+]
+
+
+def _call_fwd(h, w, n_seq, N, inner, H, drop_p=0.0, seed=0, site=0):
+    R, D = h.shape
+    I = H * 64
+    dims = _lib.AttnDims(n_seq, N, inner, H, 64, float(drop_p), seed, site, PREC_BF16, None)
+    out = torch.full((R, I), float("nan"), device=DEV, dtype=torch.bfloat16)
+    lse = torch.full((R, H), float("nan"), device=DEV, dtype=torch.float32)
+    st = torch.cuda.current_stream().cuda_stream
+    check(_lib.lib().msst_attn_block_fwd(C.byref(dims), D, h.data_ptr(), w.data_ptr(), out.data_ptr(), lse.data_ptr(), st))
+    return out, lse, dims
+
+
+def _call_bwd(dims, h, w, d_out, lse):
+    R, D = h.shape
+    I3 = w.shape[0]
+    wt = w.t().contiguous()
+    dqkv = torch.full((R, I3), float("nan"), device=DEV, dtype=torch.bfloat16)
+    dh = torch.full((R, D), float("nan"), device=DEV, dtype=torch.float32)
+    st = torch.cuda.current_stream().cuda_stream
+    check(_lib.lib().msst_attn_block_bwd(C.byref(dims), D, h.data_ptr(), w.data_ptr(), wt.data_ptr(), d_out.data_ptr(), lse.data_ptr(),
+                                         dqkv.data_ptr(), dh.data_ptr(), st))
+    return dqkv, dh
+
+
+@pytest.mark.parametrize("n_seq,N,inner,H,D", GEOMS)
+def test_attn_block_fwd_bwd_vs_fp64(n_seq, N, inner, H, D):
+    torch.manual_seed(0)
+    R, I = n_seq * N, H * 64
+    h = torch.randn(R, D).bfloat16()
+    w = (torch.randn(3 * I, D) * D ** -0.5).bfloat16()
+    g_out = torch.randn(R, I).bfloat16()
+    # reference: the kernel rounds q, k, v to bf16 before the attention contractions
+    hd = h.double().requires_grad_(True)
+    qkv = hd @ w.double().t()
+    qkv_r = qkv + (qkv.detach().float().bfloat16().double() - qkv.detach())      # straight-through bf16 rounding
+    qkv_r.retain_grad()
+    want = ref_attention(qkv_r, n_seq, N, inner, H, 64)
+    (want * g_out.double()).sum().backward()
+
+    hg, wg = h.to(DEV), w.to(DEV)
+    out, lse, dims = _call_fwd(hg, wg, n_seq, N, inner, H)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all()
+    assert rel_l2(out, want) < 8e-3
+    # lse against the reference scores
+    q, k, _ = qkv_r.detach().split(I, dim=-1)
+    dqkv, dh = _call_bwd(dims, hg, wg, g_out.to(DEV), lse)
+    torch.cuda.synchronize()
+    assert torch.isfinite(dqkv.float()).all() and torch.isfinite(dh).all()
+    assert rel_l2(dqkv, qkv_r.grad) < 2e-2
+    assert rel_l2(dh, hd.grad) < 2e-2
+
+
+@pytest.mark.parametrize("n_seq,N,inner,H", [(16, 64, 1, 8), (256, 5, 64, 8), (128, 20, 64, 4)])
+def test_attn_block_matches_unfused_kernels_with_dropout(n_seq, N, inner, H):
+    """Same (seed, site) -> the fused kernels regenerate exactly the attention-dropout mask of the unfused tcgen05 kernels:
+    outputs agree to bf16 rounding of q/k/v (identical here: the unfused path is fed the bf16 qkv the fused one computes)."""
+    torch.manual_seed(2)
+    D, I = 96, H * 64
+    R = n_seq * N
+    h = torch.randn(R, D).bfloat16().to(DEV)
+    w = (torch.randn(3 * I, D) * D ** -0.5).bfloat16().to(DEV)
+    g_out = torch.randn(R, I).bfloat16().to(DEV)
+    out, lse, dims = _call_fwd(h, w, n_seq, N, inner, H, drop_p=0.25, seed=77, site=5)
+    dqkv, dh = _call_bwd(dims, h, w, g_out, lse)
+    # unfused: qkv by an fp32-accumulated matmul rounded to bf16 (what the tcgen05 GEMM produces), then the attention kernels
+    qkv = (h.float() @ w.float().t()).bfloat16().requires_grad_(True)
+    ref = ops.attention(qkv, n_seq=n_seq, N=N, inner=inner, heads=H, dim_head=64, drop_p=0.25, seed=77, site=5)
+    (ref.float() * g_out.float()).sum().backward()
+    assert rel_l2(out, ref) < 4e-3            # a different mask would give O(1) differences
+    assert rel_l2(dqkv, qkv.grad) < 8e-3
+    want_dh = qkv.grad.float() @ w.float()
+    assert rel_l2(dh, want_dh) < 8e-3
+    # determinism
+    out2, _, _ = _call_fwd(h, w, n_seq, N, inner, H, drop_p=0.25, seed=77, site=5)
+    assert torch.equal(out, out2)

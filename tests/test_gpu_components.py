@@ -143,10 +143,39 @@ def test_fused_adam_matches_torch_optim(decoupled, wd, clamp):
             g = torch.randn(rp.shape) * 3
             rp.grad = g.clamp(-clamp, clamp) if clamp > 0 else g.clone()
             op.grad.copy_(g.to(DEV))
+        ours.mark_all_touched()          # gradients were written without autograd
         ref.step(); ours.step()
     for rp, op in zip(ref_p, our_p):
         assert torch.allclose(op.detach().cpu(), rp.detach(), rtol=2e-6, atol=2e-7)
     assert our_p[1].data_ptr() == ours.param_arena.data_ptr() + 4 * ours.offset_of(our_p[1])[0]
+
+
+@pytest.mark.parametrize("decoupled", [True, False])
+def test_fused_adam_skips_parameters_without_gradient(decoupled):
+    """torch.optim.Adam(W) skips parameters whose .grad is None: no moments, no weight decay (the reference's unused
+    encoder.mlp_head during SimMIM pre-training keeps its LayerNorm gamma at exactly 1).  The arena gives every parameter a
+    zero gradient view, so FusedAdam tracks which parameters autograd touched."""
+    torch.manual_seed(4)
+    shapes = [(96,), (64, 96), (33,), (96,), (10, 7)]
+    used = [True, True, False, True, False]
+    ref_p = [torch.nn.Parameter(torch.randn(s)) for s in shapes]
+    our_p = [torch.nn.Parameter(p.detach().clone().to(DEV)) for p in ref_p]
+    Opt = torch.optim.AdamW if decoupled else torch.optim.Adam
+    ref = Opt(ref_p, lr=0.01, weight_decay=0.05)
+    ours = FusedAdam(our_p, lr=0.01, weight_decay=0.05, decoupled=decoupled)
+    for step in range(4):
+        ref.zero_grad(); ours.zero_grad()
+        coef = [torch.randn(s) for s in shapes]
+        sum((p * c).sum() for p, c, u in zip(ref_p, coef, used) if u).backward()
+        sum((p * c.to(DEV)).sum() for p, c, u in zip(our_p, coef, used) if u).backward()
+        ref.step(); ours.step()
+    for rp, op, u in zip(ref_p, our_p, used):
+        assert torch.allclose(op.detach().cpu(), rp.detach(), rtol=2e-6, atol=2e-7)
+    assert ref_p[2].grad is None   # the premise: torch never touched them
+    # re-homing check: a gradient that left the arena is an error, not a silent no-op
+    our_p[0].grad = None
+    with pytest.raises(RuntimeError, match="arena"):
+        ours.step()
 
 
 def test_sequential_call_matches_fast_path():
