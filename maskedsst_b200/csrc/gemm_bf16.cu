@@ -664,20 +664,25 @@ int make_tmap_bf16_4d(CUtensorMap* m, const void* base, const int64_t dims[4], c
 
 // generic bf16 view of rank 2..4 (dims[0] = contiguous columns; strides in ELEMENTS for dims 1..rank-1), arbitrary box,
 // swizzle_bytes 64 or 128 (the box's inner extent must equal the swizzle span), OOB -> zeros on load
-int make_tmap_bf16_nd(CUtensorMap* m, const void* base, int rank, const int64_t* dims, const int64_t* strides, const int* box, int swizzle_bytes) {
+int make_tmap_nd(CUtensorMap* m, const void* base, int elem_bytes, int rank, const int64_t* dims, const int64_t* strides, const int* box, int swizzle_bytes) {
     EncodeTiledFn enc = get_encode();
     MSST_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
-    MSST_REQUIRE(rank >= 2 && rank <= 4 && (swizzle_bytes == 64 || swizzle_bytes == 128) && box[0] * 2 == swizzle_bytes, "make_tmap_bf16_nd: bad rank / swizzle / box");
+    MSST_REQUIRE(rank >= 2 && rank <= 4 && (elem_bytes == 2 || elem_bytes == 4) && (swizzle_bytes == 0 || swizzle_bytes == 64 || swizzle_bytes == 128) &&
+                 (swizzle_bytes == 0 ? (box[0] * elem_bytes) % 16 == 0 : box[0] * elem_bytes == swizzle_bytes), "make_tmap_nd: bad rank / element / swizzle / box");
     MSST_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA operand must be 16-byte aligned");
     cuuint64_t d[4], sb[3];
     cuuint32_t bx[4], estr[4] = {1u, 1u, 1u, 1u};
     for (int i = 0; i < rank; ++i) { d[i] = (cuuint64_t)dims[i]; bx[i] = (cuuint32_t)box[i]; }
-    for (int i = 0; i + 1 < rank; ++i) { sb[i] = (cuuint64_t)strides[i] * 2; MSST_REQUIRE(sb[i] % 16 == 0, "TMA strides must be multiples of 16 bytes"); }
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, sb, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    for (int i = 0; i + 1 < rank; ++i) { sb[i] = (cuuint64_t)strides[i] * elem_bytes; MSST_REQUIRE(sb[i] % 16 == 0, "TMA strides must be multiples of 16 bytes"); }
+    CUresult r = enc(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), d, sb, bx, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle_bytes == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MSST_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (rank %d, swizzle %d) failed with code %d", rank, swizzle_bytes, (int)r);
     return MSST_OK;
+}
+int make_tmap_bf16_nd(CUtensorMap* m, const void* base, int rank, const int64_t* dims, const int64_t* strides, const int* box, int swizzle_bytes) {
+    return make_tmap_nd(m, base, 2, rank, dims, strides, box, swizzle_bytes);
 }
 
 // MODE 6 / 8: finished fp32 rows of the four TMEM lane quarters; MODE 8 re-uses the area for its final [3][16][128] column reduction

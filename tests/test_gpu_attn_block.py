@@ -21,7 +21,7 @@ GEOMS = [
     (128, 20, 64, 8, 96),     # EnMAP spectral stack
     (640, 5, 64, 8, 96),      # more tiles than one wave of a small grid would hold per CTA: multi-item loops
     (6, 22, 2, 4, 64),        # ragged packing, 4 heads, D = 64
-    (37, 16, 1, 2, 128),      # contiguous short sequences with a partial last group, D = 128
+    (37, 16, 1, 2, 32),       # contiguous short sequences with a partial last group, D = 32
     (3, 1, 1, 1, 32),         # degenerate
     (2368, 64, 1, 8, 96),     # 1184 tiles = 8 per CTA: steady-state pipeline, tile changes, h double buffer
 ]

@@ -221,14 +221,18 @@ def test_cuda_graph_step_matches_eager():
     a, b = build(0.0), build(0.0)
     oa = FusedAdam(a.parameters(), lr=0.01, weight_decay=0.05, clamp=1.0)
     ob = FusedAdam(b.parameters(), lr=0.01, weight_decay=0.05, clamp=1.0, capturable=True)
-    g = GraphedStep(b, ob, (x, y), loss_fn=loss_fn, warmup=2)        # 2 eager warm-up steps applied; the capture itself executes nothing
-    for _ in range(2):
-        oa.zero_grad(); loss_fn(a, x, y).backward(); oa.step()
-    lg = g(x, y)                                                     # 3rd step, replayed
-    oa.zero_grad(); le = loss_fn(a, x, y); le.backward(); oa.step()
+    p0 = ob.param_arena.clone()
+    g = GraphedStep(b, ob, (x, y), loss_fn=loss_fn, warmup=2)        # warm-up steps are rolled back: capturing changes no training state
+    assert torch.equal(ob.param_arena, p0) and int(ob._step_t) == 0 and float(ob.exp_avg.abs().sum()) == 0.0
+    for _ in range(3):
+        lg = g(x, y)                                                 # replayed steps 1..3
+        oa.zero_grad(); le = loss_fn(a, x, y); le.backward(); oa.step()
     torch.cuda.synchronize()
-    assert abs(float(lg) - float(le)) < 1e-5 * abs(float(le))
+    assert abs(float(lg) - float(le.detach())) < 1e-5 * abs(float(le.detach()))
     assert rel_l2(ob.param_arena, oa.param_arena) < 1e-5
+    assert ob.state_dict()["step"] == 3                              # the device counter, not the stale host one
+    g.recapture()                                                    # e.g. after a scheduler LR change: must not move the state either
+    assert rel_l2(ob.param_arena, oa.param_arena) < 1e-5 and ob.state_dict()["step"] == 3
     # dropout: two replays on the same input give different losses (fresh masks), and training state stays finite
     c = build(0.2)
     oc = FusedAdam(c.parameters(), lr=0.0, weight_decay=0.0, capturable=True)   # lr 0: parameters frozen, only masks change
