@@ -367,7 +367,7 @@ def simmim_forward(img, sd, spec: Spec, bool_mask: torch.Tensor, idx: torch.Tens
     tokens = torch.where(bool_mask[..., None], mask_tokens, tokens)
     enc = transformer_forward(tokens, sd, spec, pre, drop)
     nm = idx.shape[1]
-    br = torch.arange(B)[:, None]
+    br = torch.arange(B, device=idx.device)[:, None]
     sel = enc[br, idx]                                              # [B,nm,D]
     if blockwise_decoder:
         blk = idx // spec.S                                         # arange(C).repeat_interleave(S)[idx]
