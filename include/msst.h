@@ -72,6 +72,9 @@ typedef struct {
     const double* mean;          /* device [raw_bands] float64 */
     const double* std;           /* device [raw_bands] float64 */
     int clip; float clip_lo, clip_hi;
+    int win_y, win_x;            /* 0 / 1: one crop window per tile (above).  > 1: whole-tile sliding-window inference (notebook cell 13,
+                                    src/utils.py:477-605): sample n = window n % (win_y*win_x) of tile n / (win_y*win_x), its origin
+                                    (y0 + (w / win_x) * H, x0 + (w % win_x) * W) -- the windows are never copied out of the tile */
 } msst_raw_input;
 
 typedef struct {
@@ -226,6 +229,19 @@ MSST_API int msst_simmim_decode_l1_bwd(const msst_decode_dims* d, const float* e
                               const float* target_tokens, const float* W, const float* bias, const float* d_loss,
                               float* d_enc, float* d_W, float* d_bias, float* d_target_tokens /*or NULL*/,
                               msst_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * SimMIM block / tube mask generation on the device: replaces MaskGenerator.get_batch /
+ * get_batch_tube_masked / bool_mask_to_indices (vit_simmim_original.py:343-416) with one launch.  A draw = a uniformly random
+ * subset of mask_count of the rand_size^2 cells, upsampled by `scale` to the token grid; tube: one draw per sample shared by its C
+ * spectral blocks, else one per (sample, block).  idx follows the reference's slicing (quirk C3): the ascending set positions of all
+ * samples concatenated and cut into runs of nm.   mask [B, C*(rand_size*scale)^2] uint8, idx [B, nm] int64.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int B, C, rand_size, scale, mask_count, nm, tube;
+    uint64_t seed; const uint64_t* seed_dev;
+} msst_maskgen_dims;
+MSST_API int msst_draw_masks(const msst_maskgen_dims* d, uint8_t* mask, int64_t* idx, msst_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (5) fused Adam/AdamW over a flat fp32 arena segment (torch.optim.AdamW/Adam as configured by

@@ -18,7 +18,7 @@ RAW_I16, RAW_U16, RAW_F32 = 0, 1, 2
 class RawInput(C.Structure):   # msst_raw_input
     _fields_ = [("tiles", vp), ("dtype", C.c_int), ("raw_bands", C.c_int), ("tile_h", C.c_int), ("tile_w", C.c_int),
                 ("y0", C.c_int), ("x0", C.c_int), ("mean", vp), ("std", vp), ("clip", C.c_int), ("clip_lo", C.c_float),
-                ("clip_hi", C.c_float)]
+                ("clip_hi", C.c_float), ("win_y", C.c_int), ("win_x", C.c_int)]
 
 
 class EmbedDims(C.Structure):
@@ -56,6 +56,11 @@ class DecodeDims(C.Structure):
                 ("nm", C.c_int), ("n_weight_blocks", C.c_int), ("raw", C.POINTER(RawInput))]
 
 
+class MaskGenDims(C.Structure):
+    _fields_ = [("B", C.c_int), ("C", C.c_int), ("rand_size", C.c_int), ("scale", C.c_int), ("mask_count", C.c_int), ("nm", C.c_int),
+                ("tube", C.c_int), ("seed", C.c_uint64), ("seed_dev", vp)]
+
+
 class AdamArgs(C.Structure):
     _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
                 ("weight_decay", C.c_float), ("decoupled", C.c_int), ("clamp", C.c_float), ("grad_scale", C.c_float),
@@ -87,6 +92,7 @@ SIGNATURES = {
     "msst_cross_entropy_fwd_bwd": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     "msst_simmim_decode_l1_fwd": (C.c_int, [C.POINTER(DecodeDims)] + [vp] * 9 + [vp]),
     "msst_simmim_decode_l1_bwd": (C.c_int, [C.POINTER(DecodeDims)] + [vp] * 11 + [vp]),
+    "msst_draw_masks": (C.c_int, [C.POINTER(MaskGenDims), vp, vp, vp]),
     "msst_adam_step": (C.c_int, [C.POINTER(AdamArgs), vp, vp, vp, vp, vp, C.c_int64, vp]),
 }
 

@@ -21,7 +21,7 @@ class RawTiles:
     reference's StandardizeEnMAP / StandardizeHouston2018) + the crop window.  Quacks like the [B, bands, H, W] cube where the
     modules only need its shape / device."""
 
-    def __init__(self, tiles, means, stds, *, image_size, crop=(0, 0), pad_bands=0, clip=None):
+    def __init__(self, tiles, means, stds, *, image_size, crop=(0, 0), pad_bands=0, clip=None, windows=(1, 1)):
         if not tiles.is_cuda:
             raise RuntimeError("maskedsst_b200: RawTiles needs CUDA tiles (there is no CPU path)")
         if tiles.dtype not in _DT or tiles.dim() != 4:
@@ -33,6 +33,7 @@ class RawTiles:
         if self.means.numel() != nb or self.stds.numel() != nb:
             raise RuntimeError(f"maskedsst_b200: need one mean / std per raw band ({nb}), got {self.means.numel()} / {self.stds.numel()}")
         self.image_size, self.pad_bands, self.clip = int(image_size), int(pad_bands), clip
+        self.windows = (int(windows[0]), int(windows[1]))   # (rows, cols) of image_size windows per tile taken as consecutive samples
         self.crop = (0, 0)
         self.set_crop(*crop)
 
@@ -40,14 +41,15 @@ class RawTiles:
         """Window origin inside the tile, shared by the batch (pretrain.py:99-107 draws it with randint(0, 64 - image_size))."""
         y0, x0 = int(y0), int(x0)
         th, tw = self.tiles.shape[2:]
-        if not (0 <= y0 and y0 + self.image_size <= th and 0 <= x0 and x0 + self.image_size <= tw):
-            raise RuntimeError(f"maskedsst_b200: crop ({y0},{x0}) + {self.image_size} outside the {th}x{tw} tile")
+        if not (0 <= y0 and y0 + self.windows[0] * self.image_size <= th and 0 <= x0 and x0 + self.windows[1] * self.image_size <= tw):
+            raise RuntimeError(f"maskedsst_b200: crop ({y0},{x0}) + {self.windows} x {self.image_size} outside the {th}x{tw} tile")
         self.crop = (y0, x0)
         return self
 
     @property
     def shape(self):
-        return torch.Size((self.tiles.shape[0], self.tiles.shape[1] + self.pad_bands, self.image_size, self.image_size))
+        return torch.Size((self.tiles.shape[0] * self.windows[0] * self.windows[1], self.tiles.shape[1] + self.pad_bands,
+                           self.image_size, self.image_size))
 
     @property
     def device(self):
@@ -57,13 +59,18 @@ class RawTiles:
         lo, hi = self.clip if self.clip is not None else (0.0, 0.0)
         _, nb, th, tw = self.tiles.shape
         return _lib.RawInput(self.tiles.data_ptr(), _DT[self.tiles.dtype], nb, th, tw, self.crop[0], self.crop[1],
-                             self.means.data_ptr(), self.stds.data_ptr(), int(self.clip is not None), float(lo), float(hi))
+                             self.means.data_ptr(), self.stds.data_ptr(), int(self.clip is not None), float(lo), float(hi),
+                             self.windows[0], self.windows[1])
 
     def materialize(self):
         """The fp32 cube the reference would have built (unfused equivalent, torch ops; for callers that need the tensor)."""
         y0, x0 = self.crop
         s = self.image_size
-        win = self.tiles[:, :, y0:y0 + s, x0:x0 + s]
+        wy, wx = self.windows
+        win = self.tiles[:, :, y0:y0 + wy * s, x0:x0 + wx * s]
+        if wy * wx > 1:   # windows become consecutive samples
+            B, nb = win.shape[:2]
+            win = win.reshape(B, nb, wy, s, wx, s).permute(0, 2, 4, 1, 3, 5).reshape(B * wy * wx, nb, s, s)
         win = win.to(torch.int32).to(torch.float64) if win.dtype != torch.float32 else win.to(torch.float64)
         x = ((win - self.means[None, :, None, None]) / self.stds[None, :, None, None]).to(torch.float32)
         if self.clip is not None:

@@ -143,9 +143,26 @@ class SimMIMSpatialSpectral(nn.Module):
         return fn(batch_size=batch, channel_tokens=enc.num_spectral_patches, num_masked=num_masked, device=device)
 
     def _draw_masks_device(self, batch, num_masked, device):
-        """MaskGenerator.get_batch / get_batch_tube_masked (+ bool_mask_to_indices) with static shapes on the device:
-        a uniformly random subset of mask_count cells per draw, upsampled by `scale`; the index list is the row-major
-        list of set positions cut into consecutive runs of num_masked (the reference's slicing, quirk C3)."""
+        """MaskGenerator.get_batch / get_batch_tube_masked (+ bool_mask_to_indices) on the device in ONE kernel launch
+        (csrc/maskgen.cu, msst_draw_masks): a uniformly random subset of mask_count cells per draw, upsampled by `scale`; the
+        index list is the row-major list of set positions cut into consecutive runs of num_masked (the reference's slicing,
+        quirk C3).  On a CPU device (host-logic tests only) the same semantics run as torch ops."""
+        if torch.device(device).type != "cuda":
+            return self._draw_masks_torch(batch, num_masked, device)
+        import ctypes as C
+        from . import _lib
+        g, enc = self.mask_generator, self.encoder
+        T = enc.num_patches
+        if batch * g.mask_count * g.scale * g.scale * enc.num_spectral_patches < batch * num_masked:
+            raise RuntimeError("mask has fewer set positions than batch * num_masked")
+        mask = torch.empty(batch, T, dtype=torch.uint8, device=device)
+        idx = torch.empty(batch, num_masked, dtype=torch.int64, device=device)
+        dims = _lib.MaskGenDims(batch, enc.num_spectral_patches, g.rand_size, g.scale, g.mask_count, num_masked, int(bool(self.tube_masking)),
+                                ops.next_seed(), ops._seed_dev())
+        _lib.check(_lib.lib().msst_draw_masks(C.byref(dims), mask.data_ptr(), idx.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        return mask.view(torch.bool), idx
+
+    def _draw_masks_torch(self, batch, num_masked, device):
         g, enc = self.mask_generator, self.encoder
         C, T = enc.num_spectral_patches, enc.num_patches
         n = batch if self.tube_masking else batch * C
