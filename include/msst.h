@@ -168,6 +168,16 @@ MSST_API int msst_attn_block_fwd(const msst_attn_dims* d, int D, const void* h, 
 MSST_API int msst_attn_block_bwd(const msst_attn_dims* d, int D, const void* h, const void* w_qkv, const void* w_qkv_t,
                                  const void* d_out, const float* lse, void* d_qkv, float* d_h, msst_stream_t stream);
 
+/* Fused FeedForward block (bf16 / tcgen05 only; mlp_dim = 64, D in {32, 64, 96}): FeedForward.forward vit_spatial_spectral.py:35-44 +
+ * the residual add (:103) + the next layer's pre-norm (:25-29) in one kernel; the hidden activation goes from the first to the second
+ * GEMM through shared memory.   h2 [R,D] bf16 (the pre-norm output), xmid [R,D] fp32 (residual), w1 [64,D] / w2 [D,64] bf16,
+ * outputs u (pre-GELU) and g = dropout(gelu(u)) [R,64] bf16 (saved for the backward), y [R,D] fp32, and -- when h1 != NULL --
+ * h1 = LayerNorm(y; ln_w, ln_b) bf16 with ln_stats [R,2] = (mean, rstd).  Dropout sites: site_hidden on g, site_out on the branch output. */
+MSST_API int msst_mlp_block_fwd(const void* h2, const float* xmid, const void* w1, const void* w2, const float* b1, const float* b2,
+                                void* u, void* g, float* y, const float* ln_w, const float* ln_b, void* h1, float* ln_stats,
+                                int64_t R, int D, int M, float drop_p, uint64_t seed, uint32_t site_hidden, uint32_t site_out,
+                                const uint64_t* seed_dev, msst_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Transformer stack: L x { x = attn(LN(x)) + x ; x = ff(LN(x)) + x }  (Transformer.forward :100-104),
  * all launches of one stack issued from native code.  Parameter pointers per layer, in reference

@@ -75,6 +75,12 @@ int attn_block_fwd(const AttnGeom& g, int D, const __nv_bfloat16* h, const __nv_
 int attn_block_bwd(const AttnGeom& g, int D, const __nv_bfloat16* h, const __nv_bfloat16* w_qkv, const __nv_bfloat16* w_qkv_t,
                    const __nv_bfloat16* d_out, const float* lse, __nv_bfloat16* d_qkv, float* d_h, Drop drop, cudaStream_t st);
 
+// mlp_block_tc.cu (tcgen05): Linear -> GELU -> dropout -> Linear -> dropout -> residual (-> next pre-norm LayerNorm) in one kernel
+bool mlp_block_supported(int D, int M);
+int mlp_block_fwd(const __nv_bfloat16* h2, const float* xmid, const __nv_bfloat16* w1, const __nv_bfloat16* w2, const float* b1, const float* b2,
+                  __nv_bfloat16* u, __nv_bfloat16* g, float* y, const float* ln_w, const float* ln_b, __nv_bfloat16* h1, float* ln_stats,
+                  int64_t R, int D, int M, Drop drop_h, Drop drop_o, cudaStream_t st);
+
 // attention_f32.cu
 int attention_fwd_f32(const msst_attn_dims* d, const float* qkv, float* out, float* lse, cudaStream_t st);
 int attention_bwd_f32(const msst_attn_dims* d, const float* qkv, const float* out, const float* lse, const float* d_out,

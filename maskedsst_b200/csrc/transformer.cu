@@ -38,6 +38,13 @@ static bool attn_fused(const msst_tf_dims* d) {
     return attn_block_supported(g, d->D);
 }
 
+// bf16 mode: the FeedForward block as one kernel (mlp_block_tc.cu).  MSST_MLP_FUSED=0 selects the two GEMM launches.
+static bool mlp_fused(const msst_tf_dims* d) {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MSST_MLP_FUSED"); v = e ? atoi(e) : 1; }
+    return v && d->prec == MSST_PREC_BF16 && mlp_block_supported(d->D, d->M);
+}
+
 static TfLayout make_layout(const msst_tf_dims* d) {
     TfLayout L{};
     L.R = d->n_seq * d->N; L.I = d->H * d->dh;
@@ -158,6 +165,18 @@ static int tf_fwd_bf16(const msst_tf_dims* d, const msst_layer_params* layers, c
         if (fuse_ln) { a.ln_w = p.ln2_w; a.ln_b = p.ln2_b; a.ln_out = h2; a.ln_stats = stats2; }
         if (int rc = gemm_tn_bf16(a, st)) return rc;
         if (!fuse_ln) { if (int rc = layernorm_fwd(xmid, p.ln2_w, p.ln2_b, h2, 1, stats2, R, D, 1e-5f, st)) return rc; }
+        if (mlp_fused(d)) {   // Linear -> GELU -> dropout -> Linear -> dropout -> + xmid (-> LN1 of the next layer): one kernel
+            const bool next_ln = l + 1 < d->L;
+            char* nlw = ws + L.layer_bytes * (d->save_for_backward ? l + 1 : 0);
+            if (int rc = mlp_block_fwd(h2, xmid, w.w1, w.w2, p.b1, p.b2, u, g, y, next_ln ? layers[l + 1].ln1_w : nullptr,
+                                       next_ln ? layers[l + 1].ln1_b : nullptr,
+                                       next_ln ? (d->save_for_backward ? (bf16*)(nlw + L.o_h1) : h) : nullptr,
+                                       next_ln ? (float*)(nlw + L.o_stats1) : nullptr, R, D, M,
+                                       make_drop(d->drop_p, d->seed, site + kSiteMlpHidden, d->seed_dev),
+                                       make_drop(d->drop_p, d->seed, site + kSiteMlpOut, d->seed_dev), st)) return rc;
+            x = y;
+            continue;
+        }
         a = gemm_args(h2, w.w1, R, M, D, g, 0);
         a.bias = p.b1; a.pre_act = u; a.act = 1; a.drop = make_drop(d->drop_p, d->seed, site + kSiteMlpHidden, d->seed_dev);
         if (int rc = gemm_tn_bf16(a, st)) return rc;
@@ -423,6 +442,14 @@ extern "C" int msst_attn_block_bwd(const msst_attn_dims* d, int D, const void* h
     if (g.n_seq == 0) return MSST_OK;
     return attn_block_bwd(g, D, (const bf16*)h, (const bf16*)w_qkv, (const bf16*)w_qkv_t, (const bf16*)d_out, lse, (bf16*)d_qkv, d_h,
                           make_drop(d->drop_p, d->seed, d->site, d->seed_dev), (cudaStream_t)stream);
+}
+extern "C" int msst_mlp_block_fwd(const void* h2, const float* xmid, const void* w1, const void* w2, const float* b1, const float* b2, void* u,
+                                  void* g, float* y, const float* ln_w, const float* ln_b, void* h1, float* ln_stats, int64_t R, int D, int M,
+                                  float drop_p, uint64_t seed, uint32_t site_hidden, uint32_t site_out, const uint64_t* seed_dev, msst_stream_t stream) {
+    MSST_REQUIRE(h2 && xmid && w1 && w2 && b1 && b2 && u && g && y, "mlp_block_fwd: null pointer");
+    MSST_REQUIRE(!h1 || (ln_w && ln_b && ln_stats), "mlp_block_fwd: h1 needs ln_w, ln_b and ln_stats");
+    return mlp_block_fwd((const bf16*)h2, xmid, (const bf16*)w1, (const bf16*)w2, b1, b2, (bf16*)u, (bf16*)g, y, ln_w, ln_b, (bf16*)h1, ln_stats, R, D, M,
+                         make_drop(drop_p, seed, site_hidden, seed_dev), make_drop(drop_p, seed, site_out, seed_dev), (cudaStream_t)stream);
 }
 extern "C" int msst_dropout_apply(const float* x, float* y, int64_t n, float p, uint64_t seed, uint32_t site,
                                   const uint64_t* seed_dev, msst_stream_t stream) {
