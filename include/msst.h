@@ -177,6 +177,13 @@ MSST_API int msst_mlp_block_fwd(const void* h2, const float* xmid, const void* w
                                 void* u, void* g, float* y, const float* ln_w, const float* ln_b, void* h1, float* ln_stats,
                                 int64_t R, int D, int M, float drop_p, uint64_t seed, uint32_t site_hidden, uint32_t site_out,
                                 const uint64_t* seed_dev, msst_stream_t stream);
+/* Backward of the block (autograd of FeedForward.forward :35-44) in one kernel: dyb [R,D] bf16 = the branch-output gradient after the
+ * output dropout, u / g as saved by the forward, h2 the block's input, w2_t = W2^T [64,D] and w1_t = W1^T [D,64] bf16.
+ * du = (dyb W2) * gelu'(u) * hidden-dropout stays on the SM;  d_w1 [64,D] += du^T h2,  d_w2 [D,64] += dyb^T g,  d_b1 [64] += colsum(du)
+ * (fp32, accumulated in TMEM over the launch),  d_h [R,D] fp32 = du W1 (the gradient w.r.t. h2). */
+MSST_API int msst_mlp_block_bwd(const void* dyb, const void* u, const void* g, const void* h2, const void* w2_t, const void* w1_t,
+                                float* d_w1, float* d_w2, float* d_b1, float* d_h, int64_t R, int D, int M, float drop_p, uint64_t seed,
+                                uint32_t site_hidden, const uint64_t* seed_dev, msst_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Transformer stack: L x { x = attn(LN(x)) + x ; x = ff(LN(x)) + x }  (Transformer.forward :100-104),

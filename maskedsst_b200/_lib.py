@@ -85,6 +85,7 @@ SIGNATURES = {
     "msst_attn_block_fwd": (C.c_int, [C.POINTER(AttnDims), C.c_int, vp, vp, vp, vp, vp]),
     "msst_attn_block_bwd": (C.c_int, [C.POINTER(AttnDims), C.c_int] + [vp] * 7 + [vp]),
     "msst_mlp_block_fwd": (C.c_int, [vp] * 13 + [C.c_int64, C.c_int, C.c_int, C.c_float, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp]),
+    "msst_mlp_block_bwd": (C.c_int, [vp] * 10 + [C.c_int64, C.c_int, C.c_int, C.c_float, C.c_uint64, C.c_uint32, vp, vp]),
     "msst_transformer_workspace_bytes": (C.c_int64, [C.POINTER(TfDims)]),
     "msst_transformer_fwd": (C.c_int, [C.POINTER(TfDims), C.POINTER(LayerPtrs), vp, vp, vp, vp]),
     "msst_transformer_bwd": (C.c_int, [C.POINTER(TfDims), C.POINTER(LayerPtrs), C.POINTER(LayerPtrs), vp, vp, vp, vp, vp]),

@@ -80,6 +80,9 @@ bool mlp_block_supported(int D, int M);
 int mlp_block_fwd(const __nv_bfloat16* h2, const float* xmid, const __nv_bfloat16* w1, const __nv_bfloat16* w2, const float* b1, const float* b2,
                   __nv_bfloat16* u, __nv_bfloat16* g, float* y, const float* ln_w, const float* ln_b, __nv_bfloat16* h1, float* ln_stats,
                   int64_t R, int D, int M, Drop drop_h, Drop drop_o, cudaStream_t st);
+// backward of the block: du = (dyb W2) gelu'(u) drop stays on the SM; dW1 / dW2 / db1 accumulate (+=), dh [R,D] fp32 = du W1
+int mlp_block_bwd(const __nv_bfloat16* dyb, const __nv_bfloat16* u, const __nv_bfloat16* g, const __nv_bfloat16* h2, const __nv_bfloat16* w2t,
+                  const __nv_bfloat16* w1t, float* dw1, float* dw2, float* db1, float* dh, int64_t R, int D, int M, Drop drop_h, cudaStream_t st);
 
 // attention_f32.cu
 int attention_fwd_f32(const msst_attn_dims* d, const float* qkv, float* out, float* lse, cudaStream_t st);

@@ -221,6 +221,14 @@ static int tf_bwd_bf16(const msst_tf_dims* d, const msst_layer_params* layers, c
         if (!dyb_ready) {
             if (int rc = cast_rows_f32(dcur, dyb, gr.b2, R, D, make_drop(d->drop_p, d->seed, site + kSiteMlpOut, d->seed_dev), st)) return rc;
         }
+        const bool fuse_lnb = (D % 4 == 0 && D <= 128) && lnb_enabled();
+        if (mlp_fused(d) && !fuse_lnb) {
+            // the whole FeedForward backward in one kernel: du never reaches HBM, dW1 / dW2 accumulate in TMEM across the launch
+            if (int rc = mlp_block_bwd(dyb, u, g, (const bf16*)(lw + L.o_h2), w.w2T, w.w1T, gr.w1, gr.w2, gr.b1, dh, R, D, M,
+                                       make_drop(d->drop_p, d->seed, site + kSiteMlpHidden, d->seed_dev), st)) return rc;
+            if (int rc = layernorm_bwd(xmid, p.ln2_w, stats2, dh, dcur, dxa, gr.ln2_w, gr.ln2_b, R, D, st, dyb,
+                                       make_drop(d->drop_p, d->seed, site + kSiteAttnOut, d->seed_dev), gr.b_out)) return rc;
+        } else {
         if (int rc = gemm_wgrad_bf16(dyb, g, gr.w2, R, D, M, st)) return rc;
         GemmBf16Args a = gemm_args(dyb, w.w2T, R, M, D, du, 0);        // du = (dy . W2) * gelu'(u) * hidden-dropout
         a.aux = u; a.act = 2; a.drop = make_drop(d->drop_p, d->seed, site + kSiteMlpHidden, d->seed_dev);
@@ -231,7 +239,6 @@ static int tf_bwd_bf16(const msst_tf_dims* d, const msst_layer_params* layers, c
         if (int rc = gemm_wgrad_bf16(du, (const bf16*)(lw + L.o_h2), gr.w1, R, M, D, st)) return rc;
         // LN2 backward -> dxa (fp32) + fused: dyb = bf16(dropout_attn_out(dxa)), db_out += colsum.  With fuse_lnb the LayerNorm
         // backward runs in the epilogue of the data-gradient GEMM that produces its dy (no [R,D] fp32 round trip, one launch less)
-        const bool fuse_lnb = (D % 4 == 0 && D <= 128) && lnb_enabled();
         if (fuse_lnb) {
             GemmBf16Args b = gemm_args(du, w.w1T, R, D, M, dxa, 1);
             b.residual = dcur; b.ln_w = p.ln2_w; b.lnb_x = xmid; b.lnb_stats = stats2; b.lnb_dw = gr.ln2_w; b.lnb_db = gr.ln2_b;
@@ -241,6 +248,7 @@ static int tf_bwd_bf16(const msst_tf_dims* d, const msst_layer_params* layers, c
             if (int rc = gemm_tn_bf16(gemm_args(du, w.w1T, R, D, M, dh, 1), st)) return rc;
             if (int rc = layernorm_bwd(xmid, p.ln2_w, stats2, dh, dcur, dxa, gr.ln2_w, gr.ln2_b, R, D, st, dyb,
                                        make_drop(d->drop_p, d->seed, site + kSiteAttnOut, d->seed_dev), gr.b_out)) return rc;
+        }
         }
         // ---- attention branch ----
         if (int rc = gemm_wgrad_bf16(dyb, o, gr.w_out, R, D, I, st)) return rc;
@@ -450,6 +458,13 @@ extern "C" int msst_mlp_block_fwd(const void* h2, const float* xmid, const void*
     MSST_REQUIRE(!h1 || (ln_w && ln_b && ln_stats), "mlp_block_fwd: h1 needs ln_w, ln_b and ln_stats");
     return mlp_block_fwd((const bf16*)h2, xmid, (const bf16*)w1, (const bf16*)w2, b1, b2, (bf16*)u, (bf16*)g, y, ln_w, ln_b, (bf16*)h1, ln_stats, R, D, M,
                          make_drop(drop_p, seed, site_hidden, seed_dev), make_drop(drop_p, seed, site_out, seed_dev), (cudaStream_t)stream);
+}
+extern "C" int msst_mlp_block_bwd(const void* dyb, const void* u, const void* g, const void* h2, const void* w2_t, const void* w1_t, float* d_w1,
+                                  float* d_w2, float* d_b1, float* d_h, int64_t R, int D, int M, float drop_p, uint64_t seed, uint32_t site_hidden,
+                                  const uint64_t* seed_dev, msst_stream_t stream) {
+    MSST_REQUIRE(dyb && u && g && h2 && w2_t && w1_t && d_w1 && d_w2 && d_b1 && d_h, "mlp_block_bwd: null pointer");
+    return mlp_block_bwd((const bf16*)dyb, (const bf16*)u, (const bf16*)g, (const bf16*)h2, (const bf16*)w2_t, (const bf16*)w1_t, d_w1, d_w2, d_b1, d_h,
+                         R, D, M, make_drop(drop_p, seed, site_hidden, seed_dev), (cudaStream_t)stream);
 }
 extern "C" int msst_dropout_apply(const float* x, float* y, int64_t n, float p, uint64_t seed, uint32_t site,
                                   const uint64_t* seed_dev, msst_stream_t stream) {

@@ -1,4 +1,4 @@
-"""GPU: the fused FeedForward kernel (csrc/mlp_block_tc.cu) through the C ABI against an fp64 torch restatement of
+"""GPU: the fused FeedForward kernels (csrc/mlp_block_tc.cu, forward and backward) through the C ABI against an fp64 torch restatement of
 Linear -> GELU(erf) -> Linear -> + residual -> LayerNorm (reference FeedForward.forward, src/vit_spatial_spectral.py:35-44,
 Transformer.forward :103, PreNorm :25-29), and -- with dropout on -- against the two-GEMM path it replaces (same masks)."""
 import ctypes as C
@@ -57,6 +57,70 @@ def test_mlp_block_vs_fp64(R, D, with_ln):
         assert rel_l2(h1, h1_ref) < 5e-3
         assert rel_l2(st[:, 0], y_ref.mean(-1)) < 1e-3
         assert rel_l2(st[:, 1], (y_ref.var(-1, unbiased=False) + 1e-5).rsqrt()) < 1e-3
+
+
+@pytest.mark.parametrize("R,D", [(128, 96), (1000, 96), (327, 64), (5, 32), (128 * 300 + 17, 96), (128 * 149, 96)])
+def test_mlp_block_bwd_vs_fp64(R, D):
+    """msst_mlp_block_bwd (one kernel: du on the SM, dW1 / dW2 / db1 accumulated in TMEM, dh by TMA store) against fp64 autograd of
+    Linear -> GELU(erf) -> Linear fed with the same bf16 operands; the gradients ACCUMULATE into non-zero buffers."""
+    torch.manual_seed(1)
+    M = 64
+    h2 = torch.randn(R, D).bfloat16()
+    dyb = torch.randn(R, D).bfloat16()
+    w1 = (torch.randn(M, D) * D ** -0.5).bfloat16()
+    w2 = (torch.randn(D, M) * M ** -0.5).bfloat16()
+    b1 = torch.randn(M) * 0.1
+    u = (h2.double() @ w1.double().t() + b1.double()).bfloat16()
+    g = torch.nn.functional.gelu(u.double()).bfloat16()
+    # fp64 reference on the saved (bf16-rounded) u / g, du rounded to bf16 before the two contractions that consume it (as the kernel does)
+    ud = u.double()
+    gp = 0.5 * (1 + torch.erf(ud / 2 ** 0.5)) + ud * torch.exp(-0.5 * ud * ud) / (2 * torch.pi) ** 0.5
+    du = (dyb.double() @ w2.double()) * gp
+    dub = du.bfloat16().double()
+    ref = {"dw2": dyb.double().t() @ g.double(), "dw1": dub.t() @ h2.double(), "db1": du.sum(0), "dh": dub @ w1.double()}
+    dev = lambda t: t.to(DEV)
+    init = {"dw1": torch.randn(M, D), "dw2": torch.randn(D, M), "db1": torch.randn(M)}
+    out = {k: dev(v.clone()) for k, v in init.items()}
+    dh = torch.full((R, D), float("nan"), device=DEV)
+    args = [dev(t) for t in (dyb, u, g, h2, w2.t().contiguous(), w1.t().contiguous())]
+    check(_lib.lib().msst_mlp_block_bwd(*[a.data_ptr() for a in args], out["dw1"].data_ptr(), out["dw2"].data_ptr(), out["db1"].data_ptr(), dh.data_ptr(),
+                                        R, D, M, 0.0, 0, 18, None, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert torch.isfinite(dh).all()
+    assert rel_l2(dh, ref["dh"]) < 2e-3, rel_l2(dh, ref["dh"])
+    for k in ("dw1", "dw2", "db1"):
+        got = out[k].cpu().double() - init[k].double()
+        assert rel_l2(got, ref[k]) < 2e-3, (k, rel_l2(got, ref[k]))
+
+
+def test_mlp_block_bwd_dropout_matches_unfused_kernels():
+    """dropout on: the fused backward regenerates the hidden-dropout mask of gemm_tn<4> (same site / quad indexing): du-dependent outputs agree
+    with the GEMM path run through msst_linear_bwd_data / msst_linear_bwd_weight."""
+    torch.manual_seed(2)
+    R, D, M, p, seed, site = 128 * 37 + 5, 96, 64, 0.25, 1234, 18
+    h2 = torch.randn(R, D, device=DEV).bfloat16(); dyb = torch.randn(R, D, device=DEV).bfloat16()
+    u = torch.randn(R, M, device=DEV).bfloat16(); g = torch.randn(R, M, device=DEV).bfloat16()
+    w1 = (torch.randn(M, D, device=DEV) * D ** -0.5).bfloat16(); w2 = (torch.randn(D, M, device=DEV) * M ** -0.5).bfloat16()
+    w1t, w2t = w1.t().contiguous(), w2.t().contiguous()
+    lib, st = _lib.lib(), torch.cuda.current_stream().cuda_stream
+    dw1, dw2, db1 = torch.zeros(M, D, device=DEV), torch.zeros(D, M, device=DEV), torch.zeros(M, device=DEV)
+    dh = torch.empty(R, D, device=DEV)
+    check(lib.msst_mlp_block_bwd(dyb.data_ptr(), u.data_ptr(), g.data_ptr(), h2.data_ptr(), w2t.data_ptr(), w1t.data_ptr(), dw1.data_ptr(), dw2.data_ptr(),
+                                 db1.data_ptr(), dh.data_ptr(), R, D, M, p, seed, site, None, st))
+    # unfused: du = (dyb . W2) * gelu'(u) * drop  (bf16)  ->  dW1 = du^T h2, dh = du . W1
+    du = torch.empty(R, M, device=DEV, dtype=torch.bfloat16)
+    dims = _lib.LinearDims(R, D, M, 0, p, seed, site, _lib.PREC_BF16, None, 0)          # dx[M_rows, K] = dy[M_rows, N] . W^T-copy[K, N]^T
+    check(lib.msst_linear_bwd_data(C.byref(dims), dyb.data_ptr(), w2t.data_ptr(), u.data_ptr(), None, du.data_ptr(), st))
+    dw1_ref = torch.zeros(M, D, device=DEV)
+    dims_w = _lib.LinearDims(R, M, D, 0, 0.0, 0, 0, _lib.PREC_BF16, None, 0)
+    check(lib.msst_linear_bwd_weight(C.byref(dims_w), du.data_ptr(), h2.data_ptr(), dw1_ref.data_ptr(), None, st))
+    torch.cuda.synchronize()
+    keep = (du.float() != 0).float().mean().item()
+    assert abs(keep - (1 - p)) < 0.01
+    assert rel_l2(dw1, dw1_ref) < 1e-3, rel_l2(dw1, dw1_ref)
+    assert rel_l2(db1, du.float().sum(0)) < 5e-3
+    assert rel_l2(dh, du.double() @ w1.double()) < 1e-3
+    assert rel_l2(dw2, dyb.double().t() @ g.double()) < 1e-3
 
 
 def test_fused_mlp_equals_two_gemm_path_with_dropout():
