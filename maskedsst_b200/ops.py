@@ -58,6 +58,41 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+# ---- gradient buffers -----------------------------------------------------------------------------------
+# The backward kernels ACCUMULATE (+=) parameter gradients.  Handing them freshly zeroed tensors makes autograd's
+# AccumulateGrad add every one of them into p.grad afterwards: one elementwise launch per parameter (~100 per step), which
+# is what a small-batch step spends its time on.  When the parameters live in a FusedAdam arena whose gradient arena has
+# just been zeroed (optimizer.zero_grad(): one memset, p.grad = None), the kernels write straight into the arena views and
+# autograd adopts the returned view as p.grad without launching anything.
+_arenas = []
+
+
+def register_grad_arena(arena):
+    _arenas.append(arena)
+
+
+def _grad_buffers(params):
+    """One fp32 buffer per tensor in `params` for a kernel to accumulate into; arena views for leaf parameters when allowed
+    (see above), slices of ONE zero-filled allocation for the rest."""
+    out = [None] * len(params)
+    fresh = []
+    for i, p in enumerate(params):
+        if p.is_leaf and p.requires_grad and p.grad is None:
+            for a in _arenas:
+                v = a.claim(p)
+                if v is not None:
+                    out[i] = v
+                    break
+        if out[i] is None:
+            fresh.append(i)
+    if fresh:
+        sizes = [params[i].numel() for i in fresh]
+        flat = torch.zeros(sum(sizes), device=params[fresh[0]].device, dtype=torch.float32)
+        for i, g in zip(fresh, torch.split(flat, sizes)):
+            out[i] = g.view(params[i].shape)
+    return out
+
+
 # ---- (1) patch embedding ------------------------------------------------------------------------------
 class PatchEmbedFn(torch.autograd.Function):
     """tokens[B,T,D] = [mask-select](LN_D(W_c LN_P(patch) + b_c)) + pos  (+ emb-dropout)."""
@@ -100,16 +135,15 @@ class PatchEmbedFn(torch.autograd.Function):
         img, pre_w, pre_b, W, bias, post_w, post_b, mask_u8 = ctx.saved_tensors
         dims = ctx.dims
         T, D = ctx.pos_shape
-        sizes = [pre_w.numel(), pre_b.numel(), W.numel(), bias.numel(), post_w.numel(), post_b.numel(), T * D, D]
-        flat = torch.zeros(sum(sizes), device=pre_w.device, dtype=torch.float32)
-        g = list(torch.split(flat, sizes))
+        g = _grad_buffers([pre_w, pre_b, W, bias, post_w, post_b])
+        g += list(torch.split(torch.zeros(T * D + D, device=pre_w.device, dtype=torch.float32), [T * D, D]))   # pos rows, mask token
         d_tokens = _c(d_tokens)
         d_pln = _c(d_pln) if d_pln is not None else None
         check(_lib.lib().msst_patch_embed_bwd(C.byref(dims), _p(img), _p(pre_w), _p(pre_b), _p(W), _p(bias), _p(post_w),
                                               _p(post_b), _p(mask_u8), _p(d_tokens), _p(d_pln), _p(g[0]), _p(g[1]), _p(g[2]),
                                               _p(g[3]), _p(g[4]), _p(g[5]), _p(g[6]), _p(g[7]) if ctx.has_mt else None,
                                               _stream()))
-        return (None, g[0], g[1], g[2].view_as(W), g[3].view_as(bias), g[4], g[5], g[6].view(T, D),
+        return (None, g[0], g[1], g[2], g[3], g[4], g[5], g[6].view(T, D),
                 g[7] if ctx.has_mt else None, None, None, None, None, None)
 
 
@@ -161,9 +195,7 @@ class TransformerStackFn(torch.autograd.Function):
         dims = ctx.dims
         L = dims.L
         dy = _c(dy)
-        sizes = [p.numel() for p in params]
-        flat = torch.zeros(sum(sizes), device=x.device, dtype=torch.float32)
-        grads = [g.view_as(p) for g, p in zip(torch.split(flat, sizes), params)]
+        grads = _grad_buffers(params)
         dx = torch.empty_like(x)
         check(_lib.lib().msst_transformer_bwd(C.byref(dims), _layer_array(params, L), _layer_array(grads, L), _p(x), _p(dy),
                                               _p(dx), _p(ws), _stream()))
@@ -190,22 +222,20 @@ class HeadFn(torch.autograd.Function):
         dims = _lib.HeadDims(B, C_, G, p1, D, nc)
         logits = torch.empty(B, nc, G * p1, G * p1, device=x.device, dtype=torch.float32)
         check(_lib.lib().msst_head_fwd(C.byref(dims), _p(x), _p(ln_w), _p(ln_b), _p(W), _p(bias), _p(logits), _stream()))
-        ctx.save_for_backward(x, ln_w, ln_b, W)
+        ctx.save_for_backward(x, ln_w, ln_b, W, bias)
         ctx.dims = dims
         return logits
 
     @staticmethod
     def backward(ctx, d_logits):
-        x, ln_w, ln_b, W = ctx.saved_tensors
+        x, ln_w, ln_b, W, bias = ctx.saved_tensors
         dims = ctx.dims
         d_logits = _c(d_logits)
-        sizes = [ln_w.numel(), ln_b.numel(), W.numel(), W.shape[0]]
-        flat = torch.zeros(sum(sizes), device=x.device, dtype=torch.float32)
-        g = torch.split(flat, sizes)
+        g = _grad_buffers([ln_w, ln_b, W, bias])
         dx = torch.empty_like(x)
         check(_lib.lib().msst_head_bwd(C.byref(dims), _p(x), _p(ln_w), _p(ln_b), _p(W), _p(d_logits), _p(dx), _p(g[0]), _p(g[1]),
                                        _p(g[2]), _p(g[3]), _stream()))
-        return dx, g[0], g[1], g[2].view_as(W), g[3], None
+        return dx, g[0], g[1], g[2], g[3], None
 
 
 def head(x, ln_w, ln_b, W, bias, *, geom):
@@ -301,15 +331,13 @@ class DecodeL1Fn(torch.autograd.Function):
         dims = ctx.dims
         d_loss = _c(d_loss.to(torch.float32))
         d_enc = torch.zeros_like(enc)
-        sizes = [W.numel(), bias.numel()]
-        flat = torch.zeros(sum(sizes), device=enc.device, dtype=torch.float32)
-        g = torch.split(flat, sizes)
+        g = _grad_buffers([W, bias])
         d_tgt = None
         if target_tokens is not None and ctx.needs_input_grad[3]:
             d_tgt = torch.zeros_like(target_tokens)
         check(_lib.lib().msst_simmim_decode_l1_bwd(C.byref(dims), _p(enc), _p(idx), _p(img), _p(target_tokens), _p(W), _p(bias),
                                                    _p(d_loss), _p(d_enc), _p(g[0]), _p(g[1]), _p(d_tgt), _stream()))
-        return d_enc, None, None, d_tgt, g[0].view_as(W), g[1].view_as(bias), None
+        return d_enc, None, None, d_tgt, g[0], g[1], None
 
 
 def simmim_decode_l1(enc, idx, img, target_tokens, W, bias, *, geom):

@@ -38,6 +38,10 @@ class FlatArena:
             self.group_ranges.append((start, total))
         self.params = torch.zeros(total, device=dev, dtype=torch.float32)
         self.grads = torch.zeros(total, device=dev, dtype=torch.float32)
+        # direct-gradient protocol (ops._grad_buffers): `clean` = the gradient arena has been zeroed and no optimiser step has
+        # consumed it since; `_claimed` = parameters whose arena view a backward kernel already accumulates into
+        self.clean = False
+        self._claimed = set()
         with torch.no_grad():
             for p in flat:
                 off, n = self.offsets[id(p)]
@@ -47,6 +51,31 @@ class FlatArena:
                 p.grad = self.grads[off: off + n].view(p.shape)
                 if old_grad is not None:
                     p.grad.copy_(old_grad)
+
+
+    def grad_view(self, p):
+        off, n = self.offsets[id(p)]
+        return self.grads[off: off + n].view(p.shape)
+
+    def claim(self, p):
+        """The arena view that a backward kernel may accumulate the gradient of parameter `p` into, or None (not ours, arena
+        not freshly zeroed, or already handed out in this accumulation window -- a second writer plus autograd's own sum of
+        the two returned views would double count)."""
+        if not self.clean:
+            return None
+        ent = self.offsets.get(id(p))
+        if ent is None or id(p) in self._claimed:
+            return None
+        self._claimed.add(id(p))
+        off, n = ent
+        return self.grads[off: off + n].view(p.shape)
+
+    def mark_zeroed(self):
+        self.clean = True
+        self._claimed = set()
+
+    def mark_consumed(self):
+        self.clean = False
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -80,20 +109,31 @@ class FusedAdam(torch.optim.Optimizer):
         # unused V1 merge layers): no moment update and, above all, NO weight decay.  In the arena every parameter has a
         # (zero) gradient view, so the set of parameters that actually received a gradient since zero_grad() is tracked
         # with post-accumulate hooks and only their arena ranges are updated.
-        self._touched = set()
+        self._touched = {}
         self._range_cache = {}
         self._hooks = [p.register_post_accumulate_grad_hook(self._mark) for g in groups for p in g if p.requires_grad]
+        from . import ops
+        ops.register_grad_arena(self.arena)
 
     def _mark(self, p):
-        self._touched.add(id(p))
+        self._touched[id(p)] = p
+        # zero_grad() leaves p.grad = None, so autograd ADOPTS whatever tensor arrives first: an arena view when the fused
+        # backward kernels wrote the gradient in place (nothing to do), otherwise a fresh tensor that is moved home here --
+        # before GradSync's hook (registered later) may launch the all-reduce of this arena range
+        g = p.grad
+        off, n = self._offsets[id(p)]
+        if g.data_ptr() != self.grad_arena.data_ptr() + 4 * off:
+            view = self.grad_arena[off: off + n].view(p.shape)
+            view.copy_(g)
+            p.grad = view
 
     def mark_all_touched(self):
         """For callers that write gradients into the arena without autograd."""
-        self._touched.update(self._offsets.keys())
+        self._touched.update({id(p): p for g in self.param_groups for p in g["params"]})
 
     def _ranges(self, gi):
         """Contiguous arena ranges (within group gi) of the parameters that received a gradient."""
-        key = (gi, frozenset(self._touched))
+        key = (gi, frozenset(self._touched.keys()))
         r = self._range_cache.get(key)
         if r is None:
             r = []
@@ -113,14 +153,17 @@ class FusedAdam(torch.optim.Optimizer):
 
     def _check_homes(self):
         """nn.Module.zero_grad() / p.grad = None re-allocates gradients outside the arena: training would silently stop."""
+        gbase, pbase = self.grad_arena.data_ptr(), self.param_arena.data_ptr()
         for g in self.param_groups:
             ps = g["params"]
             for p in (ps[0], ps[-1]) if ps else ():
                 off, n = self._offsets[id(p)]
-                if p.grad is None or p.grad.data_ptr() != self.grad_arena[off: off + 1].data_ptr() or \
-                        p.data_ptr() != self.param_arena[off: off + 1].data_ptr():
+                if (p.grad is not None and p.grad.data_ptr() != gbase + 4 * off) or p.data_ptr() != pbase + 4 * off:
                     raise RuntimeError("FusedAdam: a parameter or its .grad no longer lives in the flat arena (was "
-                                       "model.zero_grad() / p.grad = None / model.to() called?).  Use optimizer.zero_grad().")
+                                       "model.to() called, or p.grad assigned by hand?).  Use optimizer.zero_grad().")
+        if any(p.grad is None for p in self._touched.values()):
+            raise RuntimeError("FusedAdam: a parameter received a gradient and then lost it (model.zero_grad() / p.grad = None between "
+                               "backward and step?): its arena range would be stepped with stale data.  Use optimizer.zero_grad().")
 
     def offset_of(self, p):
         return self._offsets[id(p)]
@@ -132,10 +175,24 @@ class FusedAdam(torch.optim.Optimizer):
         return self.bf16_arena
 
     # ---- torch.optim API --------------------------------------------------------------------------------------
-    def zero_grad(self, set_to_none=False):
-        """One memset; gradients stay views of the arena (set_to_none would break the flat layout)."""
+    def zero_grad(self, set_to_none=True):
+        """One memset of the gradient arena.  With set_to_none (default, as torch.optim) p.grad becomes None: the next backward's
+        kernels then accumulate straight into the arena and autograd adopts those views as p.grad -- no AccumulateGrad launch per
+        parameter; a parameter that receives no gradient keeps p.grad = None and is skipped by step(), like torch.optim.  With
+        set_to_none=False the gradients stay (zeroed) arena views and autograd adds into them."""
         self.grad_arena.zero_()
-        self._touched = set()
+        self._touched = {}
+        if set_to_none:
+            for g in self.param_groups:
+                for p in g["params"]:
+                    p.grad = None
+            self.arena.mark_zeroed()
+        else:
+            for g in self.param_groups:
+                for p in g["params"]:
+                    if p.grad is None:
+                        p.grad = self.arena.grad_view(p)
+            self.arena.mark_consumed()
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -151,6 +208,7 @@ class FusedAdam(torch.optim.Optimizer):
         stream = torch.cuda.current_stream().cuda_stream
         lib = _lib.lib()
         self._check_homes()
+        self.arena.mark_consumed()
         for gi, g in enumerate(self.param_groups):
             for a, b in self._ranges(gi):
                 args = _lib.AdamArgs(float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),

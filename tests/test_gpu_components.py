@@ -138,7 +138,7 @@ def test_fused_adam_matches_torch_optim(decoupled, wd, clamp):
     ref = Opt(groups_ref, lr=0.008, weight_decay=wd)
     ours = FusedAdam(groups_our, lr=0.008, weight_decay=wd, decoupled=decoupled, clamp=clamp)
     for step in range(5):
-        ours.zero_grad()
+        ours.zero_grad(set_to_none=False)     # gradients stay arena views: they are written by hand below
         for rp, op in zip(ref_p, our_p):
             g = torch.randn(rp.shape) * 3
             rp.grad = g.clamp(-clamp, clamp) if clamp > 0 else g.clone()
@@ -172,8 +172,11 @@ def test_fused_adam_skips_parameters_without_gradient(decoupled):
     for rp, op, u in zip(ref_p, our_p, used):
         assert torch.allclose(op.detach().cpu(), rp.detach(), rtol=2e-6, atol=2e-7)
     assert ref_p[2].grad is None   # the premise: torch never touched them
-    # re-homing check: a gradient that left the arena is an error, not a silent no-op
+    # a gradient that left the arena after backward is an error, not a silent no-op
     our_p[0].grad = None
+    with pytest.raises(RuntimeError, match="arena"):
+        ours.step()
+    our_p[0].grad = torch.zeros_like(our_p[0])
     with pytest.raises(RuntimeError, match="arena"):
         ours.step()
 
