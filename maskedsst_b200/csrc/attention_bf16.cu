@@ -676,7 +676,11 @@ int attention_bwd_bf16(const msst_attn_dims* d, const bf16* qkv, const bf16* out
         }
         attn_bwd_bf16_heads_kernel<<<(unsigned)g.groups, BT, kBwdHeadsSmem, st>>>(g, qkv, lse, d_out, d_qkv, drop);
         MSST_LAUNCH_CHECK();
-    } else {   // long sequences: dQ pass over key tiles, dK/dV pass over query tiles (no atomics), cp.async double-buffered
+    } else {   // long sequences: dQ pass over key tiles, dK/dV pass over query tiles (no atomics)
+        // tcgen05 / TMEM kernels (attention_tc_long_bwd.cu) from N = MSST_ATTN_BWD_TC_LONG (default 256; 0 = never); else mma.sync, cp.async double-buffered
+        static int tc_from = -1;
+        if (tc_from < 0) { const char* e = getenv("MSST_ATTN_BWD_TC_LONG"); tc_from = e ? atoi(e) : 256; }
+        if (tc_from > 0 && g.N >= tc_from && attention_bwd_tc_long_supported(g)) return attention_bwd_tc_long(g, qkv, out, lse, d_out, d_qkv, drop, st);
         static PerDeviceOnce lattr;
         if (lattr.first()) {
             MSST_CUDA(cudaFuncSetAttribute(attn_bwd_bf16_long_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdLongSmem));

@@ -67,6 +67,11 @@ int attention_fwd_tc_long(const AttnGeom& g, const __nv_bfloat16* qkv, __nv_bflo
 int attention_bwd_tc(const AttnGeom& g, const __nv_bfloat16* qkv, const float* lse, const __nv_bfloat16* d_out, __nv_bfloat16* d_qkv,
                      Drop drop, cudaStream_t st);
 
+// attention_tc_long_bwd.cu (tcgen05 / TMEM backward for long sequences, N > 64): dK/dV pass + dQ pass, D = rowsum(dO * O) pre-pass
+bool attention_bwd_tc_long_supported(const AttnGeom& g);
+int attention_bwd_tc_long(const AttnGeom& g, const __nv_bfloat16* qkv, const __nv_bfloat16* out, const float* lse, const __nv_bfloat16* d_out,
+                          __nv_bfloat16* d_qkv, Drop drop, cudaStream_t st);
+
 // attn_block_tc.cu (tcgen05): per-head QKV projection fused into the attention kernels, N <= 64 -- q/k/v never reach HBM
 bool attn_block_supported(const AttnGeom& g, int D);
 int attn_block_fwd(const AttnGeom& g, int D, const __nv_bfloat16* h, const __nv_bfloat16* w_qkv, __nv_bfloat16* out, float* lse, Drop drop,

@@ -237,3 +237,47 @@ torch.save(out, sys.argv[1])
             res[flag] = torch.load(path)
     for k in res["1"]:
         assert rel_l2(res["1"][k], res["0"][k]) < 6e-3, (k, rel_l2(res["1"][k], res["0"][k]))
+
+
+def test_tcgen05_long_sequence_backward():
+    """N > 64: the tcgen05 / TMEM backward (attention_tc_long_bwd.cu: dK/dV pass + dQ pass over 64-key half steps, D = rowsum(dO * O)
+    pre-pass; default from N = 256, forced here for every N > 64) against the fp64 reference -- ragged tails, strided sequences,
+    several tiles per sequence -- and, with dropout on, against the mma.sync backward (MSST_ATTN_BWD_TC_LONG=0), which must see the
+    same mask."""
+    import os, subprocess, sys, tempfile
+    code = r'''
+import sys, torch
+sys.path.insert(0, ".")
+from maskedsst_b200 import ops
+from tests.test_gpu_components import ref_attention
+from tests.helpers import rel_l2
+torch.manual_seed(0)
+out = {}
+for k, (n_seq, N, inner, H) in enumerate([(3, 200, 1, 2), (2, 256, 2, 2), (5, 130, 1, 3), (1, 65, 1, 1), (4, 1000, 1, 2), (6, 128, 3, 2), (40, 512, 1, 8),
+                                          (300, 256, 1, 2)]):
+    R, I = n_seq * N, H * 64
+    qkv = torch.randn(R, 3 * I).bfloat16(); w = torch.randn(R, I).bfloat16()
+    a = qkv.double().requires_grad_(True)
+    want = ref_attention(a, n_seq, N, inner, H, 64); (want * w.double()).sum().backward()
+    b = qkv.cuda().requires_grad_(True)
+    got = ops.attention(b, n_seq=n_seq, N=N, inner=inner, heads=H, dim_head=64)
+    (got.float() * w.cuda().float()).sum().backward()
+    assert torch.isfinite(b.grad.float()).all()
+    assert rel_l2(b.grad, a.grad) < 1.5e-2, (n_seq, N, inner, H, rel_l2(b.grad, a.grad))
+    c = qkv.cuda().requires_grad_(True)
+    o = ops.attention(c, n_seq=n_seq, N=N, inner=inner, heads=H, dim_head=64, drop_p=0.2, seed=5, site=2)
+    (o.float() * w.cuda().float()).sum().backward()
+    out[k] = c.grad.float().cpu()
+torch.save(out, sys.argv[1])
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    with tempfile.TemporaryDirectory() as td:
+        for flag in ("65", "0"):
+            path = os.path.join(td, f"g{flag}.pt")
+            r = subprocess.run([sys.executable, "-c", code, path], cwd=root, env=dict(os.environ, MSST_ATTN_BWD_TC_LONG=flag),
+                               capture_output=True, text=True, timeout=900)
+            assert r.returncode == 0, r.stdout + r.stderr
+            res[flag] = torch.load(path)
+    for k in res["65"]:
+        assert rel_l2(res["65"][k], res["0"][k]) < 1e-2, (k, rel_l2(res["65"][k], res["0"][k]))
