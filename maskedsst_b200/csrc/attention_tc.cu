@@ -837,9 +837,13 @@ attn_fwd_tc_long_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
             int64_t ts = 0, tp = 0;          // next S step / next step whose pass-2 work (P~ V) is to be issued or skipped
             int ring_s = 0; uint32_t rph_s = 0; int ring_p = 0;
             int64_t npv = 0;                 // pass-2 steps issued so far (P~ buffer = npv & 1)
+            // (item, step within the item) of ts / tp, advanced incrementally (a 64-bit division per poll of this loop is ~100 instructions
+            // of the single issuing thread)
+            const int spi = (int)steps_per_item;
+            int64_t n_s = 0, n_p = 0; int rem_s = 0, rem_p = 0;
             while (tp < total) {
                 if (ts < total && ts <= tp + 1) {        // two S slots (a third measured slower: the softmax warps are the bottleneck)
-                    const int64_t n = ts / steps_per_item; const int rem = (int)(ts % steps_per_item);
+                    const int64_t n = n_s; const int rem = rem_s;
                     const int slot = (int)(ts & 1);
                     bool ok = mbar_try_wait(&bars->s_free[slot], (uint32_t)((ts >> 1) & 1) ^ 1) && mbar_try_wait(&bars->kv_full[ring_s], rph_s);
                     if (ok && rem == 0) ok = mbar_try_wait(&bars->q_full[n & 1], (uint32_t)(n >> 1) & 1);
@@ -851,12 +855,13 @@ attn_fwd_tc_long_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
                         umma_commit(&bars->s_full[slot]);
                         if (rem < nk) umma_commit(&bars->kv_empty[ring_s]);      // pass 1: K is not needed again
                         ++ts;
+                        if (++rem_s == spi) { rem_s = 0; ++n_s; }
                         if (++ring_s == 3) { ring_s = 0; rph_s ^= 1; }
                     }
                 }
                 if (tp < ts) {
-                    const int64_t n = tp / steps_per_item; const int rem = (int)(tp % steps_per_item);
-                    if (rem < nk) { ++tp; if (++ring_p == 3) ring_p = 0; }       // pass-1 step: nothing to issue
+                    const int64_t n = n_p; const int rem = rem_p;
+                    if (rem < nk) { ++tp; if (++rem_p == spi) { rem_p = 0; ++n_p; } if (++ring_p == 3) ring_p = 0; }       // pass-1 step: nothing to issue
                     else {
                         const int pb = (int)(npv & 1), os = (int)(n & 1), j = rem - nk;
                         bool ok = mbar_try_wait(&bars->p_full[pb], (uint32_t)(npv >> 1) & 1);
@@ -874,6 +879,7 @@ attn_fwd_tc_long_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
                             umma_commit(&bars->p_free[pb]);
                             if (j == nk - 1) { umma_commit(&bars->o_full[os]); umma_commit(&bars->q_empty[os]); }
                             ++npv; ++tp;
+                            if (++rem_p == spi) { rem_p = 0; ++n_p; }
                             if (++ring_p == 3) ring_p = 0;
                         }
                     }

@@ -19,6 +19,7 @@
 #include "attn_geom.cuh"
 #include "ptx.cuh"
 #include <stdlib.h>
+#include <stdio.h>
 
 namespace msst {
 using namespace ptx;
@@ -95,10 +96,11 @@ __global__ void __launch_bounds__(256) attn_rowdot_kernel(const bf16* __restrict
     }
 }
 
-template <int PASS>
+template <int PASS, bool DROP>
 __global__ void __launch_bounds__(LB_THREADS, 1)
 attn_bwd_tc_long_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do, const __grid_constant__ CUtensorMap tma_dqkv,
-                        AttnGeom g, const float* __restrict__ lse, const float* __restrict__ Dvec, Drop drop, int64_t n_items, int nt) {
+                        AttnGeom g, const float* __restrict__ lse, const float* __restrict__ Dvec, Drop drop, int64_t n_items, int nt, long long* dbg) {
+#define LB_T(t, slot) do { if (dbg && blockIdx.x == 0 && (t) < 64) dbg[(t) * 8 + (slot)] = clock64(); } while (0)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     if (smem_u32(smem) & 1023u) __trap();
@@ -113,8 +115,8 @@ attn_bwd_tc_long_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
 
     if (warp == 17 && elect_one()) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&bars->stat_full[s], 1); mbar_init(&bars->stat_empty[s], 1); mbar_init(&bars->s_full[s], 1); mbar_init(&bars->s_free[s], 16);
-            mbar_init(&bars->p_full[s], 16); mbar_init(&bars->p_free[s], 1); mbar_init(&bars->acc_full[s], 1); mbar_init(&bars->acc_free[s], 16);
+            mbar_init(&bars->stat_full[s], 1); mbar_init(&bars->stat_empty[s], 1); mbar_init(&bars->s_full[s], 1); mbar_init(&bars->s_free[s], 8);
+            mbar_init(&bars->p_full[s], 8); mbar_init(&bars->p_free[s], 1); mbar_init(&bars->acc_full[s], 1); mbar_init(&bars->acc_free[s], 16);
             mbar_init(&bars->stg_full[s], 16); mbar_init(&bars->stg_free[s], 1);
         }
         for (int s = 0; s < LB_RING; ++s) { mbar_init(&bars->ring_full[s], 1); mbar_init(&bars->ring_empty[s], 1); }
@@ -174,13 +176,18 @@ attn_bwd_tc_long_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
             const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0), idesc_mn = make_idesc_bf16(64, 64, 1, 1), idesc_q = make_idesc_bf16(128, 64, 0, 1);
             int64_t ts = 0, tp = 0;
             int ring_a = 0; uint32_t rph_a = 0; int ring_b = 0;
+            // (item, step within the item) of ts and tp, advanced incrementally: a 64-bit division per poll of this loop made the issuing
+            // thread the bottleneck of the kernel (~80 clks per MMA)
+            const int spi = (int)steps_per_item;
+            int64_t n_s = 0, n_p = 0; int rem_s = 0, rem_p = 0;
             while (tp < total) {
                 if (ts < total && ts <= tp + 1) {
-                    const int64_t n = ts / steps_per_item; const int rem = (int)(ts % steps_per_item);
+                    const int64_t n = n_s; const int rem = rem_s;
                     const int hh = rem & 1, slot = (int)(ts & 1);
                     bool ok = mbar_try_wait(&bars->s_free[slot], (uint32_t)((ts >> 1) & 1) ^ 1) && mbar_try_wait(&bars->ring_full[ring_a], rph_a);
                     if (ok && rem == 0) ok = mbar_try_wait(&bars->stat_full[n & 1], (uint32_t)(n >> 1) & 1);
                     if (ok) {
+                        LB_T(ts, 0);
                         tc_fence_after();
                         const uint32_t xs = smem_u32(stat_s + (size_t)(n & 1) * 2 * LB_TILE), ys = smem_u32(ring_s + (size_t)ring_a * 2 * LB_TILE);
                         // queries are the M dimension (TMEM lane = query row), the half's 64 keys the N dimension
@@ -191,15 +198,17 @@ attn_bwd_tc_long_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
                         for (int k = 0; k < 4; ++k) umma_bf16(d0 + 64, kdesc(do_a) + (uint64_t)(k * 2), kdesc(v_b) + (uint64_t)(k * 2), idesc_s, k != 0);     // dP_h = dO V_h^T
                         umma_commit(&bars->s_full[slot]);
                         ++ts;
+                        if (++rem_s == spi) { rem_s = 0; ++n_s; }
                         if (hh == 1 && ++ring_a == LB_RING) { ring_a = 0; rph_a ^= 1; }
                     }
                 }
                 if (tp < ts) {
-                    const int64_t n = tp / steps_per_item; const int rem = (int)(tp % steps_per_item);
+                    const int64_t n = n_p; const int rem = rem_p;
                     const int hh = rem & 1, tile = rem >> 1, pb = (int)(tp & 1), os = (int)(n & 1);
                     bool ok = mbar_try_wait(&bars->p_full[pb], (uint32_t)(tp >> 1) & 1);
                     if (ok && rem == 0) ok = mbar_try_wait(&bars->acc_free[os], (uint32_t)((n >> 1) & 1) ^ 1);
                     if (ok) {
+                        LB_T(tp, 1);
                         tc_fence_after();
                         const uint32_t xs = smem_u32(stat_s + (size_t)(n & 1) * 2 * LB_TILE), ys = smem_u32(ring_s + (size_t)ring_b * 2 * LB_TILE);
                         const uint32_t pa = smem_u32(p_s + (size_t)pb * LB_TILE), dsa = smem_u32(ds_s + (size_t)pb * LB_TILE);
@@ -217,8 +226,9 @@ attn_bwd_tc_long_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
                         }
                         umma_commit(&bars->p_free[pb]);
                         if (hh == 1) { umma_commit(&bars->ring_empty[ring_b]); if (++ring_b == LB_RING) ring_b = 0; }
-                        if (rem == steps_per_item - 1) { umma_commit(&bars->acc_full[os]); umma_commit(&bars->stat_empty[n & 1]); }
+                        if (rem == spi - 1) { umma_commit(&bars->acc_full[os]); umma_commit(&bars->stat_empty[n & 1]); }
                         ++tp;
+                        if (++rem_p == spi) { rem_p = 0; ++n_p; }
                     }
                 }
             }
@@ -243,8 +253,10 @@ attn_bwd_tc_long_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
             }
         }
     } else {
-        // ===== 512 softmax / epilogue threads: thread = (query row r of the tile, 16 of the half's 64 key columns) =====
-        const int lq = warp & 3, cq = warp >> 2;
+        // ===== two softmax groups of 8 warps ping-pong over the half steps (group = parity of the step = key half hh): thread = (query row r,
+        // 32 of the half's 64 key columns, handled as two rounds of 16 to keep the register footprint of 16 + 16 values); while one group
+        // waits for its S_h | dP_h or for its P~ / dS buffer, the other one issues.  The item epilogue uses all 16 warps (column quarter cq). =====
+        const int lq = warp & 3, cq = warp >> 2, grp = warp >> 3, ch = (warp >> 2) & 1;
         const int r = lq * 32 + lane;
         const uint32_t lane_base = (uint32_t)(lq * 32) << 16;
         const uint32_t swz = (uint32_t)(r & 7);
@@ -252,7 +264,6 @@ attn_bwd_tc_long_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
         const float sl2 = g.scale * 1.4426950408889634f;
         const uint64_t seed = drop.seed + (drop.seed_dev ? __ldg(drop.seed_dev) : 0ull);
         const uint32_t t16 = drop.thresh >> 16;
-        int64_t t = 0;
         for (int64_t n = 0; n < my_items; ++n) {
             int64_t seq; int h, stile;
             lb_item(g, blockIdx.x + n * gridDim.x, nt, seq, h, stile);
@@ -268,57 +279,68 @@ attn_bwd_tc_long_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
                         Dv = __ldg(Dvec + row * g.H + h);
                     }
                 }
-                for (int hh = 0; hh < 2; ++hh, ++t) {
-                    const int slot = (int)(t & 1), pb = slot;
-                    const uint32_t ph = (uint32_t)(t >> 1) & 1;
-                    mbar_wait(&bars->s_full[slot], ph);
-                    tc_fence_after();
+                const int hh = grp;
+                const int64_t t = n * steps_per_item + 2 * jt + hh;
+                const int slot = (int)(t & 1), pb = slot;
+                const uint32_t ph = (uint32_t)(t >> 1) & 1;
+                if (r == 0 && ch == 0) LB_T(t, 2);
+                mbar_wait(&bars->s_full[slot], ph);
+                if (r == 0 && ch == 0) LB_T(t, 3);
+                tc_fence_after();
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub) {
+                    const int cs = 2 * ch + sub;                // 16-column group of the half's 64 keys
                     float sp[16], dp[16];
                     {
                         uint32_t a[16], b[16];
-                        tmem_ld_32x16(tmem_base + lane_base + (uint32_t)slot * 128u + 16 * cq, a);
-                        tmem_ld_32x16(tmem_base + lane_base + (uint32_t)slot * 128u + 64 + 16 * cq, b);
+                        tmem_ld_32x16(tmem_base + lane_base + (uint32_t)slot * 128u + 16 * cs, a);
+                        tmem_ld_32x16(tmem_base + lane_base + (uint32_t)slot * 128u + 64 + 16 * cs, b);
                         tmem_ld_wait();
-                        tc_fence_before();
-                        warp_arrive(&bars->s_free[slot], lane);
+                        if (sub == 1) { tc_fence_before(); warp_arrive(&bars->s_free[slot], lane); }
 #pragma unroll
                         for (int j = 0; j < 16; ++j) { sp[j] = __uint_as_float(a[j]); dp[j] = __uint_as_float(b[j]); }
                     }
-                    // 64 x 64 tile coordinates of the forward kernels: qt64 = 2 qt + r / 64, kt64 = 2 kt + hh, pair = (r & 63) * 32 + 8 cq + jj
-                    const uint64_t hidx = ((((uint64_t)seq * g.H + h) * g.tiles + (uint64_t)(2 * qt + (r >> 6))) * g.tiles + (uint64_t)(2 * kt + hh)) *
-                                              (uint64_t)(TS * TS / 2) + (uint64_t)((r & 63) * 32 + 8 * cq);
-                    const uint32_t hash_lo = (uint32_t)hidx + (uint32_t)(seed >> 32);
-                    const uint32_t hash_hi = ((uint32_t)(hidx >> 32) * 0x85EBCA77u) ^ (uint32_t)seed ^ (drop.site * 0xC2B2AE3Du);
-                    const int nvalid = q_ok ? g.N - kt * LB_ROWS - hh * 64 - 16 * cq : 0;     // this thread's columns 0 .. nvalid-1 are real keys
+                    // 64 x 64 tile coordinates of the forward kernels: qt64 = 2 qt + r / 64, kt64 = 2 kt + hh, pair = (r & 63) * 32 + 8 cs + jj
+                    uint32_t hash_lo = 0, hash_hi = 0;
+                    if (DROP) {
+                        const uint64_t hidx = ((((uint64_t)seq * g.H + h) * g.tiles + (uint64_t)(2 * qt + (r >> 6))) * g.tiles + (uint64_t)(2 * kt + hh)) *
+                                                  (uint64_t)(TS * TS / 2) + (uint64_t)((r & 63) * 32 + 8 * cs);
+                        hash_lo = (uint32_t)hidx + (uint32_t)(seed >> 32);
+                        hash_hi = ((uint32_t)(hidx >> 32) * 0x85EBCA77u) ^ (uint32_t)seed ^ (drop.site * 0xC2B2AE3Du);
+                    }
+                    const int nvalid = q_ok ? g.N - kt * LB_ROWS - hh * 64 - 16 * cs : 0;     // this thread's columns 0 .. nvalid-1 are real keys
                     uint32_t pk[8], dk[8];
 #pragma unroll
                     for (int jj = 0; jj < 8; ++jj) {
                         const int j = 2 * jj;
-                        float f0 = 1.f, f1 = 1.f;
-                        if (drop.on()) {
+                        float p0 = j < nvalid ? ex2_approx(fmaf(sp[j], sl2, -L)) : 0.f;
+                        float p1 = j + 1 < nvalid ? ex2_approx(fmaf(sp[j + 1], sl2, -L)) : 0.f;
+                        float d0 = dp[j], d1 = dp[j + 1];
+                        if (DROP) {
                             uint32_t x = (hash_lo + (uint32_t)jj) * 0x9E3779B1u ^ hash_hi;
                             x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
-                            f0 = (x & 0xFFFFu) >= t16 ? drop.scale : 0.f;
-                            f1 = (x >> 16) >= t16 ? drop.scale : 0.f;
-                        }
-                        const float p0 = j < nvalid ? ex2_approx(fmaf(sp[j], sl2, -L)) : 0.f;
-                        const float p1 = j + 1 < nvalid ? ex2_approx(fmaf(sp[j + 1], sl2, -L)) : 0.f;
-                        if (PASS == 0) pk[jj] = pack_bf(p0 * f0, p1 * f1);
-                        dk[jj] = pack_bf(p0 * g.scale * (dp[j] * f0 - Dv), p1 * g.scale * (dp[j + 1] * f1 - Dv));
+                            const float f0 = (x & 0xFFFFu) >= t16 ? drop.scale : 0.f, f1 = (x >> 16) >= t16 ? drop.scale : 0.f;
+                            if (PASS == 0) pk[jj] = pack_bf(p0 * f0, p1 * f1);
+                            d0 *= f0; d1 *= f1;
+                        } else if (PASS == 0) pk[jj] = pack_bf(p0, p1);
+                        p0 *= g.scale; p1 *= g.scale;
+                        dk[jj] = pack_bf(p0 * (d0 - Dv), p1 * (d1 - Dv));
                     }
-                    mbar_wait(&bars->p_free[pb], ph ^ 1);       // the contractions of step t - 2 have read this P~ / dS buffer
+                    if (sub == 0) { if (r == 0 && ch == 0) LB_T(t, 4); mbar_wait(&bars->p_free[pb], ph ^ 1); if (r == 0 && ch == 0) LB_T(t, 5); }   // the contractions of step t - 2 have read this P~ / dS buffer
+                    const uint32_t o0 = (((uint32_t)(2 * cs)) ^ swz) << 4, o1 = (((uint32_t)(2 * cs + 1)) ^ swz) << 4;
                     if (PASS == 0) {
                         uint8_t* prow = p_s + (size_t)pb * LB_TILE + r * 128;
-                        *reinterpret_cast<uint4*>(prow + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        *reinterpret_cast<uint4*>(prow + c1o) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        *reinterpret_cast<uint4*>(prow + o0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4*>(prow + o1) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                     }
                     uint8_t* drow = ds_s + (size_t)pb * LB_TILE + r * 128;
-                    *reinterpret_cast<uint4*>(drow + c0) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
-                    *reinterpret_cast<uint4*>(drow + c1o) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
-                    fence_proxy_async();
-                    tc_fence_before();
-                    warp_arrive(&bars->p_full[pb], lane);
+                    *reinterpret_cast<uint4*>(drow + o0) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+                    *reinterpret_cast<uint4*>(drow + o1) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
                 }
+                fence_proxy_async();
+                tc_fence_before();
+                warp_arrive(&bars->p_full[pb], lane);
+                if (r == 0 && ch == 0) LB_T(t, 6);
             }
             // ---- item epilogue: accumulators -> bf16 -> staging tiles -> TMA store ----
             const int os = (int)(n & 1);
@@ -365,6 +387,7 @@ attn_bwd_tc_long_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
     tc_fence_before();
     __syncthreads();
     if (warp == 16) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+#undef LB_T
 }
 
 // 4-D view whose box is 128 consecutive positions of ONE sequence (rows beyond the sequence end: zero on load, clipped on store)
@@ -405,8 +428,10 @@ int attention_bwd_tc_long(const AttnGeom& g, const bf16* qkv, const bf16* out, c
     MSST_REQUIRE(attention_bwd_tc_long_supported(g), "attention_bwd_tc_long: needs N > 64");
     static PerDeviceOnce once;
     if (once.first()) {
-        MSST_CUDA(cudaFuncSetAttribute(attn_bwd_tc_long_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLbSmem));
-        MSST_CUDA(cudaFuncSetAttribute(attn_bwd_tc_long_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLbSmem));
+        MSST_CUDA(cudaFuncSetAttribute(attn_bwd_tc_long_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLbSmem));
+        MSST_CUDA(cudaFuncSetAttribute(attn_bwd_tc_long_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLbSmem));
+        MSST_CUDA(cudaFuncSetAttribute(attn_bwd_tc_long_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLbSmem));
+        MSST_CUDA(cudaFuncSetAttribute(attn_bwd_tc_long_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLbSmem));
     }
     const int64_t I = (int64_t)g.H * 64, rows = g.n_seq * g.N;
     float* D = rowdot_scratch((size_t)rows * g.H);
@@ -423,10 +448,34 @@ int attention_bwd_tc_long(const AttnGeom& g, const bf16* qkv, const bf16* out, c
     if (int rc = lb_tmap(&t_do, g, d_out, I)) return rc;
     if (int rc = lb_tmap(&t_dqkv, g, d_qkv, 3 * I)) return rc;
     const int grid = (int)(n_items < kNumSMs ? n_items : kNumSMs);
-    attn_bwd_tc_long_kernel<0><<<grid, LB_THREADS, kLbSmem, st>>>(t_qkv, t_do, t_dqkv, g, lse, D, drop, n_items, nt);
+    static int dbg_on = -1;
+    static long long* dbg = nullptr;
+    if (dbg_on < 0) { const char* e = getenv("MSST_LB_DBG"); dbg_on = e ? atoi(e) : 0; if (dbg_on) cudaMalloc(&dbg, 2 * 64 * 8 * 8); }
+    if (dbg_on) cudaMemsetAsync(dbg, 0, 2 * 64 * 8 * 8, st);
+    if (drop.on()) {
+        attn_bwd_tc_long_kernel<0, true><<<grid, LB_THREADS, kLbSmem, st>>>(t_qkv, t_do, t_dqkv, g, lse, D, drop, n_items, nt, nullptr);
+        MSST_LAUNCH_CHECK();
+        attn_bwd_tc_long_kernel<1, true><<<grid, LB_THREADS, kLbSmem, st>>>(t_qkv, t_do, t_dqkv, g, lse, D, drop, n_items, nt, nullptr);
+    } else {
+        attn_bwd_tc_long_kernel<0, false><<<grid, LB_THREADS, kLbSmem, st>>>(t_qkv, t_do, t_dqkv, g, lse, D, drop, n_items, nt, dbg);
+        MSST_LAUNCH_CHECK();
+        attn_bwd_tc_long_kernel<1, false><<<grid, LB_THREADS, kLbSmem, st>>>(t_qkv, t_do, t_dqkv, g, lse, D, drop, n_items, nt, dbg ? dbg + 64 * 8 : nullptr);
+    }
     MSST_LAUNCH_CHECK();
-    attn_bwd_tc_long_kernel<1><<<grid, LB_THREADS, kLbSmem, st>>>(t_qkv, t_do, t_dqkv, g, lse, D, drop, n_items, nt);
-    MSST_LAUNCH_CHECK();
+    if (dbg_on) {
+        static int calls = 0;
+        if (++calls == dbg_on) {
+            static long long hbuf[2 * 64 * 8];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(hbuf, dbg, sizeof(hbuf), cudaMemcpyDeviceToHost);
+            for (int pass = 0; pass < 2; ++pass) {
+                printf("attn_bwd_tc_long pass %d timeline, CTA 0, per half step: S issue | contractions issue | (group thread 0) wait S | S ready | computed | buffer free | written\n", pass);
+                const long long* hb = hbuf + pass * 64 * 8; const long long t0 = hb[0];
+                for (int i = 0; i < 40; ++i) { printf("%2d:", i); for (int k = 0; k < 7; ++k) printf(" %7lld", hb[i * 8 + k] ? hb[i * 8 + k] - t0 : -1); printf("\n"); }
+            }
+            fflush(stdout);
+        }
+    }
     return MSST_OK;
 }
 
