@@ -177,7 +177,7 @@ __device__ __forceinline__ void load_w_slice(const AbParams& p, const CUtensorMa
 }
 // MMA issuer: [Q|K|V] of the item (tile counter k, head h) = h tile x the head's three weight sub-slices -> TMEM columns [0, 192)
 template <int NCH>
-__device__ __forceinline__ void issue_prologue(const AbParams& p, const AbCommon& s, int64_t k, int h, Ring& r) {
+__device__ __forceinline__ void issue_prologue(const AbParams& p, const AbCommon& s, int64_t k, int h, Ring& r, bool lead) {
     const int buf = (int)(k & 1);
     if (h == 0) mbar_wait(&s.bars->h_full[buf], (uint32_t)(k >> 1) & 1);
     const uint64_t ha = make_smem_desc_sw64(s.h_addr + (uint32_t)buf * p.hbuf_bytes);
@@ -189,13 +189,13 @@ __device__ __forceinline__ void issue_prologue(const AbParams& p, const AbCommon
         const uint64_t wa = make_smem_desc_sw64(s.w_addr + (uint32_t)r.slot * p.slot_bytes);
 #pragma unroll
         for (int ks = 0; ks < 2 * NCH; ++ks)
-            umma_bf16(s.tmem + COL_P + 64 * t, ha + (uint64_t)(((ks >> 1) * 8192 + (ks & 1) * 32) >> 4), wa + (uint64_t)(((ks >> 1) * 4096 + (ks & 1) * 32) >> 4),
+            if (lead) umma_bf16(s.tmem + COL_P + 64 * t, ha + (uint64_t)(((ks >> 1) * 8192 + (ks & 1) * 32) >> 4), wa + (uint64_t)(((ks >> 1) * 4096 + (ks & 1) * 32) >> 4),
                       idesc, ks != 0);
-        umma_commit(&s.bars->w_empty[r.slot]);
+        if (lead) umma_commit(&s.bars->w_empty[r.slot]);
         r.next();
     }
-    if (h == p.g.H - 1) umma_commit(&s.bars->h_empty[buf]);
-    umma_commit(&s.bars->pro_full);
+    if (lead && h == p.g.H - 1) umma_commit(&s.bars->h_empty[buf]);
+    if (lead) umma_commit(&s.bars->pro_full);
 }
 // backward variant: ONE weight layout serves both uses.  The ring holds W^T column blocks [D rows][64 features] (SWIZZLE_128B) of
 // (t, h): here they are the MN-major B operand of the recomputation (N = 64 features contiguous, K = D rows, 16 rows = 2 KB per
@@ -204,7 +204,7 @@ __device__ __forceinline__ void issue_prologue(const AbParams& p, const AbCommon
 // item's blocks then arrive ~2 k clks late (measured); fetched per use, every load has a whole item of latency budget.
 // Single h buffer: tile k + 1 is loaded while the last items of tile k (whose recomputation was issued earlier) still run.
 template <int NCH>
-__device__ __forceinline__ void issue_prologue_bwd(const AbParams& p, const AbCommon& s, int64_t k, int h, Ring& r) {
+__device__ __forceinline__ void issue_prologue_bwd(const AbParams& p, const AbCommon& s, int64_t k, int h, Ring& r, bool lead) {
     if (h == 0) mbar_wait(&s.bars->h_full[0], (uint32_t)k & 1);
     const uint64_t ha = make_smem_desc_sw64(s.h_addr);
     const uint32_t idesc = make_idesc_bf16(128, 64, 0, 1);
@@ -215,12 +215,12 @@ __device__ __forceinline__ void issue_prologue_bwd(const AbParams& p, const AbCo
         const uint64_t wa = mndesc(s.w_addr + (uint32_t)r.slot * p.slot_bytes);
 #pragma unroll
         for (int ks = 0; ks < 2 * NCH; ++ks)
-            umma_bf16(s.tmem + COL_P + 64 * t, ha + (uint64_t)(((ks >> 1) * 8192 + (ks & 1) * 32) >> 4), wa + (uint64_t)(ks * 128), idesc, ks != 0);
-        umma_commit(&s.bars->w_empty[r.slot]);
+            if (lead) umma_bf16(s.tmem + COL_P + 64 * t, ha + (uint64_t)(((ks >> 1) * 8192 + (ks & 1) * 32) >> 4), wa + (uint64_t)(ks * 128), idesc, ks != 0);
+        if (lead) umma_commit(&s.bars->w_empty[r.slot]);
         r.next();
     }
-    if (h == p.g.H - 1) umma_commit(&s.bars->h_empty[0]);
-    umma_commit(&s.bars->pro_full);
+    if (lead && h == p.g.H - 1) umma_commit(&s.bars->h_empty[0]);
+    if (lead) umma_commit(&s.bars->pro_full);
 }
 // compute threads: Q, K, V accumulators (fp32, TMEM lane L = tile row L) -> bf16 smem tiles at qkv (Q | K | V, 16 KB each)
 __device__ __forceinline__ void convert_qkv(uint32_t tmem, uint8_t* qkv, uint32_t lane_addr, int L, int cq) {
@@ -316,26 +316,28 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
         }
     } else if (warp == 17) {
         // ===== MMA issuer: prologue(0), S(0), prologue(1); then per item: O(i), S(i+1), prologue(i+2) =====
-        if (elect_one() && n_items > 0) {
+        // (the whole warp runs the control flow, one elected lane issues: see the backward kernel)
+        if (n_items > 0) {
+            const bool lead = elect_one();
             Ring r{0, 0u, p.NR};
             const uint32_t idesc_s = make_idesc_bf16(64, 64, 0, 0), idesc_o = make_idesc_bf16(64, 64, 0, 1);
             const uint32_t qkv_addr = smem_u32(qkv_s);
             const uint64_t pd0 = kdesc(smem_u32(p_s)), pd1 = kdesc(smem_u32(p_s) + AB_BLK);
             int64_t pk = 0; int phd = 0;                          // (tile counter, head) of the next prologue
-            auto next_pro = [&]() { issue_prologue<NCH>(p, s, pk, phd, r); if (++phd == H) { phd = 0; ++pk; } };
+            auto next_pro = [&]() { issue_prologue<NCH>(p, s, pk, phd, r, lead); if (++phd == H) { phd = 0; ++pk; } };
             auto issue_s = [&](int64_t it) {
                 const uint32_t qa = qkv_addr + (uint32_t)(it & 1) * 3 * AB_T16;
                 mbar_wait(&bars->conv_done, (uint32_t)it & 1);    // Q, K, V tiles written (generic proxy + the writers' fence)
-                AB_T(it, 8);
+                if (lead) AB_T(it, 8);
                 tc_fence_after();
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
                     const uint64_t dq = kdesc(qa + b * AB_BLK), dk = kdesc(qa + AB_T16 + b * AB_BLK);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)                // S_b = Q_b K_b^T
-                        umma_bf16(s.tmem + COL_S + ((uint32_t)(16 * b) << 16), dq + (uint64_t)(ks * 2), dk + (uint64_t)(ks * 2), idesc_s, ks != 0);
+                        if (lead) umma_bf16(s.tmem + COL_S + ((uint32_t)(16 * b) << 16), dq + (uint64_t)(ks * 2), dk + (uint64_t)(ks * 2), idesc_s, ks != 0);
                 }
-                umma_commit(&bars->s_full);
+                if (lead) umma_commit(&bars->s_full);
             };
             next_pro();
             issue_s(0);
@@ -343,21 +345,21 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
             for (int64_t it = 0; it < n_items; ++it) {
                 const uint32_t va = qkv_addr + (uint32_t)(it & 1) * 3 * AB_T16 + 2 * AB_T16;
                 mbar_wait(&bars->p_full, (uint32_t)it & 1);
-                AB_T(it, 10);
+                if (lead) AB_T(it, 10);
                 tc_fence_after();
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
                     const uint64_t dv = mndesc(va + b * AB_BLK), dp = b ? pd1 : pd0;
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)                // O_b = P~_b V_b (V as MN-major B)
-                        umma_bf16(s.tmem + COL_O + ((uint32_t)(16 * b) << 16), dp + (uint64_t)(ks * 2), dv + (uint64_t)(ks * 128), idesc_o, ks != 0);
+                        if (lead) umma_bf16(s.tmem + COL_O + ((uint32_t)(16 * b) << 16), dp + (uint64_t)(ks * 2), dv + (uint64_t)(ks * 128), idesc_o, ks != 0);
                 }
-                umma_commit(&bars->o_full);
+                if (lead) umma_commit(&bars->o_full);
                 if (it + 1 < n_items) {
                     issue_s(it + 1);
                     if (it + 2 < n_items) next_pro();             // the accumulators of item it + 1 were read before its conv_done
                 }
-                AB_T(it, 9);
+                if (lead) AB_T(it, 9);
             }
         }
     } else if (warp == 18) {
@@ -577,19 +579,23 @@ attn_block_bwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
         }
     } else if (warp == 17) {
         // ===== MMA issuer.  Order: prologue(0), S|dP(0), phase2(0), prologue(1); then per item i: S|dP(i+1), dgrad(i), phase2(i+1), prologue(i+2) =====
-        if (elect_one() && n_items > 0) {
+        // The whole warp runs the control flow (waits, ring / descriptor arithmetic: warp-uniform, so it lives in uniform registers) and one
+        // elected lane issues the tcgen05 instructions: with everything under elect_one() every descriptor crossed from vector to uniform
+        // registers before each UMMA group (~13 instructions per UMMA on a single dependent-issue warp that sits on the item's critical path)
+        if (n_items > 0) {
+            const bool lead = elect_one();
             Ring r{0, 0u, p.NR};
             const uint32_t idesc_kk = make_idesc_bf16(64, 64, 0, 0), idesc_mn = make_idesc_bf16(64, 64, 1, 1), idesc_kmn = make_idesc_bf16(64, 64, 0, 1);
             const uint32_t idesc_dh = make_idesc_bf16(128, D, 0, 0);
             const uint32_t qa = smem_u32(qkv_s), ka = qa + AB_T16, va = ka + AB_T16, pa = smem_u32(p_s), dsa = smem_u32(ds_s);
             int64_t pk = 0; int phd = 0;                          // (tile counter, head) of the next prologue
-            auto next_pro = [&]() { issue_prologue_bwd<NCH>(p, s, pk, phd, r); if (++phd == H) { phd = 0; ++pk; } };
+            auto next_pro = [&]() { issue_prologue_bwd<NCH>(p, s, pk, phd, r, lead); if (++phd == H) { phd = 0; ++pk; } };
             auto issue_sdp = [&](int64_t it) {                    // S_b = Q_b K_b^T | dP_b = dO_b V_b^T  -> the (dead) prologue columns [0, 128)
                 const int st = (int)(it & 1);
                 const uint32_t doa = smem_u32(do_s) + (uint32_t)st * AB_T16;
                 mbar_wait(&bars->conv_done, (uint32_t)it & 1);
                 mbar_wait(&bars->do_full[st], (uint32_t)(it >> 1) & 1);
-                AB_T(it, 8);
+                if (lead) AB_T(it, 8);
                 tc_fence_after();
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
@@ -597,18 +603,18 @@ attn_block_bwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
                     const uint64_t dq = kdesc(qa + b * AB_BLK), dk = kdesc(ka + b * AB_BLK), dd = kdesc(doa + b * AB_BLK), dv = kdesc(va + b * AB_BLK);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
-                        umma_bf16(s.tmem + COL_P + lane_off, dq + (uint64_t)(ks * 2), dk + (uint64_t)(ks * 2), idesc_kk, ks != 0);
+                        if (lead) umma_bf16(s.tmem + COL_P + lane_off, dq + (uint64_t)(ks * 2), dk + (uint64_t)(ks * 2), idesc_kk, ks != 0);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
-                        umma_bf16(s.tmem + COL_P + 64 + lane_off, dd + (uint64_t)(ks * 2), dv + (uint64_t)(ks * 2), idesc_kk, ks != 0);
+                        if (lead) umma_bf16(s.tmem + COL_P + 64 + lane_off, dd + (uint64_t)(ks * 2), dv + (uint64_t)(ks * 2), idesc_kk, ks != 0);
                 }
-                umma_commit(&bars->s_full);
+                if (lead) umma_commit(&bars->s_full);
             };
             auto issue_phase2 = [&](int64_t it) {                 // dV | dK | dQ of item it -> X
                 const int st = (int)(it & 1);
                 const uint32_t doa = smem_u32(do_s) + (uint32_t)st * AB_T16;
                 mbar_wait(&bars->p_full, (uint32_t)it & 1);       // P~ and dS written
-                AB_T(it, 10);
+                if (lead) AB_T(it, 10);
                 tc_fence_after();
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
@@ -617,15 +623,15 @@ attn_block_bwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
                     const uint64_t kds = kdesc(dsa + b * AB_BLK), mk = mndesc(ka + b * AB_BLK);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)                // dV_b = P~_b^T dO_b (reduction over the block's 64 queries, 16 rows = 2 KB per step)
-                        umma_bf16(s.tmem + COL_X + lane_off, mp + (uint64_t)(ks * 128), mdo + (uint64_t)(ks * 128), idesc_mn, ks != 0);
+                        if (lead) umma_bf16(s.tmem + COL_X + lane_off, mp + (uint64_t)(ks * 128), mdo + (uint64_t)(ks * 128), idesc_mn, ks != 0);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)                // dK_b = dS_b^T Q_b
-                        umma_bf16(s.tmem + COL_X + 64 + lane_off, mds + (uint64_t)(ks * 128), mq + (uint64_t)(ks * 128), idesc_mn, ks != 0);
+                        if (lead) umma_bf16(s.tmem + COL_X + 64 + lane_off, mds + (uint64_t)(ks * 128), mq + (uint64_t)(ks * 128), idesc_mn, ks != 0);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)                // dQ_b = dS_b K_b
-                        umma_bf16(s.tmem + COL_X + 128 + lane_off, kds + (uint64_t)(ks * 2), mk + (uint64_t)(ks * 128), idesc_kmn, ks != 0);
+                        if (lead) umma_bf16(s.tmem + COL_X + 128 + lane_off, kds + (uint64_t)(ks * 2), mk + (uint64_t)(ks * 128), idesc_kmn, ks != 0);
                 }
-                umma_commit(&bars->o_full);
+                if (lead) umma_commit(&bars->o_full);
             };
             // the recomputation of item i + 2 is issued as soon as the softmax threads hold S | dP of item i + 1 in registers (sdp_read), i.e.
             // BEFORE the dV | dK | dQ contractions of item i + 1: behind them in the in-order tensor pipe it finished ~1 k clks after o_full
@@ -643,7 +649,7 @@ attn_block_bwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
                 if (it + 1 < n_items) issue_sdp(it + 1);
                 // ---- data gradient of the projection: dh (+)= [dQ | dK | dV] (bf16 rows in TMEM) x W^T blocks ----
                 mbar_wait(&bars->a_ready, (uint32_t)it & 1);
-                AB_T(it, 11);
+                if (lead) AB_T(it, 11);
                 if (h == 0 && k > 0) mbar_wait(&bars->dh_free, (uint32_t)(k - 1) & 1);   // the previous tile's dh rows have been read
                 tc_fence_after();
 #pragma unroll
@@ -653,16 +659,16 @@ attn_block_bwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
                     const uint64_t bw = kdesc(s.w_addr + (uint32_t)r.slot * p.slot_bytes);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
-                        umma_bf16_ts(s.tmem + COL_DH, s.tmem + COL_X + 32 * t + 8 * ks, bw + (uint64_t)(ks * 2), idesc_dh, (h | t | ks) != 0);
-                    umma_commit(&bars->w_empty[r.slot]);
+                        if (lead) umma_bf16_ts(s.tmem + COL_DH, s.tmem + COL_X + 32 * t + 8 * ks, bw + (uint64_t)(ks * 2), idesc_dh, (h | t | ks) != 0);
+                    if (lead) umma_commit(&bars->w_empty[r.slot]);
                     r.next();
                 }
-                if (h == H - 1) umma_commit(&bars->dh_full);
-                AB_T(it, 12);
+                if (h == H - 1) if (lead) umma_commit(&bars->dh_full);
+                if (lead) AB_T(it, 12);
                 if (it + 1 < n_items) {
                     if (it + 2 < n_items) pro_after_read(it + 1);
                     issue_phase2(it + 1);
-                    AB_T(it, 9);
+                    if (lead) AB_T(it, 9);
                 }
                 if (++h == H) { h = 0; ++k; }
             }
