@@ -170,7 +170,7 @@ class Workload:
         import torch
         import maskedsst_b200 as M
         from maskedsst_b200.optim import FusedAdam
-        from maskedsst_b200.dp import GradSync
+        from maskedsst_b200.dp import GradSync, stage_boundaries
         self.ds, self.kind, self.B, self.dev, self.world = ds, workload, B, dev, world
         channels, ncls, _, _ = SHAPES[ds]
         self.channels = channels
@@ -204,7 +204,7 @@ class Workload:
             self.dev_y = [t.to(dev) for t in self.host_y]
         else:
             self.dev_masks = [self.model.draw_masks(B, dev) for _ in range(pool)]
-        self.sync = GradSync(self.opt.arena, num_buckets=3, overlap=overlap) if world > 1 else None
+        self.sync = GradSync(self.opt.arena, overlap=overlap, boundaries=stage_boundaries(self.model)) if world > 1 else None
 
     def step_resident(self, i):
         from maskedsst_b200.dp import cross_entropy_dp
@@ -335,7 +335,7 @@ def dp_parity_check(dev, rank, world):
     import torch.distributed as dist
     import maskedsst_b200 as M
     from maskedsst_b200.optim import FusedAdam
-    from maskedsst_b200.dp import GradSync
+    from maskedsst_b200.dp import GradSync, stage_boundaries
     Bl = 8
 
     def build():
@@ -357,7 +357,7 @@ def dp_parity_check(dev, rank, world):
         dist.broadcast(ix, 0)
         masks_g.append((mk8.bool(), ix))
     opt = FusedAdam(m.parameters(), lr=0.008, weight_decay=0.05, clamp=1.0, grad_scale=1.0 / world)
-    sync = GradSync(opt.arena, num_buckets=3)
+    sync = GradSync(opt.arena, boundaries=stage_boundaries(m))
     for s in range(2):
         sl = slice(rank * Bl, (rank + 1) * Bl)
         opt.zero_grad()

@@ -11,9 +11,29 @@ import torch
 import torch.distributed as dist
 
 
+def stage_boundaries(model):
+    """Parameters that start a new all-reduce bucket so that a bucket never straddles two backward stages: every transformer stack
+    (one autograd node: all of its gradients land together when the stack's backward returns) gets its own bucket, and so does
+    whatever follows it in parameter order.  With equal-size buckets the bucket holding the patch embedding also holds part of the
+    spatial stack, so that stack's gradient is exchanged only after the LAST backward kernel; cut at the stage edges it overlaps the
+    patch-embedding backward and only the (small) embedding bucket is exposed."""
+    order = list(model.parameters())
+    pos = {id(p): i for i, p in enumerate(order)}
+    cuts = set()
+    for mod in model.modules():
+        if hasattr(mod, "layer_params") and callable(mod.layer_params):
+            idx = sorted(pos[id(p)] for p in mod.parameters())
+            if idx:
+                cuts.add(idx[0])
+                if idx[-1] + 1 < len(order):
+                    cuts.add(idx[-1] + 1)
+    return [order[i] for i in sorted(cuts) if i > 0]
+
+
 class GradSync:
-    def __init__(self, arena, process_group=None, num_buckets=3, overlap=True):
-        """arena: maskedsst_b200.optim.FlatArena (FusedAdam(...).arena)."""
+    def __init__(self, arena, process_group=None, num_buckets=3, overlap=True, boundaries=None):
+        """arena: maskedsst_b200.optim.FlatArena (FusedAdam(...).arena).  boundaries: optional parameters that each START a new bucket
+        (see stage_boundaries); default: num_buckets roughly equal arena ranges."""
         self.arena = arena
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
@@ -25,12 +45,17 @@ class GradSync:
         total = arena.grads.numel()
         target = max(1, total // max(1, num_buckets))
         self.buckets, lo, members = [], 0, []
+        starts = None if boundaries is None else {id(p) for p in boundaries}
         for i, p in enumerate(params):
             off, n = arena.offsets[id(p)]
             members.append(p)
             end = (off + (n + 3) // 4 * 4)
             last = i == len(params) - 1
-            if last or (end - lo >= target and len(self.buckets) < num_buckets - 1):
+            if starts is not None:
+                cut = last or id(params[i + 1]) in starts
+            else:
+                cut = last or (end - lo >= target and len(self.buckets) < num_buckets - 1)
+            if cut:
                 self.buckets.append({"lo": lo, "hi": total if last else end, "params": members, "expected": None,
                                      "pending": 0, "work": None, "launched": False})
                 lo, members = end, []

@@ -119,3 +119,32 @@ def test_ce_valid_count_correction():
         g, = torch.autograd.grad(nll_sum * ce_dp_scale(cnt_global, world), logits)
         acc += g
     assert torch.allclose(acc / world, ggrad, atol=1e-7)
+
+
+def test_stage_boundaries_cut_buckets_at_the_transformer_stacks():
+    """dp.stage_boundaries: every transformer stack is its own all-reduce bucket (its gradients land together, one autograd node) and
+    the bucket that holds the patch embedding contains nothing of the spatial stack."""
+    import torch
+    import maskedsst_b200 as M
+    from maskedsst_b200.dp import GradSync, stage_boundaries
+    from maskedsst_b200.optim import FlatArena
+    enc = M.ViTSpatialSpectral(image_size=8, spatial_patch_size=1, spectral_patch_size=10, num_classes=20, dim=96, depth=2, heads=8, mlp_dim=64,
+                               channels=50, spectral_pos_embed=False)
+    m = M.SimMIMSpatialSpectral(encoder=enc, masking_ratio=0.7, mask_patch_size=4, tube_masking=True, to_pixels_per_spectral_block=True)
+    arena = FlatArena([list(m.parameters())])
+    sync = GradSync(arena, boundaries=stage_boundaries(m))
+    stacks = [mod for mod in m.modules() if hasattr(mod, "layer_params")]
+    assert len(stacks) == 2
+    owner = {}
+    for bi, b in enumerate(sync.buckets):
+        for p in b["params"]:
+            owner[id(p)] = bi
+    stack_buckets = [{owner[id(p)] for p in s.parameters()} for s in stacks]
+    assert all(len(sb) == 1 for sb in stack_buckets) and stack_buckets[0] != stack_buckets[1]
+    in_stacks = {id(p) for s in stacks for p in s.parameters()}
+    for sb in stack_buckets:        # nothing else shares a stack's bucket
+        (bi,) = sb
+        assert all(id(p) in in_stacks for p in sync.buckets[bi]["params"])
+    # buckets tile the arena without gaps
+    assert sync.buckets[0]["lo"] == 0 and sync.buckets[-1]["hi"] == arena.grads.numel()
+    assert all(a["hi"] == b["lo"] for a, b in zip(sync.buckets, sync.buckets[1:]))
