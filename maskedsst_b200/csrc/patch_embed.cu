@@ -120,7 +120,7 @@ patch_embed_fwd_kernel(EmbedGeom g, int n_wb, const float* __restrict__ img, con
 // Backward.  grid = (C * chunks, nb): CTA (c, chunk, z) loops over samples b = z, z+nb, ... so the token set
 // it touches is fixed -> d_pos / parameter gradients accumulate in registers, one atomic flush at the end.
 template <int NJ, int PMAX>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)      // <= 128 registers: two CTAs per SM (three: spills, 381 vs 288 us) (the token loop is a chain of warp reductions: latency, not issue, bound)
 patch_embed_bwd_kernel(EmbedGeom g, int n_wb, const float* __restrict__ img, const float* __restrict__ pre_w,
                        const float* __restrict__ pre_b, const float* __restrict__ W, const float* __restrict__ bias,
                        const float* __restrict__ post_w, const float* __restrict__ post_b, const uint8_t* __restrict__ mask,
@@ -343,7 +343,7 @@ static int launch_bwd(const EmbedGeom& g, int n_wb, size_t smem, cudaStream_t st
                       const uint8_t* mask, const float* d_tokens, const float* d_pln, float* d_pre_w, float* d_pre_b,
                       float* d_W, float* d_bias, float* d_post_w, float* d_post_b, float* d_pos, float* d_mt, Drop drop) {
     const int chunks = (g.S + kTok - 1) / kTok;
-    int nb = (int)((2 * kNumSMs) / ((int64_t)g.C * chunks));   // floor: at most two full waves of one CTA per SM (no tail wave)
+    int nb = (int)((4 * kNumSMs) / ((int64_t)g.C * chunks));   // floor: at most two full waves of two CTAs per SM (no tail wave)
     nb = nb < 1 ? 1 : (nb > g.B ? g.B : nb);
     MSST_CUDA(cudaFuncSetAttribute(patch_embed_bwd_kernel<NJ, PMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     patch_embed_bwd_kernel<NJ, PMAX><<<dim3(g.C * chunks, nb), kThreads, smem, st>>>(
@@ -384,7 +384,7 @@ extern "C" int msst_patch_embed_bwd(const msst_embed_dims* d, const float* img, 
     EmbedGeom g;
     if (int rc = make_geom(d, img, g)) return rc;
     MSST_REQUIRE(g.P <= 16, "patch_embed_bwd: pixels per patch %d > 16 unsupported in backward", g.P);
-    const int pmax = 16;
+    const int pmax = g.P <= 10 ? 10 : 16;   // the per-lane G accumulators are [D/32][pmax] registers
     size_t red = (size_t)8 * g.D;
     if (red < (size_t)8 * 2 * pmax) red = (size_t)8 * 2 * pmax;
     const size_t smem = sizeof(float) * ((size_t)2 * kTok * (g.P + 1) + (size_t)g.D * (g.P + 1) + kTok + red);
@@ -394,6 +394,10 @@ extern "C" int msst_patch_embed_bwd(const msst_embed_dims* d, const float* img, 
     if (pmax == 16) {
         switch (g.D / 32) {
             case 1: MSST_BWD(1, 16); case 2: MSST_BWD(2, 16); case 3: MSST_BWD(3, 16); case 4: MSST_BWD(4, 16);
+        }
+    } else {
+        switch (g.D / 32) {
+            case 1: MSST_BWD(1, 10); case 2: MSST_BWD(2, 10); case 3: MSST_BWD(3, 10); case 4: MSST_BWD(4, 10);
         }
     }
 #undef MSST_BWD
