@@ -165,6 +165,15 @@ MSST_API int msst_attention_bwd(const msst_attn_dims* d, const void* qkv, const 
  * d_h [R, D] fp32 = d_qkv . w_qkv (w_qkv_t = the transposed copy [D, 3*H*dh] bf16). */
 MSST_API int msst_attn_block_fwd(const msst_attn_dims* d, int D, const void* h, const void* w_qkv, void* out, float* lse,
                                  msst_stream_t stream);
+/* The same forward kernel with the tail of the attention block folded in (Attention.to_out vit_spatial_spectral.py:62-65,77, the
+ * residual add of Transformer.forward :102 and the FeedForward PreNorm :25-29):
+ *   xmid [R, D] fp32 = x + dropout(out . w_out^T + b_out)   (w_out [D, H*dh] bf16, b_out [D], x [R, D] fp32; dropout site `site_out`,
+ *                                                             probability / seed of `d`)
+ *   h2 [R, D] bf16 = LayerNorm(xmid; ln_w, ln_b),  ln_stats [R, 2] = (mean, rstd)
+ * `out` may be NULL when the attention output itself is not needed (inference). */
+MSST_API int msst_attn_block_out_fwd(const msst_attn_dims* d, int D, const void* h, const void* w_qkv, void* out, float* lse,
+                                     const void* w_out, const float* b_out, const float* x, float* xmid, const float* ln_w,
+                                     const float* ln_b, void* h2, float* ln_stats, uint32_t site_out, msst_stream_t stream);
 MSST_API int msst_attn_block_bwd(const msst_attn_dims* d, int D, const void* h, const void* w_qkv, const void* w_qkv_t,
                                  const void* d_out, const float* lse, void* d_qkv, float* d_h, msst_stream_t stream);
 

@@ -44,6 +44,7 @@ constexpr int AB_MAXR = 8;                 // weight ring slots (upper bound)
 constexpr uint32_t AB_T16 = 16384;         // one [128 rows][64 bf16] SWIZZLE_128B tile
 constexpr uint32_t AB_BLK = 8192;          // one 64-row block of such a tile
 constexpr uint32_t COL_P = 0, COL_S = 192, COL_O = 256, COL_X = 192, COL_DH = 384;
+constexpr uint32_t COL_Y = 320;                // forward with the fused out-projection: Y accumulator (D columns)
 
 struct AbParams {
     AttnGeom g;
@@ -57,6 +58,10 @@ struct AbParams {
     const float* lse_in; float* lse_out;
     bf16* o; bf16* dqkv; float* dh;
     Drop drop;
+    // forward, fused out-projection (AttnBlockOut): xmid = x + drop(o Wo^T + b_out), h2 = LN2(xmid), ln_stats = (mean, rstd)
+    const float *x_res, *b_out, *ln_w, *ln_b;
+    float *ln_stats, *xmid;
+    Drop drop_out;
     long long* dbg;            // MSST_AB_DBG: clock64 timeline of CTA 0 ([item][16] slots)
 };
 #define AB_T(it, slot) do { if (p.dbg && blockIdx.x == 0 && (it) < 48) p.dbg[(it) * 16 + (slot)] = clock64(); } while (0)
@@ -109,6 +114,7 @@ __device__ __forceinline__ uint32_t key_mask16(const AttnGeom& g, int m, int cq)
 struct alignas(8) AbBars {
     uint64_t h_full[2], h_empty[2], w_full[AB_MAXR], w_empty[AB_MAXR], do_full[2], do_empty[2];
     uint64_t pro_full, conv_done, s_full, sdp_read, p_full, o_full, a_ready, dh_full, dh_free, stg_full, stg_free, dhs_full, dhs_free;
+    uint64_t y_full, out_full, out_free;         // forward with the fused out-projection
     uint32_t tmem_base;
 };
 
@@ -235,7 +241,8 @@ __device__ __forceinline__ void convert_qkv(uint32_t tmem, uint8_t* qkv, uint32_
 }
 
 __device__ __forceinline__ void ab_setup(AbBars* bars, int warp, uint8_t* z0, uint32_t z0_bytes, uint8_t* z1, uint32_t z1_bytes, const CUtensorMap* m0,
-                                         const CUtensorMap* m1, const CUtensorMap* m2, const CUtensorMap* m3, const CUtensorMap* m4) {
+                                         const CUtensorMap* m1, const CUtensorMap* m2, const CUtensorMap* m3, const CUtensorMap* m4,
+                                         uint32_t stg_free_count = 1) {
     if (warp == 17 && elect_one()) {
         for (int i = 0; i < 2; ++i) { mbar_init(&bars->h_full[i], 1); mbar_init(&bars->h_empty[i], 1); mbar_init(&bars->do_full[i], 1); mbar_init(&bars->do_empty[i], 1); }
         for (int i = 0; i < AB_MAXR; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
@@ -243,8 +250,10 @@ __device__ __forceinline__ void ab_setup(AbBars* bars, int warp, uint8_t* z0, ui
         // shared-memory word serialise (~2 clks each) and that cost sat on the critical path four times per item
         mbar_init(&bars->pro_full, 1); mbar_init(&bars->conv_done, 16); mbar_init(&bars->s_full, 1); mbar_init(&bars->p_full, 16);
         mbar_init(&bars->o_full, 1); mbar_init(&bars->a_ready, 16); mbar_init(&bars->dh_full, 1); mbar_init(&bars->dh_free, 16);
-        mbar_init(&bars->stg_full, 16); mbar_init(&bars->stg_free, 1); mbar_init(&bars->sdp_read, 16);
+        mbar_init(&bars->stg_full, 16); mbar_init(&bars->stg_free, stg_free_count); mbar_init(&bars->sdp_read, 16);
         mbar_init(&bars->dhs_full, 16); mbar_init(&bars->dhs_free, 1);
+        mbar_init(&bars->y_full, 1);
+        mbar_init(&bars->out_full, 16); mbar_init(&bars->out_free, 1);
         fence_barrier_init();
     }
     if (warp == 16) {
@@ -278,10 +287,33 @@ __device__ __forceinline__ void store_tile(const AbParams& p, const CUtensorMap*
 // tiles) -> epilogue(i), so the S / O contractions run under the conversion / epilogue instead of being waited for.
 // smem: h [2] | weight ring | Q,K,V [2][3][16 KB] | P~ [16 KB] | row statistics | barriers.  The O tile is staged in the item's own
 // (dead) Q tile and leaves by TMA store (warp 18).
+//
+// OUT = true additionally folds the attention block's tail in (reference Attention.to_out, src/vit_spatial_spectral.py:62-65,77, the
+// residual add of Transformer.forward :102 and the PreNorm LayerNorm of the FeedForward branch :25-29):
+//     xmid = x + dropout(concat_h(O_h) Wo^T + b_out),   h2 = LayerNorm(xmid),   stats2 = (mean, rstd)
+// The staged bf16 O tile of every item is ALSO the K-major A operand of  Y (+)= O_h Wo[:, 64h .. 64h+63]^T  (M = 128, N = D), which
+// accumulates over the heads of the tile in TMEM columns [COL_Y, COL_Y + D); the head's Wo column block travels through the weight
+// ring as a fourth slot per item.  One item after the tile's last head the compute threads run the tile epilogue (bias, dropout,
+// residual, two-pass LayerNorm: the arithmetic of gemm_tn_kernel<6> / mlp_block_fwd_kernel): the fp32 residual rows come straight from
+// global memory (one 32-byte sector per thread and 32-column chunk, L2-prefetched at the tile's second item), xmid leaves by 32-byte
+// stores, and h2 is staged in the K / V tiles of the current item's buffer -- dead between that item's O contraction and the
+// conversion two items later -- from where warp 18 writes it out by TMA.  o [R, I] is still written (the Wo weight gradient of the
+// backward reads it) but never re-read in the forward, and the separate out-projection GEMM launch is gone.
 // =========================================================================================================
-template <int NCH>
+__device__ __forceinline__ void ldg_nc_256(const float* ptr, float (&v)[8]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(ptr));
+}
+__device__ __forceinline__ void stg_256(float* ptr, const float (&v)[8]) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "l"(ptr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" :: "l"(ptr)); }
+
+template <int NCH, bool OUT>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CUtensorMap tma_o,
+                      const __grid_constant__ CUtensorMap tma_wo, const __grid_constant__ CUtensorMap tma_xmid, const __grid_constant__ CUtensorMap tma_h2,
                       const AbParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
@@ -296,31 +328,50 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
     AbBars* bars = s.bars;
     const int warp = threadIdx.x >> 5;
     const int H = g.H;
-    ab_setup(bars, warp, s.h_s, 2 * p.hbuf_bytes, nullptr, 0, &tma_h, &tma_w, &tma_o, nullptr, nullptr);
+    constexpr int D = NCH * 32;
+    ab_setup(bars, warp, s.h_s, 2 * p.hbuf_bytes, nullptr, 0, &tma_h, &tma_w, &tma_o, OUT ? &tma_wo : nullptr, OUT ? &tma_xmid : nullptr, OUT ? 2u : 1u);
     s.tmem = bars->tmem_base; s.h_addr = smem_u32(s.h_s); s.w_addr = smem_u32(s.w_s);
 
     const int64_t my_tiles = blockIdx.x < p.n_tiles ? (p.n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
     const int64_t n_items = my_tiles * H;
 
     if (warp == 16) {
-        // ===== TMA producer =====
+        // ===== TMA producer.  Ring order = the MMA issuer's consumption order: P(0), P(1), then per item: [Wo(it - 1)], P(it + 2); [Wo(last)] =====
         if (elect_one()) {
             Ring r{0, 0u, p.NR};
-            for (int64_t k = 0; k < my_tiles; ++k) {
-                const int buf = (int)(k & 1);
-                mbar_wait(&bars->h_empty[buf], ((uint32_t)(k >> 1) & 1) ^ 1);
-                load_h_tile<NCH>(p, &tma_h, s.h_s + (size_t)buf * p.hbuf_bytes, &bars->h_full[buf], blockIdx.x + k * gridDim.x);
-                for (int h = 0; h < H; ++h)
-                    for (int t = 0; t < 3; ++t) load_w_slice<NCH>(p, &tma_w, bars, s.w_s, r, t, h);
+            int64_t pk = 0; int phd = 0;                          // (tile counter, head) of the next prologue
+            auto load_pro = [&]() {
+                if (phd == 0) {
+                    const int buf = (int)(pk & 1);
+                    mbar_wait(&bars->h_empty[buf], ((uint32_t)(pk >> 1) & 1) ^ 1);
+                    load_h_tile<NCH>(p, &tma_h, s.h_s + (size_t)buf * p.hbuf_bytes, &bars->h_full[buf], blockIdx.x + pk * gridDim.x);
+                }
+                for (int t = 0; t < 3; ++t) load_w_slice<NCH>(p, &tma_w, bars, s.w_s, r, t, phd);
+                if (++phd == H) { phd = 0; ++pk; }
+            };
+            int yh = 0;
+            auto load_wo = [&]() {                                // Wo[:, 64 yh .. +63]: [D rows][64 cols] SWIZZLE_128B, K-major B of the out-projection
+                mbar_wait(&bars->w_empty[r.slot], r.ph ^ 1u);
+                mbar_arrive_expect_tx(&bars->w_full[r.slot], (uint32_t)D * 128u);
+                tma_load_2d(s.w_s + (size_t)r.slot * p.slot_bytes, &tma_wo, &bars->w_full[r.slot], yh * 64, 0);
+                r.next();
+                if (++yh == H) yh = 0;
+            };
+            if (n_items > 0) load_pro();
+            if (n_items > 1) load_pro();
+            for (int64_t it = 0; it < n_items; ++it) {
+                if (OUT && it >= 1) load_wo();
+                if (it + 2 < n_items) load_pro();
             }
+            if (OUT && n_items > 0) load_wo();
         }
     } else if (warp == 17) {
-        // ===== MMA issuer: prologue(0), S(0), prologue(1); then per item: O(i), S(i+1), prologue(i+2) =====
+        // ===== MMA issuer: prologue(0), S(0), prologue(1); then per item: [Y(i-1)], O(i), S(i+1), prologue(i+2); [Y(last)] =====
         // (the whole warp runs the control flow, one elected lane issues: see the backward kernel)
         if (n_items > 0) {
             const bool lead = elect_one();
             Ring r{0, 0u, p.NR};
-            const uint32_t idesc_s = make_idesc_bf16(64, 64, 0, 0), idesc_o = make_idesc_bf16(64, 64, 0, 1);
+            const uint32_t idesc_s = make_idesc_bf16(64, 64, 0, 0), idesc_o = make_idesc_bf16(64, 64, 0, 1), idesc_y = make_idesc_bf16(128, D, 0, 0);
             const uint32_t qkv_addr = smem_u32(qkv_s);
             const uint64_t pd0 = kdesc(smem_u32(p_s)), pd1 = kdesc(smem_u32(p_s) + AB_BLK);
             int64_t pk = 0; int phd = 0;                          // (tile counter, head) of the next prologue
@@ -339,10 +390,29 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
                 }
                 if (lead) umma_commit(&bars->s_full);
             };
+            int yh = 0;
+            auto issue_y = [&](int64_t it) {                      // Y (+)= O(it) Wo_h^T: the staged O tile [128 rows][64] is the K-major A operand
+                mbar_wait(&bars->stg_full, (uint32_t)it & 1);
+                mbar_wait(&bars->w_full[r.slot], r.ph);
+                if (lead) AB_T(it, 11);
+                tc_fence_after();
+                const uint64_t ad = kdesc(qkv_addr + (uint32_t)(it & 1) * 3 * AB_T16), bd = kdesc(s.w_addr + (uint32_t)r.slot * p.slot_bytes);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    if (lead) umma_bf16(s.tmem + COL_Y, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc_y, (yh | ks) != 0);
+                if (lead) {
+                    umma_commit(&bars->w_empty[r.slot]);
+                    umma_commit(&bars->stg_free);                 // second arrival (the first is the O store's): the Q tile may be overwritten
+                    if (yh == H - 1) umma_commit(&bars->y_full);
+                }
+                r.next();
+                if (++yh == H) yh = 0;
+            };
             next_pro();
             issue_s(0);
             if (n_items > 1) next_pro();
             for (int64_t it = 0; it < n_items; ++it) {
+                if (OUT && it >= 1) issue_y(it - 1);
                 const uint32_t va = qkv_addr + (uint32_t)(it & 1) * 3 * AB_T16 + 2 * AB_T16;
                 mbar_wait(&bars->p_full, (uint32_t)it & 1);
                 if (lead) AB_T(it, 10);
@@ -361,18 +431,36 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
                 }
                 if (lead) AB_T(it, 9);
             }
+            if (OUT) issue_y(n_items - 1);
         }
     } else if (warp == 18) {
-        // ===== TMA store of the staged O tiles =====
+        // ===== TMA store of the staged O tiles (and, OUT, of the staged xmid / h2 chunks of the tile that ended one item ago) =====
         if (elect_one()) {
-            for (int64_t it = 0; it < n_items; ++it) {
-                const int64_t tile = blockIdx.x + (it / H) * gridDim.x; const int h = (int)(it % H);
-                mbar_wait(&bars->stg_full, (uint32_t)it & 1);
-                store_tile(p, &tma_o, qkv_s + (size_t)(it & 1) * 3 * AB_T16, h * 64, tile);
+            int64_t n_out = 0;                                    // tile epilogues stored so far
+            auto out_rounds = [&](int64_t tile, const uint8_t* kv) {   // the staged h2 chunks of `tile`: [128 rows][64 B] SWIZZLE_64B each, 8 KB apart
+                mbar_wait(&bars->out_full, (uint32_t)n_out & 1u);
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) store_tile_rows(p, &tma_h2, kv + c * 8192, 64, 32 * c, tile);
                 tma_store_commit();
                 tma_store_wait_read();
+                mbar_arrive(&bars->out_free);
+                ++n_out;
+            };
+            int64_t k = 0; int h = 0;
+            for (int64_t it = 0; it < n_items; ++it) {
+                const int64_t tile = blockIdx.x + k * gridDim.x;
+                const uint8_t* buf = qkv_s + (size_t)(it & 1) * 3 * AB_T16;
+                if (OUT && h == 0 && k > 0) out_rounds(tile - gridDim.x, buf + AB_T16);
+                mbar_wait(&bars->stg_full, (uint32_t)it & 1);
+                if (p.o) {
+                    store_tile(p, &tma_o, buf, h * 64, tile);
+                    tma_store_commit();
+                    tma_store_wait_read();
+                }
                 mbar_arrive(&bars->stg_free);
+                if (++h == H) { h = 0; ++k; }
             }
+            if (OUT && n_items > 0) out_rounds(blockIdx.x + (my_tiles - 1) * gridDim.x, qkv_s + (size_t)((n_items - 1) & 1) * 3 * AB_T16 + AB_T16);
         }
     } else {
         // ===== 512 compute threads: thread = (TMEM lane L, column quarter cq) =====
@@ -389,6 +477,77 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
         float* xmax = xch; float* xsum = xch + 4 * 128;
         int64_t cur_tile = -1, grow = -1; uint32_t vm = 0;
         int64_t k = 0; int h = 0;
+        // ---- OUT: the tile epilogue (the M = 128 out-projection accumulator holds tile row L in TMEM lane L) ----
+        int64_t growL = -1, growL_prev = -1;                      // global row of tile row L in the current / the previous tile
+        int64_t n_out = 0;                                        // tile epilogues staged so far
+        bool out_pending = false;                                 // the K / V tiles of some buffer hold staged h2 chunks
+        auto wait_out = [&]() {                                   // ... their TMA stores have read them
+            if (out_pending) { mbar_wait(&bars->out_free, (uint32_t)(n_out - 1) & 1u); out_pending = false; }
+        };
+        auto tile_epilogue = [&](int64_t kk, int64_t row, uint8_t* kv) {
+            const uint32_t sw64 = (uint32_t)((L >> 1) & 3);
+            const int64_t rrow = row >= 0 ? row : 0;
+            float y[NCH][8];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {                       // the residual row: NCH 32-byte sectors, in flight under the waits below
+                if (row >= 0) ldg_nc_256(p.x_res + row * D + 32 * c + 8 * cq, y[c]);
+                else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) y[c][e] = 0.f;
+                }
+            }
+            wait_out();
+            mbar_wait(&bars->y_full, (uint32_t)kk & 1);
+            tc_fence_after();
+            float sum = 0.f;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                uint32_t a[8];
+                tmem_ld_32x8(s.tmem + lane_addr + COL_Y + 32 * c + 8 * cq, a);
+                tmem_ld_wait();
+                const int col = 32 * c + 8 * cq;
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.b_out + col)), b1 = __ldg(reinterpret_cast<const float4*>(p.b_out + col + 4));
+                float f[8] = {__uint_as_float(a[0]) + b0.x, __uint_as_float(a[1]) + b0.y, __uint_as_float(a[2]) + b0.z, __uint_as_float(a[3]) + b0.w,
+                              __uint_as_float(a[4]) + b1.x, __uint_as_float(a[5]) + b1.y, __uint_as_float(a[6]) + b1.z, __uint_as_float(a[7]) + b1.w};
+                if (p.drop_out.on()) {
+                    float d4[4];
+                    drop_factor4(p.drop_out, (uint64_t)(rrow * D + col) >> 2, d4);
+                    f[0] *= d4[0]; f[1] *= d4[1]; f[2] *= d4[2]; f[3] *= d4[3];
+                    drop_factor4(p.drop_out, (uint64_t)(rrow * D + col + 4) >> 2, d4);
+                    f[4] *= d4[0]; f[5] *= d4[1]; f[6] *= d4[2]; f[7] *= d4[3];
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { y[c][e] += f[e]; sum += y[c][e]; }
+                if (row >= 0) stg_256(p.xmid + row * D + col, y[c]);
+            }
+            tc_fence_before();
+            // two-pass LayerNorm over the row's D values (4 column quarters): the statistics buffers of the softmax are idle here
+            xmax[cq * 128 + L] = sum;
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            const float mean = ((xmax[L] + xmax[128 + L]) + (xmax[256 + L] + xmax[384 + L])) / D;
+            float sq = 0.f;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { y[c][e] -= mean; sq = fmaf(y[c][e], y[c][e], sq); }
+            xsum[cq * 128 + L] = sq;
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            const float rstd = rsqrtf(((xsum[L] + xsum[128 + L]) + (xsum[256 + L] + xsum[384 + L])) / D + 1e-5f);
+            if (cq == 0 && row >= 0) { p.ln_stats[2 * row] = mean; p.ln_stats[2 * row + 1] = rstd; }
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {                       // h2 chunk c: [128 rows][64 B] SWIZZLE_64B at kv + 8 KB * c (K tile, then the V tile)
+                const int col = 32 * c + 8 * cq;
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.ln_w + col)), w1 = __ldg(reinterpret_cast<const float4*>(p.ln_w + col + 4));
+                const float4 l0 = __ldg(reinterpret_cast<const float4*>(p.ln_b + col)), l1 = __ldg(reinterpret_cast<const float4*>(p.ln_b + col + 4));
+                *reinterpret_cast<uint4*>(kv + c * 8192 + L * 64 + ((((uint32_t)cq) ^ sw64) << 4)) =
+                    make_uint4(pack_bf(y[c][0] * rstd * w0.x + l0.x, y[c][1] * rstd * w0.y + l0.y), pack_bf(y[c][2] * rstd * w0.z + l0.z, y[c][3] * rstd * w0.w + l0.w),
+                               pack_bf(y[c][4] * rstd * w1.x + l1.x, y[c][5] * rstd * w1.y + l1.y), pack_bf(y[c][6] * rstd * w1.z + l1.z, y[c][7] * rstd * w1.w + l1.w));
+            }
+            fence_proxy_async();
+            warp_arrive(&bars->out_full, lane);
+            ++n_out;
+            out_pending = true;
+        };
         if (n_items > 0) {                                        // pipeline prologue: Q, K, V of item 0
             mbar_wait(&bars->pro_full, 0);
             tc_fence_after();
@@ -407,6 +566,12 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
                 const bool ok = group < g.groups && slot_to(g, group, 0, m, seq, pos);
                 grow = ok ? row_of(g, seq, pos) : -1;
                 vm = ok ? vm_geom : 0u;
+                if (OUT) {
+                    const int64_t gl = tile * 2 + (L >> 6);
+                    const bool okl = gl < g.groups && slot_to(g, gl, 0, L & 63, seq, pos);
+                    growL_prev = growL;
+                    growL = okl ? row_of(g, seq, pos) : -1;
+                }
             }
             // ---- softmax of row `slot`, key columns 16*cq .. +15 of its block ----
             const uint64_t hidx = pair_base(g, tile * 2 + blk, h) + (uint64_t)(m * 32 + 8 * cq);
@@ -460,9 +625,15 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
             l = (xsum[L] + xsum[128 + L]) + (xsum[256 + L] + xsum[384 + L]);
             const float inv = l > 0.f ? 1.f / l : 0.f;
             if (cq == 0 && grow >= 0) p.lse_out[grow * H + h] = (sub + log2f(l)) * 0.6931471805599453f;
+            // ---- OUT: pull the tile's residual rows into L2 well before the tile epilogue reads them (one 128-byte line per row and chunk) ----
+            if (OUT && cq == 0 && growL >= 0 && h == (H > 1 ? 1 : 0)) {
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) prefetch_l2(p.x_res + growL * D + 32 * c);
+            }
             // ---- Q, K, V of item it + 1 -> the other tile buffer (runs under the O MMAs of item it) ----
             if (it + 1 < n_items) {
-                if (it >= 1) mbar_wait(&bars->stg_free, (uint32_t)(it - 1) & 1);   // that buffer's Q tile staged O(it - 1): its store has read it
+                if (it >= 1) mbar_wait(&bars->stg_free, (uint32_t)(it - 1) & 1);   // that buffer's Q tile staged O(it - 1): its store (and out-projection MMA) has read it
+                if (OUT) wait_out();                              // ... and its K / V tiles staged h2
                 mbar_wait(&bars->pro_full, ph ^ 1u);
                 if (threadIdx.x == 0) AB_T(it, 3);
                 tc_fence_after();
@@ -472,10 +643,15 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
                 warp_arrive(&bars->conv_done, lane);
                 if (threadIdx.x == 0) AB_T(it, 4);
             }
-            // ---- epilogue: O row / l -> bf16 -> staging (the item's own Q tile, dead since S) -> TMA store ----
             mbar_wait(&bars->o_full, ph);
             if (threadIdx.x == 0) AB_T(it, 5);
             tc_fence_after();
+            if (OUT) {
+                // the tile that ended with the previous item: its Y accumulator is complete, and this item's K / V tiles are dead (S and O done)
+                if (h == 0 && k > 0) tile_epilogue(k - 1, growL_prev, qkv_s + (size_t)(it & 1) * 3 * AB_T16 + AB_T16);
+                if (threadIdx.x == 0) AB_T(it, 12);
+            }
+            // ---- epilogue: O row / l -> bf16 -> staging (the item's own Q tile, dead since S) -> TMA store ----
             {
                 uint32_t v[16], o8[8];
                 tmem_ld_32x16(s.tmem + lane_addr + COL_O + 16 * cq, v);
@@ -490,6 +666,7 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
             if (threadIdx.x == 0) AB_T(it, 6);
             if (++h == H) { h = 0; ++k; }
         }
+        if (OUT && n_items > 0) tile_epilogue(k - 1, growL, qkv_s + (size_t)((n_items - 1) & 1) * 3 * AB_T16 + AB_T16);
     }
     tc_fence_before();
     __syncthreads();
@@ -925,31 +1102,53 @@ bool attn_block_supported(const AttnGeom& g, int D) {
     return attention_bwd_tc_supported(g) && g.dh == 64 && D % 32 == 0 && D >= 32 && D <= 96 && g.H * 64 * 3 < 65536;   // D = 128: the backward's ring does not fit
 }
 
-int attn_block_fwd(const AttnGeom& g, int D, const bf16* h, const bf16* w_qkv, bf16* out, float* lse, Drop drop, cudaStream_t st) {
+template <int NCH, bool OUT>
+static int launch_fwd(const CUtensorMap& t_h, const CUtensorMap& t_w, const CUtensorMap& t_o, const CUtensorMap& t_wo, const CUtensorMap& t_xmid,
+                      const CUtensorMap& t_h2, const AbParams& p, int grid, size_t smem, cudaStream_t st) {
+    static PerDeviceOnce once;
+    if (once.first()) MSST_CUDA(cudaFuncSetAttribute(attn_block_fwd_kernel<NCH, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attn_block_fwd_kernel<NCH, OUT><<<grid, AB_THREADS, smem, st>>>(t_h, t_w, t_o, t_wo, t_xmid, t_h2, p);
+    return MSST_OK;
+}
+
+int attn_block_fwd(const AttnGeom& g, int D, const bf16* h, const bf16* w_qkv, bf16* out, float* lse, Drop drop, cudaStream_t st, const AttnBlockOut* tail) {
     MSST_REQUIRE(attn_block_supported(g, D), "attn_block_fwd: needs packed short sequences (N <= 64), dim_head 64, D in {32, 64, 96}");
     AbParams p{};
     size_t smem = 0;
     if (int rc = fill_params(p, g, D, false, smem)) return rc;
     p.lse_out = lse; p.o = out; p.drop = drop;
-    static PerDeviceOnce once;
-    if (once.first()) {
-        MSST_CUDA(cudaFuncSetAttribute(attn_block_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        MSST_CUDA(cudaFuncSetAttribute(attn_block_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        MSST_CUDA(cudaFuncSetAttribute(attn_block_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    }
-    CUtensorMap t_h, t_w, t_o;
+    CUtensorMap t_h, t_w, t_o, t_wo, t_xmid, t_h2;
+    const int64_t I = (int64_t)g.H * 64;
     if (int rc = act_tmap(&t_h, g, h, D, p.nbox, 32, 64)) return rc;
-    if (int rc = act_tmap(&t_o, g, out, (int64_t)g.H * 64, p.nbox, 64, 128)) return rc;
-    const int64_t I3 = (int64_t)g.H * 64 * 3;
+    if (out) { if (int rc = act_tmap(&t_o, g, out, I, p.nbox, 64, 128)) return rc; }
+    else t_o = t_h;
+    const int64_t I3 = I * 3;
     { const int64_t dims[2] = {D, I3}, strides[1] = {D}; const int box[2] = {32, 64};
       if (int rc = make_tmap_bf16_nd(&t_w, w_qkv, 2, dims, strides, box, 64)) return rc; }
+    if (tail) {
+        MSST_REQUIRE(tail->w_out && tail->b_out && tail->x && tail->xmid && tail->ln_w && tail->ln_b && tail->h2 && tail->ln_stats,
+                     "attn_block_fwd: the fused out-projection needs w_out, b_out, x, xmid, ln_w, ln_b, h2 and ln_stats");
+        p.x_res = tail->x; p.b_out = tail->b_out; p.ln_w = tail->ln_w; p.ln_b = tail->ln_b; p.ln_stats = tail->ln_stats; p.xmid = tail->xmid; p.drop_out = tail->drop;
+        { const int64_t dims[2] = {I, D}, strides[1] = {I}; const int box[2] = {64, D};
+          if (int rc = make_tmap_bf16_nd(&t_wo, tail->w_out, 2, dims, strides, box, 128)) return rc; }
+        t_xmid = t_h;   // (xmid leaves by direct stores)
+        if (int rc = act_tmap(&t_h2, g, tail->h2, D, p.nbox, 32, 64)) return rc;
+    } else {
+        MSST_REQUIRE(out, "attn_block_fwd: null output");
+        t_wo = t_h; t_xmid = t_h; t_h2 = t_h;
+    }
     const int grid = (int)(p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs);
     if (p.dbg) cudaMemsetAsync(p.dbg, 0, 48 * 16 * 8, st);
-    switch (p.nch) {
-        case 1: attn_block_fwd_kernel<1><<<grid, AB_THREADS, smem, st>>>(t_h, t_w, t_o, p); break;
-        case 2: attn_block_fwd_kernel<2><<<grid, AB_THREADS, smem, st>>>(t_h, t_w, t_o, p); break;
-        default: attn_block_fwd_kernel<3><<<grid, AB_THREADS, smem, st>>>(t_h, t_w, t_o, p); break;
+    int rc = MSST_OK;
+    switch (p.nch * 2 + (tail ? 1 : 0)) {
+        case 2: rc = launch_fwd<1, false>(t_h, t_w, t_o, t_wo, t_xmid, t_h2, p, grid, smem, st); break;
+        case 3: rc = launch_fwd<1, true>(t_h, t_w, t_o, t_wo, t_xmid, t_h2, p, grid, smem, st); break;
+        case 4: rc = launch_fwd<2, false>(t_h, t_w, t_o, t_wo, t_xmid, t_h2, p, grid, smem, st); break;
+        case 5: rc = launch_fwd<2, true>(t_h, t_w, t_o, t_wo, t_xmid, t_h2, p, grid, smem, st); break;
+        case 6: rc = launch_fwd<3, false>(t_h, t_w, t_o, t_wo, t_xmid, t_h2, p, grid, smem, st); break;
+        default: rc = launch_fwd<3, true>(t_h, t_w, t_o, t_wo, t_xmid, t_h2, p, grid, smem, st); break;
     }
+    if (rc) return rc;
     MSST_LAUNCH_CHECK();
     if (p.dbg) { static int n = 0; dbg_dump("attn_block_fwd", st, n); }
     return MSST_OK;

@@ -74,8 +74,15 @@ int attention_bwd_tc_long(const AttnGeom& g, const __nv_bfloat16* qkv, const __n
 
 // attn_block_tc.cu (tcgen05): per-head QKV projection fused into the attention kernels, N <= 64 -- q/k/v never reach HBM
 bool attn_block_supported(const AttnGeom& g, int D);
+// optional tail of the forward kernel (the attention block's out-projection, residual add and the FeedForward pre-norm in the same launch):
+//   xmid [R, D] fp32 = x + dropout(out . w_out^T + b_out)   (w_out [D, H*64] bf16, Drop = `drop`)
+//   h2 [R, D] bf16 = LayerNorm(xmid; ln_w, ln_b), ln_stats [R, 2] = (mean, rstd);   `out` may then be null (inference: o is not needed)
+struct AttnBlockOut {
+    const __nv_bfloat16* w_out; const float* b_out; const float* x; float* xmid;
+    const float* ln_w; const float* ln_b; __nv_bfloat16* h2; float* ln_stats; Drop drop;
+};
 int attn_block_fwd(const AttnGeom& g, int D, const __nv_bfloat16* h, const __nv_bfloat16* w_qkv, __nv_bfloat16* out, float* lse, Drop drop,
-                   cudaStream_t st);
+                   cudaStream_t st, const AttnBlockOut* tail = nullptr);
 // recomputes q/k/v from h; d_qkv [R, 3*H*64] bf16 (for the weight gradient) and d_h [R, D] fp32 = d_qkv . W_qkv (data gradient, accumulated over heads in TMEM)
 int attn_block_bwd(const AttnGeom& g, int D, const __nv_bfloat16* h, const __nv_bfloat16* w_qkv, const __nv_bfloat16* w_qkv_t,
                    const __nv_bfloat16* d_out, const float* lse, __nv_bfloat16* d_qkv, float* d_h, Drop drop, cudaStream_t st);

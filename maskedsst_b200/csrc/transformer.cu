@@ -38,6 +38,14 @@ static bool attn_fused(const msst_tf_dims* d) {
     return attn_block_supported(g, d->D);
 }
 
+// bf16 mode, fused attention: the out-projection + residual + FeedForward pre-norm run in the tail of the attention forward kernel
+// (no gemm_tn<6> launch, o is not re-read).  MSST_ATTN_OUT_FUSED=0 selects the separate GEMM.
+static bool attn_out_fused() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MSST_ATTN_OUT_FUSED"); v = e ? atoi(e) : 1; }
+    return v != 0;
+}
+
 // bf16 mode: the FeedForward block as one kernel (mlp_block_tc.cu).  MSST_MLP_FUSED=0 selects the two GEMM launches.
 static bool mlp_fused(const msst_tf_dims* d) {
     static int v = -1;
@@ -152,19 +160,26 @@ static int tf_fwd_bf16(const msst_tf_dims* d, const msst_layer_params* layers, c
         const bool fuse_ln = (D % 4 == 0 && D <= 128);
         if (l == 0 || !fuse_ln) { if (int rc = layernorm_fwd(x, p.ln1_w, p.ln1_b, h1, 1, stats1, R, D, 1e-5f, st)) return rc; }
         msst_attn_dims ad{d->n_seq, d->N, d->inner, d->H, d->dh, d->drop_p, d->seed, site + kSiteAttnProb, d->prec, d->seed_dev};
+        const bool tail = fused && fuse_ln && attn_out_fused();
         if (fused) {
             AttnGeom ag;
             if (int rc = make_attn_geom(&ad, ag, false)) return rc;
-            if (int rc = attn_block_fwd(ag, D, h1, w.wq, o, lse, make_drop(d->drop_p, d->seed, site + kSiteAttnProb, d->seed_dev), st)) return rc;
+            // tail: xmid = x + drop(o Wo^T + b_out) and h2 = LN2(xmid) leave the same kernel (o is only written, for the Wo weight gradient)
+            const AttnBlockOut t{w.wo, p.b_out, x, xmid, p.ln2_w, p.ln2_b, h2, stats2, make_drop(d->drop_p, d->seed, site + kSiteAttnOut, d->seed_dev)};
+            if (int rc = attn_block_fwd(ag, D, h1, w.wq, (tail && !d->save_for_backward) ? nullptr : o, lse,
+                                        make_drop(d->drop_p, d->seed, site + kSiteAttnProb, d->seed_dev), st, tail ? &t : nullptr)) return rc;
         } else {
             if (int rc = gemm_tn_bf16(gemm_args(h1, w.wq, R, 3 * I, D, qkv, 0), st)) return rc;
             if (int rc = attention_fwd_bf16(&ad, qkv, o, lse, st)) return rc;
         }
-        GemmBf16Args a = gemm_args(o, w.wo, R, D, I, xmid, 1);
-        a.bias = p.b_out; a.residual = x; a.drop = make_drop(d->drop_p, d->seed, site + kSiteAttnOut, d->seed_dev);
-        if (fuse_ln) { a.ln_w = p.ln2_w; a.ln_b = p.ln2_b; a.ln_out = h2; a.ln_stats = stats2; }
-        if (int rc = gemm_tn_bf16(a, st)) return rc;
-        if (!fuse_ln) { if (int rc = layernorm_fwd(xmid, p.ln2_w, p.ln2_b, h2, 1, stats2, R, D, 1e-5f, st)) return rc; }
+        GemmBf16Args a{};
+        if (!tail) {
+            a = gemm_args(o, w.wo, R, D, I, xmid, 1);
+            a.bias = p.b_out; a.residual = x; a.drop = make_drop(d->drop_p, d->seed, site + kSiteAttnOut, d->seed_dev);
+            if (fuse_ln) { a.ln_w = p.ln2_w; a.ln_b = p.ln2_b; a.ln_out = h2; a.ln_stats = stats2; }
+            if (int rc = gemm_tn_bf16(a, st)) return rc;
+            if (!fuse_ln) { if (int rc = layernorm_fwd(xmid, p.ln2_w, p.ln2_b, h2, 1, stats2, R, D, 1e-5f, st)) return rc; }
+        }
         if (mlp_fused(d)) {   // Linear -> GELU -> dropout -> Linear -> dropout -> + xmid (-> LN1 of the next layer): one kernel
             const bool next_ln = l + 1 < d->L;
             char* nlw = ws + L.layer_bytes * (d->save_for_backward ? l + 1 : 0);
@@ -441,6 +456,16 @@ extern "C" int msst_attn_block_fwd(const msst_attn_dims* d, int D, const void* h
     if (int rc = make_attn_geom(d, g, false)) return rc;
     if (g.n_seq == 0) return MSST_OK;
     return attn_block_fwd(g, D, (const bf16*)h, (const bf16*)w_qkv, (bf16*)out, lse, make_drop(d->drop_p, d->seed, d->site, d->seed_dev), (cudaStream_t)stream);
+}
+extern "C" int msst_attn_block_out_fwd(const msst_attn_dims* d, int D, const void* h, const void* w_qkv, void* out, float* lse, const void* w_out,
+                                       const float* b_out, const float* x, float* xmid, const float* ln_w, const float* ln_b, void* h2, float* ln_stats,
+                                       uint32_t site_out, msst_stream_t stream) {
+    MSST_REQUIRE(d && d->prec == MSST_PREC_BF16, "attn_block_out_fwd: bf16 mode only");
+    AttnGeom g;
+    if (int rc = make_attn_geom(d, g, false)) return rc;
+    if (g.n_seq == 0) return MSST_OK;
+    const AttnBlockOut t{(const bf16*)w_out, b_out, x, xmid, ln_w, ln_b, (bf16*)h2, ln_stats, make_drop(d->drop_p, d->seed, site_out, d->seed_dev)};
+    return attn_block_fwd(g, D, (const bf16*)h, (const bf16*)w_qkv, (bf16*)out, lse, make_drop(d->drop_p, d->seed, d->site, d->seed_dev), (cudaStream_t)stream, &t);
 }
 extern "C" int msst_attn_block_bwd(const msst_attn_dims* d, int D, const void* h, const void* w_qkv, const void* w_qkv_t, const void* d_out,
                                    const float* lse, void* d_qkv, float* d_h, msst_stream_t stream) {

@@ -102,3 +102,81 @@ def test_attn_block_matches_unfused_kernels_with_dropout(n_seq, N, inner, H):
     # determinism
     out2, _, _ = _call_fwd(h, w, n_seq, N, inner, H, drop_p=0.25, seed=77, site=5)
     assert torch.equal(out, out2)
+
+
+# ---- forward with the fused tail: out-projection + residual + FeedForward pre-norm in the same kernel ----
+def _call_out_fwd(h, w, w_out, b_out, x, ln_w, ln_b, n_seq, N, inner, H, drop_p=0.0, seed=0, site=0, site_out=1, want_o=True):
+    R, D = h.shape
+    I = H * 64
+    dims = _lib.AttnDims(n_seq, N, inner, H, 64, float(drop_p), seed, site, PREC_BF16, None)
+    out = torch.full((R, I), float("nan"), device=DEV, dtype=torch.bfloat16) if want_o else None
+    lse = torch.full((R, H), float("nan"), device=DEV, dtype=torch.float32)
+    xmid = torch.full((R, D), float("nan"), device=DEV, dtype=torch.float32)
+    h2 = torch.full((R, D), float("nan"), device=DEV, dtype=torch.bfloat16)
+    stats = torch.full((R, 2), float("nan"), device=DEV, dtype=torch.float32)
+    st = torch.cuda.current_stream().cuda_stream
+    check(_lib.lib().msst_attn_block_out_fwd(C.byref(dims), D, h.data_ptr(), w.data_ptr(), out.data_ptr() if want_o else None, lse.data_ptr(),
+                                             w_out.data_ptr(), b_out.data_ptr(), x.data_ptr(), xmid.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(),
+                                             h2.data_ptr(), stats.data_ptr(), site_out, st))
+    return out, lse, xmid, h2, stats
+
+
+def _tail_inputs(R, D, I):
+    w_out = (torch.randn(D, I) * I ** -0.5).bfloat16().to(DEV)
+    b_out = torch.randn(D).to(DEV)
+    x = torch.randn(R, D).to(DEV)
+    ln_w = (1 + 0.2 * torch.randn(D)).to(DEV)
+    ln_b = (0.2 * torch.randn(D)).to(DEV)
+    return w_out, b_out, x, ln_w, ln_b
+
+
+@pytest.mark.parametrize("n_seq,N,inner,H,D", GEOMS)
+def test_attn_block_out_fwd_vs_fp64(n_seq, N, inner, H, D):
+    """xmid = x + o Wo^T + b and h2 = LN(xmid) from the fused kernel against fp64 torch on the kernel's own bf16 o
+    (reference Attention.to_out + residual + PreNorm, src/vit_spatial_spectral.py:77,102,25-29); o / lse must be those of the
+    plain forward kernel bit for bit."""
+    torch.manual_seed(3)
+    R, I = n_seq * N, H * 64
+    h = torch.randn(R, D).bfloat16().to(DEV)
+    w = (torch.randn(3 * I, D) * D ** -0.5).bfloat16().to(DEV)
+    w_out, b_out, x, ln_w, ln_b = _tail_inputs(R, D, I)
+    o_ref, lse_ref, _ = _call_fwd(h, w, n_seq, N, inner, H)
+    out, lse, xmid, h2, stats = _call_out_fwd(h, w, w_out, b_out, x, ln_w, ln_b, n_seq, N, inner, H)
+    torch.cuda.synchronize()
+    assert torch.equal(out, o_ref) and torch.equal(lse, lse_ref)
+    for t in (xmid, h2.float(), stats):
+        assert torch.isfinite(t).all()
+    want = x.double() + out.double() @ w_out.double().t() + b_out.double()
+    assert rel_l2(xmid, want) < 2e-6
+    mean = xmid.double().mean(-1)
+    var = xmid.double().var(-1, unbiased=False)
+    assert rel_l2(stats[:, 0], mean) < 1e-5 and rel_l2(stats[:, 1], (var + 1e-5).rsqrt()) < 1e-5
+    want_h2 = torch.nn.functional.layer_norm(xmid.double(), (D,), ln_w.double(), ln_b.double(), 1e-5)
+    assert rel_l2(h2, want_h2) < 4e-3
+    # inference form: no o output
+    _, lse3, xmid3, h23, _ = _call_out_fwd(h, w, w_out, b_out, x, ln_w, ln_b, n_seq, N, inner, H, want_o=False)
+    assert torch.equal(xmid3, xmid) and torch.equal(h23, h2) and torch.equal(lse3, lse)
+
+
+@pytest.mark.parametrize("n_seq,N,inner,H", [(16, 64, 1, 8), (256, 5, 64, 8), (2368, 64, 1, 8)])
+def test_attn_block_out_matches_unfused_gemm_with_dropout(n_seq, N, inner, H):
+    """Same (seed, site) -> the fused tail regenerates the out-projection dropout mask of the stand-alone GEMM epilogue."""
+    torch.manual_seed(4)
+    D, I = 96, H * 64
+    R = n_seq * N
+    h = torch.randn(R, D).bfloat16().to(DEV)
+    w = (torch.randn(3 * I, D) * D ** -0.5).bfloat16().to(DEV)
+    w_out, b_out, x, ln_w, ln_b = _tail_inputs(R, D, I)
+    out, lse, xmid, h2, stats = _call_out_fwd(h, w, w_out, b_out, x, ln_w, ln_b, n_seq, N, inner, H, drop_p=0.25, seed=77, site=5, site_out=9)
+    o_ref, _, _ = _call_fwd(h, w, n_seq, N, inner, H, drop_p=0.25, seed=77, site=5)
+    assert torch.equal(out, o_ref)
+    y = torch.empty(R, D, device=DEV)
+    d = _lib.LinearDims(R, D, I, 0, 0.25, 77, 9, PREC_BF16, None, 1)
+    st = torch.cuda.current_stream().cuda_stream
+    check(_lib.lib().msst_linear_fwd(C.byref(d), out.data_ptr(), w_out.data_ptr(), b_out.data_ptr(), x.data_ptr(), y.data_ptr(), None, st))
+    torch.cuda.synchronize()
+    assert rel_l2(xmid, y) < 2e-6                 # a different mask would give O(1) differences
+    want_h2 = torch.nn.functional.layer_norm(xmid.double(), (D,), ln_w.double(), ln_b.double(), 1e-5)
+    assert rel_l2(h2, want_h2) < 4e-3
+    out2, _, xmid2, h22, _ = _call_out_fwd(h, w, w_out, b_out, x, ln_w, ln_b, n_seq, N, inner, H, drop_p=0.25, seed=77, site=5, site_out=9)
+    assert torch.equal(xmid, xmid2) and torch.equal(h2, h22)
