@@ -30,6 +30,7 @@
 #include "ptx.cuh"
 #include <stdlib.h>
 #include <stdio.h>
+#include <type_traits>
 
 namespace msst {
 using namespace ptx;
@@ -44,7 +45,7 @@ constexpr int AB_MAXR = 8;                 // weight ring slots (upper bound)
 constexpr uint32_t AB_T16 = 16384;         // one [128 rows][64 bf16] SWIZZLE_128B tile
 constexpr uint32_t AB_BLK = 8192;          // one 64-row block of such a tile
 constexpr uint32_t COL_P = 0, COL_S = 192, COL_O = 256, COL_X = 192, COL_DH = 384;
-constexpr uint32_t COL_Y = 320;                // forward with the fused out-projection: Y accumulator (D columns)
+constexpr uint32_t COL_Y = 320, Y_COLS = 96;   // forward with the fused out-projection: two Y accumulators (tile parity), D <= 96 columns each
 
 struct AbParams {
     AttnGeom g;
@@ -60,8 +61,9 @@ struct AbParams {
     Drop drop;
     // forward, fused out-projection (AttnBlockOut): xmid = x + drop(o Wo^T + b_out), h2 = LN2(xmid), ln_stats = (mean, rstd)
     const float *x_res, *b_out, *ln_w, *ln_b;
-    float *ln_stats, *xmid;
+    float* ln_stats;
     Drop drop_out;
+    int tail_dbg;              // MSST_AB_TAILDBG (profiling only): 1 = no out-projection MMAs, 2 = no phase arithmetic
     long long* dbg;            // MSST_AB_DBG: clock64 timeline of CTA 0 ([item][16] slots)
 };
 #define AB_T(it, slot) do { if (p.dbg && blockIdx.x == 0 && (it) < 48) p.dbg[(it) * 16 + (slot)] = clock64(); } while (0)
@@ -114,7 +116,7 @@ __device__ __forceinline__ uint32_t key_mask16(const AttnGeom& g, int m, int cq)
 struct alignas(8) AbBars {
     uint64_t h_full[2], h_empty[2], w_full[AB_MAXR], w_empty[AB_MAXR], do_full[2], do_empty[2];
     uint64_t pro_full, conv_done, s_full, sdp_read, p_full, o_full, a_ready, dh_full, dh_free, stg_full, stg_free, dhs_full, dhs_free;
-    uint64_t y_full, out_full, out_free;         // forward with the fused out-projection
+    uint64_t y_full, out_full, out_free, xin_full, t_kfree[2], t_vfree, kv_free[2];   // forward with the fused out-projection
     uint32_t tmem_base;
 };
 
@@ -253,7 +255,8 @@ __device__ __forceinline__ void ab_setup(AbBars* bars, int warp, uint8_t* z0, ui
         mbar_init(&bars->stg_full, 16); mbar_init(&bars->stg_free, stg_free_count); mbar_init(&bars->sdp_read, 16);
         mbar_init(&bars->dhs_full, 16); mbar_init(&bars->dhs_free, 1);
         mbar_init(&bars->y_full, 1);
-        mbar_init(&bars->out_full, 16); mbar_init(&bars->out_free, 1);
+        mbar_init(&bars->out_full, 4); mbar_init(&bars->out_free, 1); mbar_init(&bars->xin_full, 1);
+        mbar_init(&bars->t_kfree[0], 1); mbar_init(&bars->t_kfree[1], 1); mbar_init(&bars->t_vfree, 1); mbar_init(&bars->kv_free[0], 1); mbar_init(&bars->kv_free[1], 1);
         fence_barrier_init();
     }
     if (warp == 16) {
@@ -261,8 +264,8 @@ __device__ __forceinline__ void ab_setup(AbBars* bars, int warp, uint8_t* z0, ui
         if (elect_one()) { prefetch_tmap(m0); prefetch_tmap(m1); prefetch_tmap(m2); if (m3) prefetch_tmap(m3); if (m4) prefetch_tmap(m4); }
     }
     // zero once: rows a slot group's box never writes (slots G*N .. 63) must stay finite (0 x NaN would poison the contractions)
-    for (uint32_t i = threadIdx.x; i < z0_bytes / 16; i += AB_THREADS) reinterpret_cast<uint4*>(z0)[i] = make_uint4(0, 0, 0, 0);
-    for (uint32_t i = threadIdx.x; i < z1_bytes / 16; i += AB_THREADS) reinterpret_cast<uint4*>(z1)[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = threadIdx.x; i < z0_bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(z0)[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = threadIdx.x; i < z1_bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(z1)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -292,29 +295,58 @@ __device__ __forceinline__ void store_tile(const AbParams& p, const CUtensorMap*
 // residual add of Transformer.forward :102 and the PreNorm LayerNorm of the FeedForward branch :25-29):
 //     xmid = x + dropout(concat_h(O_h) Wo^T + b_out),   h2 = LayerNorm(xmid),   stats2 = (mean, rstd)
 // The staged bf16 O tile of every item is ALSO the K-major A operand of  Y (+)= O_h Wo[:, 64h .. 64h+63]^T  (M = 128, N = D), which
-// accumulates over the heads of the tile in TMEM columns [COL_Y, COL_Y + D); the head's Wo column block travels through the weight
-// ring as a fourth slot per item.  One item after the tile's last head the compute threads run the tile epilogue (bias, dropout,
-// residual, two-pass LayerNorm: the arithmetic of gemm_tn_kernel<6> / mlp_block_fwd_kernel): the fp32 residual rows come straight from
-// global memory (one 32-byte sector per thread and 32-column chunk, L2-prefetched at the tile's second item), xmid leaves by 32-byte
-// stores, and h2 is staged in the K / V tiles of the current item's buffer -- dead between that item's O contraction and the
-// conversion two items later -- from where warp 18 writes it out by TMA.  o [R, I] is still written (the Wo weight gradient of the
-// backward reads it) but never re-read in the forward, and the separate out-projection GEMM launch is gone.
+// accumulates over the heads of the tile in TMEM (two accumulators of D columns, alternating with the tile); the head's Wo column
+// block travels through the weight ring as a fourth slot per item.  The tile epilogue (bias, dropout, residual, two-pass LayerNorm:
+// the arithmetic of gemm_tn_kernel<6> / mlp_block_fwd_kernel) belongs to FOUR EXTRA WARPS (20-23, thread = tile row = TMEM lane of
+// the M = 128 accumulator), not to the 512 softmax threads: folded into their loop (three variants were measured) it cost every item
+// ~0.7 k clks of worse code on top of its own work.  It runs in NCH + 1 phases under the first items of the NEXT tile and moves its
+// data through the K (| V) tile of the hosting item, which is dead from the item's S (O) contraction to the conversion two items
+// later -- so no shared memory is added and nothing is accessed row-per-thread in global memory (one LSU wavefront per row):
+//   phase c < NCH (item c):  S done (the MMA issuer commits t_kfree) -> TMA load of the [128 rows][32] fp32 chunk c of the residual x
+//                            into the K tile -> xmid = x + drop(Y + b) formed IN PLACE -> warp 18 TMA-stores the chunk; the values
+//                            are parked in the Y accumulator's own TMEM columns (tcgen05.st), the row sum rides in a register
+//   phase NCH (item NCH):    O done (t_vfree) -> mean / rstd over the parked row (two-pass, thread-local) -> h2 into the K | V tiles
+//                            as SWIZZLE_64B chunks -> TMA store
+// The softmax threads only wait (kv_free) before the conversion that overwrites a buffer a phase used.  Registers: the kernel is
+// launched with 768 threads x 80 registers; the softmax warps raise themselves to 96 (setmaxnreg), all other warps drop to 48.
+// o [R, I] is still written (the Wo weight gradient of the backward reads it) but never re-read in the forward, and the separate
+// out-projection GEMM launch (gemm_tn_kernel<6>) is gone.
 // =========================================================================================================
-__device__ __forceinline__ void ldg_nc_256(const float* ptr, float (&v)[8]) {
-    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(ptr));
+constexpr int AB_THREADS_OUT = 768;
+// one thread: chunk c of the residual rows of `tile` -> dst ([128 rows][32 fp32] SWIZZLE_128B)
+__device__ __forceinline__ void tail_load_x(const AbParams& p, AbBars* bars, const CUtensorMap* tma_x, uint8_t* dst, int c, int64_t tile) {
+    const AttnGeom& g = p.g;
+    const uint32_t rows = p.nbox == 1 ? 128u : (uint32_t)(g.G * g.N);
+    mbar_arrive_expect_tx(&bars->xin_full, (uint32_t)p.nbox * rows * 128u);
+    if (p.nbox == 1) tma_load_2d(dst, tma_x, &bars->xin_full, c * 32, (int)(tile * 128));
+    else
+        for (int gi = 0; gi < 2; ++gi) {
+            int c1, c2, c3;
+            group_coords(g, tile * 2 + gi, c1, c2, c3);
+            tma_load_4d(dst + gi * AB_BLK, tma_x, &bars->xin_full, c * 32, c1, c2, c3);
+        }
 }
-__device__ __forceinline__ void stg_256(float* ptr, const float (&v)[8]) {
-    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                 :: "l"(ptr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+__device__ __forceinline__ void tail_prefetch_x(const AbParams& p, const CUtensorMap* tma_x, int c, int64_t tile) {
+    if (tile >= p.n_tiles) return;
+    if (p.nbox == 1) tma_prefetch_l2_2d(tma_x, c * 32, (int)(tile * 128));
+    else
+        for (int gi = 0; gi < 2; ++gi) {
+            int c1, c2, c3;
+            group_coords(p.g, tile * 2 + gi, c1, c2, c3);
+            tma_prefetch_l2_4d(tma_x, c * 32, c1, c2, c3);
+        }
 }
-__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" :: "l"(ptr)); }
+// phases of the previous tile's epilogue that run at head h of the current tile: j in [lo, hi]; phase j runs at item min(j, H - 1)
+__device__ __forceinline__ void tail_schedule(int h, int H, int nch, int& lo, int& hi) {
+    lo = h; hi = (h == H - 1) ? nch : h;
+    if (hi > nch) hi = nch;                                       // (lo > hi: nothing at this item)
+}
 
 template <int NCH, bool OUT>
-__global__ void __launch_bounds__(AB_THREADS, 1)
+__global__ void __launch_bounds__(OUT ? AB_THREADS_OUT : AB_THREADS, 1)
 attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CUtensorMap tma_o,
                       const __grid_constant__ CUtensorMap tma_wo, const __grid_constant__ CUtensorMap tma_xmid, const __grid_constant__ CUtensorMap tma_h2,
-                      const AbParams p) {
+                      const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ AbParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     if (smem_u32(smem) & 1023u) __trap();
@@ -334,136 +366,10 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
 
     const int64_t my_tiles = blockIdx.x < p.n_tiles ? (p.n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
     const int64_t n_items = my_tiles * H;
-
-    if (warp == 16) {
-        // ===== TMA producer.  Ring order = the MMA issuer's consumption order: P(0), P(1), then per item: [Wo(it - 1)], P(it + 2); [Wo(last)] =====
-        if (elect_one()) {
-            Ring r{0, 0u, p.NR};
-            int64_t pk = 0; int phd = 0;                          // (tile counter, head) of the next prologue
-            auto load_pro = [&]() {
-                if (phd == 0) {
-                    const int buf = (int)(pk & 1);
-                    mbar_wait(&bars->h_empty[buf], ((uint32_t)(pk >> 1) & 1) ^ 1);
-                    load_h_tile<NCH>(p, &tma_h, s.h_s + (size_t)buf * p.hbuf_bytes, &bars->h_full[buf], blockIdx.x + pk * gridDim.x);
-                }
-                for (int t = 0; t < 3; ++t) load_w_slice<NCH>(p, &tma_w, bars, s.w_s, r, t, phd);
-                if (++phd == H) { phd = 0; ++pk; }
-            };
-            int yh = 0;
-            auto load_wo = [&]() {                                // Wo[:, 64 yh .. +63]: [D rows][64 cols] SWIZZLE_128B, K-major B of the out-projection
-                mbar_wait(&bars->w_empty[r.slot], r.ph ^ 1u);
-                mbar_arrive_expect_tx(&bars->w_full[r.slot], (uint32_t)D * 128u);
-                tma_load_2d(s.w_s + (size_t)r.slot * p.slot_bytes, &tma_wo, &bars->w_full[r.slot], yh * 64, 0);
-                r.next();
-                if (++yh == H) yh = 0;
-            };
-            if (n_items > 0) load_pro();
-            if (n_items > 1) load_pro();
-            for (int64_t it = 0; it < n_items; ++it) {
-                if (OUT && it >= 1) load_wo();
-                if (it + 2 < n_items) load_pro();
-            }
-            if (OUT && n_items > 0) load_wo();
-        }
-    } else if (warp == 17) {
-        // ===== MMA issuer: prologue(0), S(0), prologue(1); then per item: [Y(i-1)], O(i), S(i+1), prologue(i+2); [Y(last)] =====
-        // (the whole warp runs the control flow, one elected lane issues: see the backward kernel)
-        if (n_items > 0) {
-            const bool lead = elect_one();
-            Ring r{0, 0u, p.NR};
-            const uint32_t idesc_s = make_idesc_bf16(64, 64, 0, 0), idesc_o = make_idesc_bf16(64, 64, 0, 1), idesc_y = make_idesc_bf16(128, D, 0, 0);
-            const uint32_t qkv_addr = smem_u32(qkv_s);
-            const uint64_t pd0 = kdesc(smem_u32(p_s)), pd1 = kdesc(smem_u32(p_s) + AB_BLK);
-            int64_t pk = 0; int phd = 0;                          // (tile counter, head) of the next prologue
-            auto next_pro = [&]() { issue_prologue<NCH>(p, s, pk, phd, r, lead); if (++phd == H) { phd = 0; ++pk; } };
-            auto issue_s = [&](int64_t it) {
-                const uint32_t qa = qkv_addr + (uint32_t)(it & 1) * 3 * AB_T16;
-                mbar_wait(&bars->conv_done, (uint32_t)it & 1);    // Q, K, V tiles written (generic proxy + the writers' fence)
-                if (lead) AB_T(it, 8);
-                tc_fence_after();
-#pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    const uint64_t dq = kdesc(qa + b * AB_BLK), dk = kdesc(qa + AB_T16 + b * AB_BLK);
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)                // S_b = Q_b K_b^T
-                        if (lead) umma_bf16(s.tmem + COL_S + ((uint32_t)(16 * b) << 16), dq + (uint64_t)(ks * 2), dk + (uint64_t)(ks * 2), idesc_s, ks != 0);
-                }
-                if (lead) umma_commit(&bars->s_full);
-            };
-            int yh = 0;
-            auto issue_y = [&](int64_t it) {                      // Y (+)= O(it) Wo_h^T: the staged O tile [128 rows][64] is the K-major A operand
-                mbar_wait(&bars->stg_full, (uint32_t)it & 1);
-                mbar_wait(&bars->w_full[r.slot], r.ph);
-                if (lead) AB_T(it, 11);
-                tc_fence_after();
-                const uint64_t ad = kdesc(qkv_addr + (uint32_t)(it & 1) * 3 * AB_T16), bd = kdesc(s.w_addr + (uint32_t)r.slot * p.slot_bytes);
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                    if (lead) umma_bf16(s.tmem + COL_Y, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc_y, (yh | ks) != 0);
-                if (lead) {
-                    umma_commit(&bars->w_empty[r.slot]);
-                    umma_commit(&bars->stg_free);                 // second arrival (the first is the O store's): the Q tile may be overwritten
-                    if (yh == H - 1) umma_commit(&bars->y_full);
-                }
-                r.next();
-                if (++yh == H) yh = 0;
-            };
-            next_pro();
-            issue_s(0);
-            if (n_items > 1) next_pro();
-            for (int64_t it = 0; it < n_items; ++it) {
-                if (OUT && it >= 1) issue_y(it - 1);
-                const uint32_t va = qkv_addr + (uint32_t)(it & 1) * 3 * AB_T16 + 2 * AB_T16;
-                mbar_wait(&bars->p_full, (uint32_t)it & 1);
-                if (lead) AB_T(it, 10);
-                tc_fence_after();
-#pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    const uint64_t dv = mndesc(va + b * AB_BLK), dp = b ? pd1 : pd0;
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)                // O_b = P~_b V_b (V as MN-major B)
-                        if (lead) umma_bf16(s.tmem + COL_O + ((uint32_t)(16 * b) << 16), dp + (uint64_t)(ks * 2), dv + (uint64_t)(ks * 128), idesc_o, ks != 0);
-                }
-                if (lead) umma_commit(&bars->o_full);
-                if (it + 1 < n_items) {
-                    issue_s(it + 1);
-                    if (it + 2 < n_items) next_pro();             // the accumulators of item it + 1 were read before its conv_done
-                }
-                if (lead) AB_T(it, 9);
-            }
-            if (OUT) issue_y(n_items - 1);
-        }
-    } else if (warp == 18) {
-        // ===== TMA store of the staged O tiles (and, OUT, of the staged xmid / h2 chunks of the tile that ended one item ago) =====
-        if (elect_one()) {
-            int64_t n_out = 0;                                    // tile epilogues stored so far
-            auto out_rounds = [&](int64_t tile, const uint8_t* kv) {   // the staged h2 chunks of `tile`: [128 rows][64 B] SWIZZLE_64B each, 8 KB apart
-                mbar_wait(&bars->out_full, (uint32_t)n_out & 1u);
-#pragma unroll
-                for (int c = 0; c < NCH; ++c) store_tile_rows(p, &tma_h2, kv + c * 8192, 64, 32 * c, tile);
-                tma_store_commit();
-                tma_store_wait_read();
-                mbar_arrive(&bars->out_free);
-                ++n_out;
-            };
-            int64_t k = 0; int h = 0;
-            for (int64_t it = 0; it < n_items; ++it) {
-                const int64_t tile = blockIdx.x + k * gridDim.x;
-                const uint8_t* buf = qkv_s + (size_t)(it & 1) * 3 * AB_T16;
-                if (OUT && h == 0 && k > 0) out_rounds(tile - gridDim.x, buf + AB_T16);
-                mbar_wait(&bars->stg_full, (uint32_t)it & 1);
-                if (p.o) {
-                    store_tile(p, &tma_o, buf, h * 64, tile);
-                    tma_store_commit();
-                    tma_store_wait_read();
-                }
-                mbar_arrive(&bars->stg_free);
-                if (++h == H) { h = 0; ++k; }
-            }
-            if (OUT && n_items > 0) out_rounds(blockIdx.x + (my_tiles - 1) * gridDim.x, qkv_s + (size_t)((n_items - 1) & 1) * 3 * AB_T16 + AB_T16);
-        }
-    } else {
+    // OUT: register split between the warp groups (see the header); each group's code is dominated by its own setmaxnreg
+    if (warp < 16) {
         // ===== 512 compute threads: thread = (TMEM lane L, column quarter cq) =====
+        if (OUT) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
         const int lq = warp & 3, cq = warp >> 2, lane = threadIdx.x & 31;
         const int L = lq * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(lq * 32) << 16;
@@ -477,77 +383,7 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
         float* xmax = xch; float* xsum = xch + 4 * 128;
         int64_t cur_tile = -1, grow = -1; uint32_t vm = 0;
         int64_t k = 0; int h = 0;
-        // ---- OUT: the tile epilogue (the M = 128 out-projection accumulator holds tile row L in TMEM lane L) ----
-        int64_t growL = -1, growL_prev = -1;                      // global row of tile row L in the current / the previous tile
-        int64_t n_out = 0;                                        // tile epilogues staged so far
-        bool out_pending = false;                                 // the K / V tiles of some buffer hold staged h2 chunks
-        auto wait_out = [&]() {                                   // ... their TMA stores have read them
-            if (out_pending) { mbar_wait(&bars->out_free, (uint32_t)(n_out - 1) & 1u); out_pending = false; }
-        };
-        auto tile_epilogue = [&](int64_t kk, int64_t row, uint8_t* kv) {
-            const uint32_t sw64 = (uint32_t)((L >> 1) & 3);
-            const int64_t rrow = row >= 0 ? row : 0;
-            float y[NCH][8];
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {                       // the residual row: NCH 32-byte sectors, in flight under the waits below
-                if (row >= 0) ldg_nc_256(p.x_res + row * D + 32 * c + 8 * cq, y[c]);
-                else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) y[c][e] = 0.f;
-                }
-            }
-            wait_out();
-            mbar_wait(&bars->y_full, (uint32_t)kk & 1);
-            tc_fence_after();
-            float sum = 0.f;
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                uint32_t a[8];
-                tmem_ld_32x8(s.tmem + lane_addr + COL_Y + 32 * c + 8 * cq, a);
-                tmem_ld_wait();
-                const int col = 32 * c + 8 * cq;
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.b_out + col)), b1 = __ldg(reinterpret_cast<const float4*>(p.b_out + col + 4));
-                float f[8] = {__uint_as_float(a[0]) + b0.x, __uint_as_float(a[1]) + b0.y, __uint_as_float(a[2]) + b0.z, __uint_as_float(a[3]) + b0.w,
-                              __uint_as_float(a[4]) + b1.x, __uint_as_float(a[5]) + b1.y, __uint_as_float(a[6]) + b1.z, __uint_as_float(a[7]) + b1.w};
-                if (p.drop_out.on()) {
-                    float d4[4];
-                    drop_factor4(p.drop_out, (uint64_t)(rrow * D + col) >> 2, d4);
-                    f[0] *= d4[0]; f[1] *= d4[1]; f[2] *= d4[2]; f[3] *= d4[3];
-                    drop_factor4(p.drop_out, (uint64_t)(rrow * D + col + 4) >> 2, d4);
-                    f[4] *= d4[0]; f[5] *= d4[1]; f[6] *= d4[2]; f[7] *= d4[3];
-                }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) { y[c][e] += f[e]; sum += y[c][e]; }
-                if (row >= 0) stg_256(p.xmid + row * D + col, y[c]);
-            }
-            tc_fence_before();
-            // two-pass LayerNorm over the row's D values (4 column quarters): the statistics buffers of the softmax are idle here
-            xmax[cq * 128 + L] = sum;
-            asm volatile("bar.sync 1, 512;" ::: "memory");
-            const float mean = ((xmax[L] + xmax[128 + L]) + (xmax[256 + L] + xmax[384 + L])) / D;
-            float sq = 0.f;
-#pragma unroll
-            for (int c = 0; c < NCH; ++c)
-#pragma unroll
-                for (int e = 0; e < 8; ++e) { y[c][e] -= mean; sq = fmaf(y[c][e], y[c][e], sq); }
-            xsum[cq * 128 + L] = sq;
-            asm volatile("bar.sync 1, 512;" ::: "memory");
-            const float rstd = rsqrtf(((xsum[L] + xsum[128 + L]) + (xsum[256 + L] + xsum[384 + L])) / D + 1e-5f);
-            if (cq == 0 && row >= 0) { p.ln_stats[2 * row] = mean; p.ln_stats[2 * row + 1] = rstd; }
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {                       // h2 chunk c: [128 rows][64 B] SWIZZLE_64B at kv + 8 KB * c (K tile, then the V tile)
-                const int col = 32 * c + 8 * cq;
-                const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.ln_w + col)), w1 = __ldg(reinterpret_cast<const float4*>(p.ln_w + col + 4));
-                const float4 l0 = __ldg(reinterpret_cast<const float4*>(p.ln_b + col)), l1 = __ldg(reinterpret_cast<const float4*>(p.ln_b + col + 4));
-                *reinterpret_cast<uint4*>(kv + c * 8192 + L * 64 + ((((uint32_t)cq) ^ sw64) << 4)) =
-                    make_uint4(pack_bf(y[c][0] * rstd * w0.x + l0.x, y[c][1] * rstd * w0.y + l0.y), pack_bf(y[c][2] * rstd * w0.z + l0.z, y[c][3] * rstd * w0.w + l0.w),
-                               pack_bf(y[c][4] * rstd * w1.x + l1.x, y[c][5] * rstd * w1.y + l1.y), pack_bf(y[c][6] * rstd * w1.z + l1.z, y[c][7] * rstd * w1.w + l1.w));
-            }
-            fence_proxy_async();
-            warp_arrive(&bars->out_full, lane);
-            ++n_out;
-            out_pending = true;
-        };
+        bool hosted = false; uint32_t n_kvf0 = 0, n_kvf1 = 0;     // OUT: the previous item hosted epilogue phases / kv_free completions consumed
         if (n_items > 0) {                                        // pipeline prologue: Q, K, V of item 0
             mbar_wait(&bars->pro_full, 0);
             tc_fence_after();
@@ -566,12 +402,6 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
                 const bool ok = group < g.groups && slot_to(g, group, 0, m, seq, pos);
                 grow = ok ? row_of(g, seq, pos) : -1;
                 vm = ok ? vm_geom : 0u;
-                if (OUT) {
-                    const int64_t gl = tile * 2 + (L >> 6);
-                    const bool okl = gl < g.groups && slot_to(g, gl, 0, L & 63, seq, pos);
-                    growL_prev = growL;
-                    growL = okl ? row_of(g, seq, pos) : -1;
-                }
             }
             // ---- softmax of row `slot`, key columns 16*cq .. +15 of its block ----
             const uint64_t hidx = pair_base(g, tile * 2 + blk, h) + (uint64_t)(m * 32 + 8 * cq);
@@ -625,15 +455,13 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
             l = (xsum[L] + xsum[128 + L]) + (xsum[256 + L] + xsum[384 + L]);
             const float inv = l > 0.f ? 1.f / l : 0.f;
             if (cq == 0 && grow >= 0) p.lse_out[grow * H + h] = (sub + log2f(l)) * 0.6931471805599453f;
-            // ---- OUT: pull the tile's residual rows into L2 well before the tile epilogue reads them (one 128-byte line per row and chunk) ----
-            if (OUT && cq == 0 && growL >= 0 && h == (H > 1 ? 1 : 0)) {
-#pragma unroll
-                for (int c = 0; c < NCH; ++c) prefetch_l2(p.x_res + growL * D + 32 * c);
-            }
             // ---- Q, K, V of item it + 1 -> the other tile buffer (runs under the O MMAs of item it) ----
             if (it + 1 < n_items) {
-                if (it >= 1) mbar_wait(&bars->stg_free, (uint32_t)(it - 1) & 1);   // that buffer's Q tile staged O(it - 1): its store (and out-projection MMA) has read it
-                if (OUT) wait_out();                              // ... and its K / V tiles staged h2
+                if (it >= 1) mbar_wait(&bars->stg_free, (uint32_t)(it - 1) & 1);   // that buffer's Q tile staged O(it - 1): its store (and, OUT, the out-projection MMA) has read it
+                if (OUT && hosted) {                              // ... and the epilogue phases its K | V tiles staged at item it - 1 have left
+                    if (it & 1) { mbar_wait(&bars->kv_free[0], n_kvf0 & 1u); ++n_kvf0; }   // (one barrier per item parity: a completion can never run two ahead of this wait)
+                    else { mbar_wait(&bars->kv_free[1], n_kvf1 & 1u); ++n_kvf1; }
+                }
                 mbar_wait(&bars->pro_full, ph ^ 1u);
                 if (threadIdx.x == 0) AB_T(it, 3);
                 tc_fence_after();
@@ -643,15 +471,10 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
                 warp_arrive(&bars->conv_done, lane);
                 if (threadIdx.x == 0) AB_T(it, 4);
             }
+            // ---- epilogue: O row / l -> bf16 -> staging (the item's own Q tile, dead since S) -> TMA store ----
             mbar_wait(&bars->o_full, ph);
             if (threadIdx.x == 0) AB_T(it, 5);
             tc_fence_after();
-            if (OUT) {
-                // the tile that ended with the previous item: its Y accumulator is complete, and this item's K / V tiles are dead (S and O done)
-                if (h == 0 && k > 0) tile_epilogue(k - 1, growL_prev, qkv_s + (size_t)(it & 1) * 3 * AB_T16 + AB_T16);
-                if (threadIdx.x == 0) AB_T(it, 12);
-            }
-            // ---- epilogue: O row / l -> bf16 -> staging (the item's own Q tile, dead since S) -> TMA store ----
             {
                 uint32_t v[16], o8[8];
                 tmem_ld_32x16(s.tmem + lane_addr + COL_O + 16 * cq, v);
@@ -664,9 +487,290 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
             fence_proxy_async();
             warp_arrive(&bars->stg_full, lane);
             if (threadIdx.x == 0) AB_T(it, 6);
+            if (OUT) { int lo, hi; tail_schedule(h, H, NCH, lo, hi); hosted = k > 0 && lo <= hi; }   // did THIS item host phases? (tested at the next one)
             if (++h == H) { h = 0; ++k; }
         }
-        if (OUT && n_items > 0) tile_epilogue(k - 1, growL, qkv_s + (size_t)((n_items - 1) & 1) * 3 * AB_T16 + AB_T16);
+    } else
+    if (warp >= 16 && warp < 20) {
+    if (OUT) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    if (warp == 16) {
+        // ===== TMA producer.  Ring order = the MMA issuer's consumption order: P(0), P(1), then per item: [Wo(it - 1)], P(it + 2); [Wo(last)] =====
+        if (elect_one()) {
+            Ring r{0, 0u, p.NR};
+            int64_t pk = 0; int phd = 0;                          // (tile counter, head) of the next prologue
+            auto load_pro = [&]() {
+                if (phd == 0) {
+                    const int buf = (int)(pk & 1);
+                    mbar_wait(&bars->h_empty[buf], ((uint32_t)(pk >> 1) & 1) ^ 1);
+                    load_h_tile<NCH>(p, &tma_h, s.h_s + (size_t)buf * p.hbuf_bytes, &bars->h_full[buf], blockIdx.x + pk * gridDim.x);
+                }
+                for (int t = 0; t < 3; ++t) load_w_slice<NCH>(p, &tma_w, bars, s.w_s, r, t, phd);
+                if (++phd == H) { phd = 0; ++pk; }
+            };
+            int yh = 0;
+            auto load_wo = [&]() {                                // Wo[:, 64 yh .. +63]: [D rows][64 cols] SWIZZLE_128B, K-major B of the out-projection
+                mbar_wait(&bars->w_empty[r.slot], r.ph ^ 1u);
+                mbar_arrive_expect_tx(&bars->w_full[r.slot], (uint32_t)D * 128u);
+                tma_load_2d(s.w_s + (size_t)r.slot * p.slot_bytes, &tma_wo, &bars->w_full[r.slot], yh * 64, 0);
+                r.next();
+                if (++yh == H) yh = 0;
+            };
+            if (n_items > 0) load_pro();
+            if (n_items > 1) load_pro();
+            for (int64_t it = 0; it < n_items; ++it) {
+                if (OUT && it >= 1) load_wo();
+                if (it + 2 < n_items) load_pro();
+            }
+            if (OUT && n_items > 0) load_wo();
+        }
+    } else if (warp == 17) {
+        // ===== MMA issuer: prologue(0), S(0), prologue(1); then per item: [Y(i-1)], O(i), S(i+1), prologue(i+2); [Y(last)] =====
+        // (the whole warp runs the control flow, one elected lane issues: see the backward kernel)
+        if (n_items > 0) {
+            const bool lead = elect_one();
+            Ring r{0, 0u, p.NR};
+            const uint32_t idesc_s = make_idesc_bf16(64, 64, 0, 0), idesc_o = make_idesc_bf16(64, 64, 0, 1), idesc_y = make_idesc_bf16(128, D, 0, 0);
+            const uint32_t qkv_addr = smem_u32(qkv_s);
+            const uint64_t pd0 = kdesc(smem_u32(p_s)), pd1 = kdesc(smem_u32(p_s) + AB_BLK);
+            int64_t pk = 0; int phd = 0;                          // (tile counter, head) of the next prologue
+            auto next_pro = [&]() { issue_prologue<NCH>(p, s, pk, phd, r, lead); if (++phd == H) { phd = 0; ++pk; } };
+            int64_t sk = 0; int sh = 0;                           // (tile counter, head) of the next S item
+            auto issue_s = [&](int64_t it) {
+                const uint32_t qa = qkv_addr + (uint32_t)(it & 1) * 3 * AB_T16;
+                mbar_wait(&bars->conv_done, (uint32_t)it & 1);    // Q, K, V tiles written (generic proxy + the writers' fence)
+                if (lead) AB_T(it, 8);
+                tc_fence_after();
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const uint64_t dq = kdesc(qa + b * AB_BLK), dk = kdesc(qa + AB_T16 + b * AB_BLK);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)                // S_b = Q_b K_b^T
+                        if (lead) umma_bf16(s.tmem + COL_S + ((uint32_t)(16 * b) << 16), dq + (uint64_t)(ks * 2), dk + (uint64_t)(ks * 2), idesc_s, ks != 0);
+                }
+                if (lead) umma_commit(&bars->s_full);
+                if (OUT) {                                        // the item hosts phases of the previous tile's epilogue: its K tile is theirs once S is done
+                    int lo, hi;
+                    tail_schedule(sh, H, NCH, lo, hi);
+                    if (lead && sk > 0 && lo <= hi) umma_commit(&bars->t_kfree[it & 1]);
+                    if (++sh == H) { sh = 0; ++sk; }
+                }
+            };
+            int yh = 0; uint32_t ycol = COL_Y;                    // head / accumulator (tile parity) of the next out-projection item
+            auto issue_y = [&](int64_t it) {                      // Y (+)= O(it) Wo_h^T: the staged O tile [128 rows][64] is the K-major A operand
+                mbar_wait(&bars->stg_full, (uint32_t)it & 1);
+                mbar_wait(&bars->w_full[r.slot], r.ph);
+                if (lead) AB_T(it, 11);
+                tc_fence_after();
+                const uint64_t ad = kdesc(qkv_addr + (uint32_t)(it & 1) * 3 * AB_T16), bd = kdesc(s.w_addr + (uint32_t)r.slot * p.slot_bytes);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    if (lead && !(p.tail_dbg & 1)) umma_bf16(s.tmem + ycol, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc_y, (yh | ks) != 0);
+                if (lead) {
+                    umma_commit(&bars->w_empty[r.slot]);
+                    umma_commit(&bars->stg_free);                 // second arrival (the first is the O store's): the Q tile may be overwritten
+                    if (yh == H - 1) umma_commit(&bars->y_full);
+                }
+                r.next();
+                if (++yh == H) { yh = 0; ycol ^= (COL_Y ^ (COL_Y + Y_COLS)); }
+            };
+            next_pro();
+            issue_s(0);
+            if (n_items > 1) next_pro();
+            int64_t k = 0; int h = 0;
+            for (int64_t it = 0; it < n_items; ++it) {
+                if (OUT && it >= 1) issue_y(it - 1);
+                const uint32_t va = qkv_addr + (uint32_t)(it & 1) * 3 * AB_T16 + 2 * AB_T16;
+                mbar_wait(&bars->p_full, (uint32_t)it & 1);
+                if (lead) AB_T(it, 10);
+                tc_fence_after();
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const uint64_t dv = mndesc(va + b * AB_BLK), dp = b ? pd1 : pd0;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)                // O_b = P~_b V_b (V as MN-major B)
+                        if (lead) umma_bf16(s.tmem + COL_O + ((uint32_t)(16 * b) << 16), dp + (uint64_t)(ks * 2), dv + (uint64_t)(ks * 128), idesc_o, ks != 0);
+                }
+                if (lead) umma_commit(&bars->o_full);
+                if (OUT) {                                        // the item hosts the LayerNorm phase: its V tile is free as well once O is done
+                    int lo, hi;
+                    tail_schedule(h, H, NCH, lo, hi);
+                    if (lead && k > 0 && lo <= hi && hi == NCH) umma_commit(&bars->t_vfree);
+                    if (++h == H) { h = 0; ++k; }
+                }
+                if (it + 1 < n_items) {
+                    issue_s(it + 1);
+                    if (it + 2 < n_items) next_pro();             // the accumulators of item it + 1 were read before its conv_done
+                }
+                if (lead) AB_T(it, 9);
+            }
+            if (OUT) {
+                issue_y(n_items - 1);
+                if (lead) { umma_commit(&bars->t_kfree[n_items & 1]); umma_commit(&bars->t_vfree); }   // the CTA's last tile: its phases run after the last item
+            }
+        }
+    } else if (warp == 18) {
+        // ===== TMA store of the staged O tiles (and, OUT, of the staged xmid / h2 chunks of the previous tile's epilogue phases) =====
+        if (elect_one()) {
+            uint32_t n_out = 0;                                   // staging rounds stored so far
+            auto out_round = [&](int j, int64_t tile, const uint8_t* kv) {   // phase j of the epilogue of `tile`, staged at kv
+                mbar_wait(&bars->out_full, n_out & 1u);
+                if (j < NCH) store_tile(p, &tma_xmid, kv, 32 * j, tile);
+                else {
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) store_tile_rows(p, &tma_h2, kv + c * 8192, 64, 32 * c, tile);
+                }
+                tma_store_commit();
+                tma_store_wait_read();
+                mbar_arrive(&bars->out_free);
+                ++n_out;
+            };
+            int64_t k = 0; int h = 0;
+            for (int64_t it = 0; it < n_items; ++it) {
+                const int64_t tile = blockIdx.x + k * gridDim.x;
+                const uint8_t* buf = qkv_s + (size_t)(it & 1) * 3 * AB_T16;
+                if (OUT && k > 0) {
+                    int lo, hi;
+                    tail_schedule(h, H, NCH, lo, hi);
+                    for (int j = lo; j <= hi; ++j) out_round(j, tile - gridDim.x, buf + AB_T16);
+                    if (lo <= hi) mbar_arrive(&bars->kv_free[it & 1]);   // the softmax threads may convert into this buffer again
+                }
+                mbar_wait(&bars->stg_full, (uint32_t)it & 1);
+                if (p.o) {
+                    store_tile(p, &tma_o, buf, h * 64, tile);
+                    tma_store_commit();
+                    tma_store_wait_read();
+                }
+                mbar_arrive(&bars->stg_free);
+                if (++h == H) { h = 0; ++k; }
+            }
+            if (OUT && n_items > 0)
+                for (int j = 0; j <= NCH; ++j) out_round(j, blockIdx.x + (my_tiles - 1) * gridDim.x, qkv_s + (size_t)(n_items & 1) * 3 * AB_T16 + AB_T16);
+        }
+    }
+    } else if (OUT && warp >= 20) {
+        // ===== tile-epilogue warps: thread = tile row T = TMEM lane T of the out-projection accumulator =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+        const int lane = threadIdx.x & 31, tq = warp - 20;
+        const int T = tq * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(tq * 32) << 16;
+        const uint32_t sw128 = (uint32_t)(T & 7), sw64 = (uint32_t)((T >> 1) & 3);
+        uint32_t n_in = 0, n_out = 0, n_kf0 = 0, n_kf1 = 0, n_vf = 0;   // completions consumed so far per barrier
+        // b_out | ln_w | ln_b in shared memory: every thread needs all D of each, and a global load per use misses the (tiny) L1 -- ~600 clks apiece,
+        // which made a chunk phase take 6 k clks
+        float* cst = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + ((sizeof(AbBars) + 15) & ~size_t(15)));
+        if (T < D) { cst[T] = p.b_out[T]; cst[D + T] = p.ln_w[T]; cst[2 * D + T] = p.ln_b[T]; }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        Drop dro = p.drop_out;                                    // (device-resident seed offset folded in once)
+        dro.seed += dro.seed_dev ? __ldg(dro.seed_dev) : 0ull;
+        dro.seed_dev = nullptr;
+        for (int64_t kk = 0; kk < my_tiles; ++kk) {
+            const bool last = kk + 1 == my_tiles;
+            const int64_t ptile = blockIdx.x + kk * gridDim.x;
+            int64_t row;                                          // global row of tile row T, or -1
+            {
+                int64_t seq; int pos;
+                const int64_t gl = ptile * 2 + (T >> 6);
+                row = (gl < g.groups && slot_to(g, gl, 0, T & 63, seq, pos)) ? row_of(g, seq, pos) : -1;
+            }
+            const uint32_t ty = s.tmem + lane_addr + COL_Y + (uint32_t)(kk & 1) * Y_COLS;
+            float sum = 0.f;
+            int64_t host_prev = -1;
+            for (int j = 0; j <= NCH; ++j) {
+                const int64_t host = last ? n_items : (kk + 1) * H + (j < H - 1 ? j : H - 1);   // the item whose K | V tiles stage this phase
+                uint8_t* kv = qkv_s + (size_t)(host & 1) * 3 * AB_T16 + AB_T16;
+                const bool same_host = host == host_prev;
+                if (same_host && n_out > 0) mbar_wait(&bars->out_free, (n_out - 1u) & 1u);   // the K tile still stages the previous round
+                if (!same_host) {                                 // S of the hosting item is done: its K tile is dead
+                    if (host & 1) { mbar_wait(&bars->t_kfree[1], n_kf1 & 1u); ++n_kf1; }
+                    else { mbar_wait(&bars->t_kfree[0], n_kf0 & 1u); ++n_kf0; }
+                    host_prev = host;
+                }
+                if (T == 0 && !last) AB_T(host, 13);
+                // (a different hosting item = the other buffer: the chunk load below overlaps the previous round's TMA store)
+                if (j < NCH && tq == 0 && lane == 0) {
+                    tail_load_x(p, bars, &tma_x, kv, j, ptile);
+                    // pull what the next phase / the next tile's first phase will load into L2 meanwhile
+                    if (j + 1 < NCH) tail_prefetch_x(p, &tma_x, j + 1, ptile);
+                    else if (!last) tail_prefetch_x(p, &tma_x, 0, ptile + gridDim.x);
+                }
+                if (!same_host && n_out > 0) mbar_wait(&bars->out_free, (n_out - 1u) & 1u);   // (completions are observed in order)
+                if (j < NCH) {
+                    const int c = j;
+                    if (j == 0) mbar_wait(&bars->y_full, (uint32_t)kk & 1u);
+                    mbar_wait(&bars->xin_full, n_in & 1u);
+                    ++n_in;
+                    if (T == 0 && !last) AB_T(host, 14);
+                    tc_fence_after();
+                    uint8_t* xr = kv + T * 128;
+#pragma unroll 1
+                    for (int i = 0; i < 2; ++i) {                 // 16 columns at a time
+                        uint32_t a[16];
+                        tmem_ld_32x16(ty + 32 * c + 16 * i, a);
+                        tmem_ld_wait();
+                        const int col = 32 * c + 16 * i;
+#pragma unroll
+                        for (int hf = 0; hf < 4; ++hf) {
+                            float4* xp = reinterpret_cast<float4*>(xr + ((((uint32_t)(4 * i + hf)) ^ sw128) << 4));
+                            const float4 r = *xp;
+                            const float4 bb = *reinterpret_cast<const float4*>(cst + col + 4 * hf);
+                            float f0 = __uint_as_float(a[4 * hf]) + bb.x, f1 = __uint_as_float(a[4 * hf + 1]) + bb.y, f2 = __uint_as_float(a[4 * hf + 2]) + bb.z,
+                                  f3 = __uint_as_float(a[4 * hf + 3]) + bb.w;
+                            if (dro.on()) {
+                                float d4[4];
+                                drop_factor4(dro, (uint64_t)((row >= 0 ? row : 0) * D + col + 4 * hf) >> 2, d4);
+                                f0 *= d4[0]; f1 *= d4[1]; f2 *= d4[2]; f3 *= d4[3];
+                            }
+                            f0 += r.x; f1 += r.y; f2 += r.z; f3 += r.w;
+                            *xp = make_float4(f0, f1, f2, f3);    // xmid, staged in place for the TMA store
+                            sum += (f0 + f1) + (f2 + f3);
+                            a[4 * hf] = __float_as_uint(f0); a[4 * hf + 1] = __float_as_uint(f1); a[4 * hf + 2] = __float_as_uint(f2); a[4 * hf + 3] = __float_as_uint(f3);
+                        }
+                        tmem_st_32x16(ty + 32 * c + 16 * i, a);   // parked for the LayerNorm phase
+                    }
+                    tmem_st_wait();
+                } else {
+                    mbar_wait(&bars->t_vfree, n_vf & 1u);         // O of the hosting item is done: the V tile is dead as well
+                    ++n_vf;
+                    tc_fence_after();
+                    const float mean = sum / D;
+                    float sq = 0.f;
+#pragma unroll 1
+                    for (int i = 0; i < D / 16; ++i) {
+                        uint32_t a[16];
+                        tmem_ld_32x16(ty + 16 * i, a);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) { const float d = __uint_as_float(a[e]) - mean; sq = fmaf(d, d, sq); }
+                    }
+                    const float rstd = rsqrtf(sq / D + 1e-5f);
+                    if (row >= 0) *reinterpret_cast<float2*>(p.ln_stats + 2 * row) = make_float2(mean, rstd);
+#pragma unroll 1
+                    for (int i = 0; i < D / 16; ++i) {            // h2 chunk i / 2 ([128 rows][64 B] SWIZZLE_64B at kv + 8 KB * chunk), 16-byte units 2 (i % 2), + 1
+                        uint32_t a[16];
+                        tmem_ld_32x16(ty + 16 * i, a);
+                        tmem_ld_wait();
+                        const int col = 16 * i;
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            uint32_t o[4];
+#pragma unroll
+                            for (int hf = 0; hf < 2; ++hf) {
+                                const int e0 = 8 * u + 4 * hf;
+                                const float4 w = *reinterpret_cast<const float4*>(cst + D + col + e0), lb = *reinterpret_cast<const float4*>(cst + 2 * D + col + e0);
+                                o[2 * hf] = pack_bf((__uint_as_float(a[e0]) - mean) * rstd * w.x + lb.x, (__uint_as_float(a[e0 + 1]) - mean) * rstd * w.y + lb.y);
+                                o[2 * hf + 1] = pack_bf((__uint_as_float(a[e0 + 2]) - mean) * rstd * w.z + lb.z, (__uint_as_float(a[e0 + 3]) - mean) * rstd * w.w + lb.w);
+                            }
+                            *reinterpret_cast<uint4*>(kv + (i >> 1) * 8192 + T * 64 + ((((uint32_t)(2 * (i & 1) + u)) ^ sw64) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async();
+                warp_arrive(&bars->out_full, lane);
+                ++n_out;
+                if (T == 0 && !last) AB_T(host, 15);
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -1070,7 +1174,7 @@ void dbg_dump(const char* what, cudaStream_t st, int& count) {
     printf("%s timeline, CTA 0 (clks rel. to item 0), compute slots 0-6 | MMA-issuer slots 8-12 (see the AB_T calls)\n", what);
     for (int i = 0; i < 40; ++i) {
         printf("%2d:", i);
-        for (int k = 0; k < 13; ++k) { if (k == 7) { printf("  |"); continue; } printf(" %7lld", h[i * 16 + k] ? h[i * 16 + k] - t0 : -1); }
+        for (int k = 0; k < 16; ++k) { if (k == 7) { printf("  |"); continue; } printf(" %7lld", h[i * 16 + k] ? h[i * 16 + k] - t0 : -1); }
         printf("\n");
     }
     fflush(stdout);
@@ -1085,7 +1189,8 @@ int fill_params(AbParams& p, const AttnGeom& g, int D, bool bwd, size_t& smem_by
     p.hbuf_bytes = (uint32_t)p.nch * 8192u;
     // forward: h [2], Q,K,V double-buffered (6 tiles) + P~ + 2 x [4][128] statistics; backward: h [1], Q,K,V + dO [2] + P~ + dS + dh staging + [4][128] partial sums
     p.hbufs = bwd ? 1 : 2;
-    const size_t fixed = (size_t)p.hbufs * p.hbuf_bytes + (bwd ? 8 * AB_T16 + 4 * 128 * sizeof(float) : 7 * AB_T16 + 2 * 4 * 128 * sizeof(float)) + sizeof(AbBars);
+    const size_t fixed = (size_t)p.hbufs * p.hbuf_bytes + (bwd ? 8 * AB_T16 + 4 * 128 * sizeof(float) : 7 * AB_T16 + 2 * 4 * 128 * sizeof(float)) + sizeof(AbBars) +
+                         (bwd ? 0 : 16 + 3 * 96 * sizeof(float));   // forward: + b_out | ln_w | ln_b of the fused tail
     const size_t cap = 232448;   // 227 KB of dynamic shared memory per CTA
     int nr = AB_MAXR;
     const int nr_min = bwd ? 6 : 3;   // backward: the data-gradient blocks of item i and the recomputation blocks of item i + 2 are consumed back to back
@@ -1104,10 +1209,10 @@ bool attn_block_supported(const AttnGeom& g, int D) {
 
 template <int NCH, bool OUT>
 static int launch_fwd(const CUtensorMap& t_h, const CUtensorMap& t_w, const CUtensorMap& t_o, const CUtensorMap& t_wo, const CUtensorMap& t_xmid,
-                      const CUtensorMap& t_h2, const AbParams& p, int grid, size_t smem, cudaStream_t st) {
+                      const CUtensorMap& t_h2, const CUtensorMap& t_x, const AbParams& p, int grid, size_t smem, cudaStream_t st) {
     static PerDeviceOnce once;
     if (once.first()) MSST_CUDA(cudaFuncSetAttribute(attn_block_fwd_kernel<NCH, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attn_block_fwd_kernel<NCH, OUT><<<grid, AB_THREADS, smem, st>>>(t_h, t_w, t_o, t_wo, t_xmid, t_h2, p);
+    attn_block_fwd_kernel<NCH, OUT><<<grid, OUT ? AB_THREADS_OUT : AB_THREADS, smem, st>>>(t_h, t_w, t_o, t_wo, t_xmid, t_h2, t_x, p);
     return MSST_OK;
 }
 
@@ -1117,7 +1222,7 @@ int attn_block_fwd(const AttnGeom& g, int D, const bf16* h, const bf16* w_qkv, b
     size_t smem = 0;
     if (int rc = fill_params(p, g, D, false, smem)) return rc;
     p.lse_out = lse; p.o = out; p.drop = drop;
-    CUtensorMap t_h, t_w, t_o, t_wo, t_xmid, t_h2;
+    CUtensorMap t_h, t_w, t_o, t_wo, t_xmid, t_h2, t_x;
     const int64_t I = (int64_t)g.H * 64;
     if (int rc = act_tmap(&t_h, g, h, D, p.nbox, 32, 64)) return rc;
     if (out) { if (int rc = act_tmap(&t_o, g, out, I, p.nbox, 64, 128)) return rc; }
@@ -1126,27 +1231,30 @@ int attn_block_fwd(const AttnGeom& g, int D, const bf16* h, const bf16* w_qkv, b
     { const int64_t dims[2] = {D, I3}, strides[1] = {D}; const int box[2] = {32, 64};
       if (int rc = make_tmap_bf16_nd(&t_w, w_qkv, 2, dims, strides, box, 64)) return rc; }
     if (tail) {
+        MSST_REQUIRE(g.n_seq * g.N < (int64_t)2147483647, "attn_block_fwd: the fused out-projection indexes rows with 32 bits");
         MSST_REQUIRE(tail->w_out && tail->b_out && tail->x && tail->xmid && tail->ln_w && tail->ln_b && tail->h2 && tail->ln_stats,
                      "attn_block_fwd: the fused out-projection needs w_out, b_out, x, xmid, ln_w, ln_b, h2 and ln_stats");
-        p.x_res = tail->x; p.b_out = tail->b_out; p.ln_w = tail->ln_w; p.ln_b = tail->ln_b; p.ln_stats = tail->ln_stats; p.xmid = tail->xmid; p.drop_out = tail->drop;
+        p.x_res = tail->x; p.b_out = tail->b_out; p.ln_w = tail->ln_w; p.ln_b = tail->ln_b; p.ln_stats = tail->ln_stats; p.drop_out = tail->drop;
+        { static int v = -1; if (v < 0) { const char* e = getenv("MSST_AB_TAILDBG"); v = e ? atoi(e) : 0; } p.tail_dbg = v; }
         { const int64_t dims[2] = {I, D}, strides[1] = {I}; const int box[2] = {64, D};
           if (int rc = make_tmap_bf16_nd(&t_wo, tail->w_out, 2, dims, strides, box, 128)) return rc; }
-        t_xmid = t_h;   // (xmid leaves by direct stores)
+        if (int rc = act_tmap(&t_xmid, g, tail->xmid, D, p.nbox, 32, 128, 4)) return rc;
+        if (int rc = act_tmap(&t_x, g, tail->x, D, p.nbox, 32, 128, 4)) return rc;
         if (int rc = act_tmap(&t_h2, g, tail->h2, D, p.nbox, 32, 64)) return rc;
     } else {
         MSST_REQUIRE(out, "attn_block_fwd: null output");
-        t_wo = t_h; t_xmid = t_h; t_h2 = t_h;
+        t_wo = t_h; t_xmid = t_h; t_h2 = t_h; t_x = t_h;
     }
     const int grid = (int)(p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs);
     if (p.dbg) cudaMemsetAsync(p.dbg, 0, 48 * 16 * 8, st);
     int rc = MSST_OK;
     switch (p.nch * 2 + (tail ? 1 : 0)) {
-        case 2: rc = launch_fwd<1, false>(t_h, t_w, t_o, t_wo, t_xmid, t_h2, p, grid, smem, st); break;
-        case 3: rc = launch_fwd<1, true>(t_h, t_w, t_o, t_wo, t_xmid, t_h2, p, grid, smem, st); break;
-        case 4: rc = launch_fwd<2, false>(t_h, t_w, t_o, t_wo, t_xmid, t_h2, p, grid, smem, st); break;
-        case 5: rc = launch_fwd<2, true>(t_h, t_w, t_o, t_wo, t_xmid, t_h2, p, grid, smem, st); break;
-        case 6: rc = launch_fwd<3, false>(t_h, t_w, t_o, t_wo, t_xmid, t_h2, p, grid, smem, st); break;
-        default: rc = launch_fwd<3, true>(t_h, t_w, t_o, t_wo, t_xmid, t_h2, p, grid, smem, st); break;
+        case 2: rc = launch_fwd<1, false>(t_h, t_w, t_o, t_wo, t_xmid, t_h2, t_x, p, grid, smem, st); break;
+        case 3: rc = launch_fwd<1, true>(t_h, t_w, t_o, t_wo, t_xmid, t_h2, t_x, p, grid, smem, st); break;
+        case 4: rc = launch_fwd<2, false>(t_h, t_w, t_o, t_wo, t_xmid, t_h2, t_x, p, grid, smem, st); break;
+        case 5: rc = launch_fwd<2, true>(t_h, t_w, t_o, t_wo, t_xmid, t_h2, t_x, p, grid, smem, st); break;
+        case 6: rc = launch_fwd<3, false>(t_h, t_w, t_o, t_wo, t_xmid, t_h2, t_x, p, grid, smem, st); break;
+        default: rc = launch_fwd<3, true>(t_h, t_w, t_o, t_wo, t_xmid, t_h2, t_x, p, grid, smem, st); break;
     }
     if (rc) return rc;
     MSST_LAUNCH_CHECK();
