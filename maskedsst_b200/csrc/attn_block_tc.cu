@@ -660,6 +660,8 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
         float* cst = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + ((sizeof(AbBars) + 15) & ~size_t(15)));
         if (T < D) { cst[T] = p.b_out[T]; cst[D + T] = p.ln_w[T]; cst[2 * D + T] = p.ln_b[T]; }
         asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (T == 0 && my_tiles > 0)                               // the first tile's residual rows -> L2 while its items run
+            for (int c = 0; c < NCH; ++c) tail_prefetch_x(p, &tma_x, c, blockIdx.x);
         Drop dro = p.drop_out;                                    // (device-resident seed offset folded in once)
         dro.seed += dro.seed_dev ? __ldg(dro.seed_dev) : 0ull;
         dro.seed_dev = nullptr;
