@@ -552,7 +552,8 @@ def roofline(args, B, dev, peaks):
     launching stream at the step's spatial-stack shape.  Its algorithmic HBM bytes per launch: R*(D*2 [h] + I*2 [dO] + H*4 [lse]) in,
     R*(3I*2 [dqkv] + D*4 [dh]) out; its tensor work: recomputation 2*R*D*3I + five 64x64x64 contractions per (64-token sequence,
     head) + data gradient 2*R*3I*D.  Both fractions are reported; `bound` names the larger.  `other_kernels`: the same kernel at the
-    spectral-stack shape, the fused forward at both shapes, and the weight-gradient GEMM that reads dqkv."""
+    spectral-stack shape, the fused forward (with its out-projection / residual / LayerNorm tail, as the step runs it) at both shapes,
+    and the weight-gradient GEMM that reads dqkv."""
     import ctypes as C
     import torch
     from maskedsst_b200 import _lib
@@ -577,7 +578,12 @@ def roofline(args, B, dev, peaks):
         dh = torch.empty(R, D, device=dev)
         flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
         bwd_bytes = R * (D * 2 + I * 2 + H * 4) + R * (3 * I * 2 + D * 4)
-        fwd_bytes = R * D * 2 + R * (I * 2 + H * 4)
+        # forward incl. its fused tail (out-projection + residual + LN2): h, x in; o, lse, xmid, h2, stats2 out
+        fwd_bytes = R * (D * 2 + D * 4) + R * (I * 2 + H * 4 + D * 4 + D * 2 + 8)
+        w_out = (torch.randn(D, I, device=dev) * I ** -0.5).bfloat16()
+        b_out = torch.randn(D, device=dev); xres = torch.randn(R, D, device=dev); xmid = torch.empty(R, D, device=dev)
+        h2 = torch.empty(R, D, device=dev, dtype=torch.bfloat16); stats2 = torch.empty(R, 2, device=dev)
+        ln_w = torch.ones(D, device=dev); ln_b = torch.zeros(D, device=dev)
 
         def timed(fn):
             for _ in range(3):
@@ -592,15 +598,18 @@ def roofline(args, B, dev, peaks):
 
         for shape, (n_seq, N, inner) in (("spatial", (B * Cb, 64, 1)), ("spectral", (B * 64, Cb, 64))):
             ad = _lib.AttnDims(n_seq, N, inner, H, 64, float(args.dropout), 1234, 16, _lib.PREC_BF16, None)
-            fwd = lambda: _lib.check(lib.msst_attn_block_fwd(C.byref(ad), D, h.data_ptr(), w.data_ptr(), o.data_ptr(), lse.data_ptr(), st))
+            fwd = lambda: _lib.check(lib.msst_attn_block_out_fwd(C.byref(ad), D, h.data_ptr(), w.data_ptr(), o.data_ptr(), lse.data_ptr(), w_out.data_ptr(),
+                                                                 b_out.data_ptr(), xres.data_ptr(), xmid.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(),
+                                                                 h2.data_ptr(), stats2.data_ptr(), 17, st))
             bwd = lambda: _lib.check(lib.msst_attn_block_bwd(C.byref(ad), D, h.data_ptr(), w.data_ptr(), wt.data_ptr(), do.data_ptr(), lse.data_ptr(),
                                                              dqkv.data_ptr(), dh.data_ptr(), st))
             sec_f, sec_b = timed(fwd), timed(bwd)
-            fl_f = 2.0 * R * D * 3 * I + 2 * 2.0 * N * 64 * R * H
+            fl_f = 2.0 * R * D * 3 * I + 2 * 2.0 * N * 64 * R * H + 2.0 * R * I * D
             fl_b = 2 * 2.0 * R * D * 3 * I + 5 * 2.0 * N * 64 * R * H
             for tag, sec, byts, fl, kern in (("backward", sec_b, bwd_bytes, fl_b, "attn_block_bwd_kernel"), ("forward", sec_f, fwd_bytes, fl_f, "attn_block_fwd_kernel")):
                 hb, tc = byts / sec / 1e9 / hbm_peak, fl / sec / 1e12 / tc_peak
-                row = {"kernel": f"fused QKV projection + attention {tag} ({kern}, tcgen05/TMEM/TMA), {shape} stack shape",
+                what = "fused QKV projection + attention backward" if tag == "backward" else "fused QKV projection + attention + out-projection + residual + LN2 forward"
+                row = {"kernel": f"{what} ({kern}, tcgen05/TMEM/TMA), {shape} stack shape",
                        "bound": "hbm" if hb >= tc else "tensor", "achieved": byts / sec / 1e9 if hb >= tc else fl / sec / 1e12,
                        "peak": hbm_peak if hb >= tc else tc_peak, "unit": "GB/s" if hb >= tc else "TFLOP/s", "frac": max(hb, tc),
                        "hbm_frac": hb, "tensor_frac": tc, "traffic": _traffic(f"{kern}:{shape}", R), "algorithmic_bytes": byts,

@@ -25,10 +25,15 @@ if __name__ == "__main__":
     o = torch.empty(R, I, device="cuda", dtype=torch.bfloat16); lse = torch.empty(R, H, device="cuda")
     do = torch.randn(R, I, device="cuda").bfloat16(); dqkv = torch.empty(R, 3 * I, device="cuda", dtype=torch.bfloat16)
     dh = torch.empty(R, D, device="cuda"); dW = torch.zeros(3 * I, D, device="cuda")
+    w_out = (torch.randn(D, I, device="cuda") * I ** -0.5).bfloat16(); b_out = torch.randn(D, device="cuda")
+    xres = torch.randn(R, D, device="cuda"); xmid = torch.empty(R, D, device="cuda"); h2 = torch.empty(R, D, device="cuda", dtype=torch.bfloat16)
+    ln_w = torch.ones(D, device="cuda"); ln_b = torch.zeros(D, device="cuda"); stats2 = torch.empty(R, 2, device="cuda")
     fns = []
     for n_seq, N, inner in ((B * Cb, 64, 1), (B * 64, Cb, 64)):
         ad = _lib.AttnDims(n_seq, N, inner, H, 64, 0.1, 1234, 16, _lib.PREC_BF16, None)
-        fns.append(lambda ad=ad: _lib.check(lib.msst_attn_block_fwd(C.byref(ad), D, h.data_ptr(), w.data_ptr(), o.data_ptr(), lse.data_ptr(), st)))
+        fns.append(lambda ad=ad: _lib.check(lib.msst_attn_block_out_fwd(C.byref(ad), D, h.data_ptr(), w.data_ptr(), o.data_ptr(), lse.data_ptr(), w_out.data_ptr(),
+                                                                        b_out.data_ptr(), xres.data_ptr(), xmid.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(),
+                                                                        h2.data_ptr(), stats2.data_ptr(), 17, st)))
         fns.append(lambda ad=ad: _lib.check(lib.msst_attn_block_bwd(C.byref(ad), D, h.data_ptr(), w.data_ptr(), wt.data_ptr(), do.data_ptr(), lse.data_ptr(),
                                                                     dqkv.data_ptr(), dh.data_ptr(), st)))
     ld = _lib.LinearDims(R, 3 * I, D, 0, 0.0, 0, 0, _lib.PREC_BF16, None, 0)
