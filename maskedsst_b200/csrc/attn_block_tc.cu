@@ -297,8 +297,8 @@ __device__ __forceinline__ void store_tile(const AbParams& p, const CUtensorMap*
 // The staged bf16 O tile of every item is ALSO the K-major A operand of  Y (+)= O_h Wo[:, 64h .. 64h+63]^T  (M = 128, N = D), which
 // accumulates over the heads of the tile in TMEM (two accumulators of D columns, alternating with the tile); the head's Wo column
 // block travels through the weight ring as a fourth slot per item.  The tile epilogue (bias, dropout, residual, two-pass LayerNorm:
-// the arithmetic of gemm_tn_kernel<6> / mlp_block_fwd_kernel) belongs to FOUR EXTRA WARPS (20-23, thread = tile row = TMEM lane of
-// the M = 128 accumulator), not to the 512 softmax threads: folded into their loop (three variants were measured) it cost every item
+// the arithmetic of gemm_tn_kernel<6> / mlp_block_fwd_kernel) belongs to FOUR EXTRA WARPS (thread = tile row = TMEM lane of
+// the M = 128 accumulator; warps 19-22, warp % 4 = lane quarter), not to the 512 softmax threads: folded into their loop (three variants were measured) it cost every item
 // ~0.7 k clks of worse code on top of its own work.  It runs in NCH + 1 phases under the first items of the NEXT tile and moves its
 // data through the K (| V) tile of the hosting item, which is dead from the item's S (O) contraction to the conversion two items
 // later -- so no shared memory is added and nothing is accessed row-per-thread in global memory (one LSU wavefront per row):
@@ -307,12 +307,13 @@ __device__ __forceinline__ void store_tile(const AbParams& p, const CUtensorMap*
 //                            are parked in the Y accumulator's own TMEM columns (tcgen05.st), the row sum rides in a register
 //   phase NCH (item NCH):    O done (t_vfree) -> mean / rstd over the parked row (two-pass, thread-local) -> h2 into the K | V tiles
 //                            as SWIZZLE_64B chunks -> TMA store
-// The softmax threads only wait (kv_free) before the conversion that overwrites a buffer a phase used.  Registers: the kernel is
-// launched with 768 threads x 80 registers; the softmax warps raise themselves to 96 (setmaxnreg), all other warps drop to 48.
+// The softmax threads only wait (kv_free) before the conversion that overwrites a buffer a phase used.  The kernel runs 23 warps
+// (736 threads, 80 registers each: warp slots are granted four at a time, so 23 warps cost what 24 do); a setmaxnreg split (softmax
+// warps 96, the others 48) was measured and gave the same time -- ptxas kept the softmax loop at ~84 registers either way.
 // o [R, I] is still written (the Wo weight gradient of the backward reads it) but never re-read in the forward, and the separate
 // out-projection GEMM launch (gemm_tn_kernel<6>) is gone.
 // =========================================================================================================
-constexpr int AB_THREADS_OUT = 768;
+constexpr int AB_THREADS_OUT = 736;            // 16 softmax warps + producer, MMA issuer, store + 4 tile-epilogue warps (19-22: warp % 4 = TMEM lane quarter)
 // one thread: chunk c of the residual rows of `tile` -> dst ([128 rows][32 fp32] SWIZZLE_128B)
 __device__ __forceinline__ void tail_load_x(const AbParams& p, AbBars* bars, const CUtensorMap* tma_x, uint8_t* dst, int c, int64_t tile) {
     const AttnGeom& g = p.g;
@@ -366,10 +367,8 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
 
     const int64_t my_tiles = blockIdx.x < p.n_tiles ? (p.n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
     const int64_t n_items = my_tiles * H;
-    // OUT: register split between the warp groups (see the header); each group's code is dominated by its own setmaxnreg
     if (warp < 16) {
         // ===== 512 compute threads: thread = (TMEM lane L, column quarter cq) =====
-        if (OUT) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
         const int lq = warp & 3, cq = warp >> 2, lane = threadIdx.x & 31;
         const int L = lq * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(lq * 32) << 16;
@@ -491,8 +490,7 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
             if (++h == H) { h = 0; ++k; }
         }
     } else
-    if (warp >= 16 && warp < 20) {
-    if (OUT) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    if (warp >= 16 && warp < 19) {
     if (warp == 16) {
         // ===== TMA producer.  Ring order = the MMA issuer's consumption order: P(0), P(1), then per item: [Wo(it - 1)], P(it + 2); [Wo(last)] =====
         if (elect_one()) {
@@ -647,10 +645,9 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
                 for (int j = 0; j <= NCH; ++j) out_round(j, blockIdx.x + (my_tiles - 1) * gridDim.x, qkv_s + (size_t)(n_items & 1) * 3 * AB_T16 + AB_T16);
         }
     }
-    } else if (OUT && warp >= 20) {
+    } else if (OUT && warp >= 19) {
         // ===== tile-epilogue warps: thread = tile row T = TMEM lane T of the out-projection accumulator =====
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
-        const int lane = threadIdx.x & 31, tq = warp - 20;
+        const int lane = threadIdx.x & 31, tq = warp & 3;
         const int T = tq * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(tq * 32) << 16;
         const uint32_t sw128 = (uint32_t)(T & 7), sw64 = (uint32_t)((T >> 1) & 3);
@@ -689,7 +686,7 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
                 }
                 if (T == 0 && !last) AB_T(host, 13);
                 // (a different hosting item = the other buffer: the chunk load below overlaps the previous round's TMA store)
-                if (j < NCH && tq == 0 && lane == 0) {
+                if (j < NCH && warp == 19 && lane == 0) {
                     tail_load_x(p, bars, &tma_x, kv, j, ptile);
                     // pull what the next phase / the next tile's first phase will load into L2 meanwhile
                     if (j + 1 < NCH) tail_prefetch_x(p, &tma_x, j + 1, ptile);
