@@ -116,7 +116,7 @@ __device__ __forceinline__ uint32_t key_mask16(const AttnGeom& g, int m, int cq)
 struct alignas(8) AbBars {
     uint64_t h_full[2], h_empty[2], w_full[AB_MAXR], w_empty[AB_MAXR], do_full[2], do_empty[2];
     uint64_t pro_full, conv_done, s_full, sdp_read, p_full, o_full, a_ready, dh_full, dh_free, stg_full, stg_free, dhs_full, dhs_free;
-    uint64_t y_full, out_full, out_free, xin_full, t_kfree[2], t_vfree, kv_free[2];   // forward with the fused out-projection
+    uint64_t y_full[2], out_full, out_free, xin_full, t_kfree[2], t_vfree[2], kv_free[2];   // forward with the fused out-projection (pairs: one per tile / item parity)
     uint32_t tmem_base;
 };
 
@@ -254,9 +254,9 @@ __device__ __forceinline__ void ab_setup(AbBars* bars, int warp, uint8_t* z0, ui
         mbar_init(&bars->o_full, 1); mbar_init(&bars->a_ready, 16); mbar_init(&bars->dh_full, 1); mbar_init(&bars->dh_free, 16);
         mbar_init(&bars->stg_full, 16); mbar_init(&bars->stg_free, stg_free_count); mbar_init(&bars->sdp_read, 16);
         mbar_init(&bars->dhs_full, 16); mbar_init(&bars->dhs_free, 1);
-        mbar_init(&bars->y_full, 1);
+        mbar_init(&bars->y_full[0], 1); mbar_init(&bars->y_full[1], 1);
         mbar_init(&bars->out_full, 4); mbar_init(&bars->out_free, 1); mbar_init(&bars->xin_full, 1);
-        mbar_init(&bars->t_kfree[0], 1); mbar_init(&bars->t_kfree[1], 1); mbar_init(&bars->t_vfree, 1); mbar_init(&bars->kv_free[0], 1); mbar_init(&bars->kv_free[1], 1);
+        mbar_init(&bars->t_kfree[0], 1); mbar_init(&bars->t_kfree[1], 1); mbar_init(&bars->t_vfree[0], 1); mbar_init(&bars->t_vfree[1], 1); mbar_init(&bars->kv_free[0], 1); mbar_init(&bars->kv_free[1], 1);
         fence_barrier_init();
     }
     if (warp == 16) {
@@ -455,8 +455,10 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
             const float inv = l > 0.f ? 1.f / l : 0.f;
             if (cq == 0 && grow >= 0) p.lse_out[grow * H + h] = (sub + log2f(l)) * 0.6931471805599453f;
             // ---- Q, K, V of item it + 1 -> the other tile buffer (runs under the O MMAs of item it) ----
+            // the other buffer's Q tile staged O(it - 1): its store (and, OUT, the out-projection MMA) has read it.  Waited for at EVERY item, the
+            // last one included: it keeps stg_full in lockstep with the store warp -- a waiter two phases behind deadlocks on the parity test
+            if (it >= 1) mbar_wait(&bars->stg_free, (uint32_t)(it - 1) & 1);
             if (it + 1 < n_items) {
-                if (it >= 1) mbar_wait(&bars->stg_free, (uint32_t)(it - 1) & 1);   // that buffer's Q tile staged O(it - 1): its store (and, OUT, the out-projection MMA) has read it
                 if (OUT && hosted) {                              // ... and the epilogue phases its K | V tiles staged at item it - 1 have left
                     if (it & 1) { mbar_wait(&bars->kv_free[0], n_kvf0 & 1u); ++n_kvf0; }   // (one barrier per item parity: a completion can never run two ahead of this wait)
                     else { mbar_wait(&bars->kv_free[1], n_kvf1 & 1u); ++n_kvf1; }
@@ -566,7 +568,7 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
                 if (lead) {
                     umma_commit(&bars->w_empty[r.slot]);
                     umma_commit(&bars->stg_free);                 // second arrival (the first is the O store's): the Q tile may be overwritten
-                    if (yh == H - 1) umma_commit(&bars->y_full);
+                    if (yh == H - 1) umma_commit(&bars->y_full[ycol != COL_Y]);   // (one barrier per tile parity, like the accumulator)
                 }
                 r.next();
                 if (++yh == H) { yh = 0; ycol ^= (COL_Y ^ (COL_Y + Y_COLS)); }
@@ -592,7 +594,7 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
                 if (OUT) {                                        // the item hosts the LayerNorm phase: its V tile is free as well once O is done
                     int lo, hi;
                     tail_schedule(h, H, NCH, lo, hi);
-                    if (lead && k > 0 && lo <= hi && hi == NCH) umma_commit(&bars->t_vfree);
+                    if (lead && k > 0 && lo <= hi && hi == NCH) umma_commit(&bars->t_vfree[it & 1]);
                     if (++h == H) { h = 0; ++k; }
                 }
                 if (it + 1 < n_items) {
@@ -603,7 +605,7 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
             }
             if (OUT) {
                 issue_y(n_items - 1);
-                if (lead) { umma_commit(&bars->t_kfree[n_items & 1]); umma_commit(&bars->t_vfree); }   // the CTA's last tile: its phases run after the last item
+                if (lead) { umma_commit(&bars->t_kfree[n_items & 1]); umma_commit(&bars->t_vfree[n_items & 1]); }   // the CTA's last tile: its phases run after the last item
             }
         }
     } else if (warp == 18) {
@@ -651,7 +653,7 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
         const int T = tq * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(tq * 32) << 16;
         const uint32_t sw128 = (uint32_t)(T & 7), sw64 = (uint32_t)((T >> 1) & 3);
-        uint32_t n_in = 0, n_out = 0, n_kf0 = 0, n_kf1 = 0, n_vf = 0;   // completions consumed so far per barrier
+        uint32_t n_in = 0, n_out = 0, n_kf0 = 0, n_kf1 = 0, n_vf0 = 0, n_vf1 = 0;   // completions consumed so far per barrier
         // b_out | ln_w | ln_b in shared memory: every thread needs all D of each, and a global load per use misses the (tiny) L1 -- ~600 clks apiece,
         // which made a chunk phase take 6 k clks
         float* cst = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + ((sizeof(AbBars) + 15) & ~size_t(15)));
@@ -695,7 +697,7 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
                 if (!same_host && n_out > 0) mbar_wait(&bars->out_free, (n_out - 1u) & 1u);   // (completions are observed in order)
                 if (j < NCH) {
                     const int c = j;
-                    if (j == 0) mbar_wait(&bars->y_full, (uint32_t)kk & 1u);
+                    if (j == 0) mbar_wait(&bars->y_full[kk & 1], (uint32_t)(kk >> 1) & 1u);
                     mbar_wait(&bars->xin_full, n_in & 1u);
                     ++n_in;
                     if (T == 0 && !last) AB_T(host, 14);
@@ -728,8 +730,10 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
                     }
                     tmem_st_wait();
                 } else {
-                    mbar_wait(&bars->t_vfree, n_vf & 1u);         // O of the hosting item is done: the V tile is dead as well
-                    ++n_vf;
+                    // O of the hosting item is done: the V tile is dead as well.  (Barrier pairs by tile / item parity throughout: with few heads
+                    //  the next completion of a single barrier can overtake this wait by two phases, and the parity test then never returns)
+                    if (host & 1) { mbar_wait(&bars->t_vfree[1], n_vf1 & 1u); ++n_vf1; }
+                    else { mbar_wait(&bars->t_vfree[0], n_vf0 & 1u); ++n_vf0; }
                     tc_fence_after();
                     const float mean = sum / D;
                     float sq = 0.f;

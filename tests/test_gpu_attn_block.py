@@ -180,3 +180,36 @@ def test_attn_block_out_matches_unfused_gemm_with_dropout(n_seq, N, inner, H):
     assert rel_l2(h2, want_h2) < 4e-3
     out2, _, xmid2, h22, _ = _call_out_fwd(h, w, w_out, b_out, x, ln_w, ln_b, n_seq, N, inner, H, drop_p=0.25, seed=77, site=5, site_out=9)
     assert torch.equal(xmid, xmid2) and torch.equal(h2, h22)
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("n_seq,N,inner,H,D", [
+    (900, 64, 1, 1, 96),      # one head: every item ends a tile, all epilogue phases share one hosting item
+    (900, 64, 1, 2, 96),
+    (900, 64, 1, 3, 64),
+    (1500, 64, 1, 4, 96),     # H - 1 = NCH: the LayerNorm phase lands on the tile's last head
+    (2048, 20, 64, 2, 96),    # strided sequences (4-D boxes), few heads
+    (4736, 64, 1, 8, 32),     # 16 tiles per CTA, one 32-column chunk
+])
+def test_attn_block_out_many_tiles_per_cta(n_seq, N, inner, H, D):
+    """Several tiles per CTA with few heads: the epilogue phases of tile k run under the items of tile k + 1 and share hosting items;
+    checks the hand-off protocol (a protocol error shows up as a hang -> timeout, or as wrong rows) against the unfused GEMM."""
+    torch.manual_seed(5)
+    I, R = H * 64, n_seq * N
+    h = torch.randn(R, D).bfloat16().to(DEV)
+    w = (torch.randn(3 * I, D) * D ** -0.5).bfloat16().to(DEV)
+    w_out, b_out, x, ln_w, ln_b = _tail_inputs(R, D, I)
+    for rep in range(3):
+        out, lse, xmid, h2, stats = _call_out_fwd(h, w, w_out, b_out, x, ln_w, ln_b, n_seq, N, inner, H, drop_p=0.1, seed=11 + rep, site=3, site_out=4)
+    o_ref, lse_ref, _ = _call_fwd(h, w, n_seq, N, inner, H, drop_p=0.1, seed=13, site=3)
+    assert torch.equal(out, o_ref) and torch.equal(lse, lse_ref)
+    y = torch.empty(R, D, device=DEV)
+    d = _lib.LinearDims(R, D, I, 0, 0.1, 13, 4, PREC_BF16, None, 1)
+    st = torch.cuda.current_stream().cuda_stream
+    check(_lib.lib().msst_linear_fwd(C.byref(d), out.data_ptr(), w_out.data_ptr(), b_out.data_ptr(), x.data_ptr(), y.data_ptr(), None, st))
+    torch.cuda.synchronize()
+    assert rel_l2(xmid, y) < 2e-6
+    want_h2 = torch.nn.functional.layer_norm(xmid.double(), (D,), ln_w.double(), ln_b.double(), 1e-5)
+    assert rel_l2(h2, want_h2) < 4e-3
+    mean = xmid.double().mean(-1)
+    assert rel_l2(stats[:, 0], mean) < 1e-5
