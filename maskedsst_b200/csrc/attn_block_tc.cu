@@ -432,18 +432,23 @@ attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tma_h, const __grid_co
             const float sub = mx == -INFINITY ? 0.f : mx * sl2;
             float l = 0.f;
             uint32_t pk[8];
+            // (the dropout test is hoisted by hand: in the larger OUT kernel the compiler no longer unswitches the unrolled loop on it)
+            auto exp_row = [&](auto drop_tag) {
+                constexpr bool DROP = decltype(drop_tag)::value;
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-                float p0 = ex2_approx(fmaf(sc[2 * jj], sl2, -sub)), p1 = ex2_approx(fmaf(sc[2 * jj + 1], sl2, -sub));
-                l += p0 + p1;
-                if (p.drop.on()) {
-                    uint32_t x = (hash_lo + (uint32_t)jj) * 0x9E3779B1u ^ hash_hi;
-                    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
-                    p0 *= (x & 0xFFFFu) >= t16 ? p.drop.scale : 0.f;
-                    p1 *= (x >> 16) >= t16 ? p.drop.scale : 0.f;
+                for (int jj = 0; jj < 8; ++jj) {
+                    float p0 = ex2_approx(fmaf(sc[2 * jj], sl2, -sub)), p1 = ex2_approx(fmaf(sc[2 * jj + 1], sl2, -sub));
+                    l += p0 + p1;
+                    if (DROP) {
+                        uint32_t x = (hash_lo + (uint32_t)jj) * 0x9E3779B1u ^ hash_hi;
+                        x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+                        p0 *= (x & 0xFFFFu) >= t16 ? p.drop.scale : 0.f;
+                        p1 *= (x >> 16) >= t16 ? p.drop.scale : 0.f;
+                    }
+                    pk[jj] = pack_bf(p0, p1);
                 }
-                pk[jj] = pack_bf(p0, p1);
-            }
+            };
+            if (p.drop.on()) exp_row(std::true_type{}); else exp_row(std::false_type{});
             xsum[cq * 128 + L] = l;
             store_row16_packed(p_s + blk * AB_BLK, m, cq, pk);      // its last readers (the O MMAs of item it - 1) completed before S(it) did
             fence_proxy_async();
